@@ -1,0 +1,479 @@
+"""arrayfire_b200 -- host-side mirror of ArrayFire's ``af::`` interface for the reduce / scan /
+scan_by_key / where path, bound over the C-ABI of libafb200.so (include/afb200.h).
+
+This module is plumbing only: every function is a thin ctypes call into the ``af_*`` symbols the
+reference's C++ wrapper binds (/root/reference/src/api/cpp/reduce.cpp:17-346, scan.cpp:15-33,
+where.cpp:16-24, array.cpp), with the same names, argument meaning, defaults (``dim=-1`` picks the first
+non-singleton dimension, src/api/cpp/common.hpp:27-38) and error behaviour (an ``af_err`` becomes an
+``AfError`` carrying the thread-local message of af_get_last_error, like af::exception).
+
+There is NO fallback: if libafb200.so is missing or no CUDA device is usable, import / first use fails.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+__all__ = [
+    "Array", "AfError", "lib", "f32", "c32", "f64", "c64", "b8", "s32", "u32", "u8", "s64", "u64", "s16", "u16", "f16",
+    "s8", "AF_BINARY_ADD", "AF_BINARY_MUL", "AF_BINARY_MIN", "AF_BINARY_MAX", "sum", "product", "min", "max", "count",
+    "all_true", "any_true", "sum_all", "product_all", "min_all", "max_all", "count_all", "all_true_all", "any_true_all",
+    "imin", "imax", "imin_all", "imax_all", "accum", "scan", "scan_by_key", "where", "sync", "constant", "info_string",
+    "get_stream", "launch_count", "device_gc", "seq", "span",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libafb200.so")
+
+# af_dtype, include/af/defines.h:210-233
+f32, c32, f64, c64, b8, s32, u32, u8, s64, u64, s16, u16, f16, s8 = range(14)
+AF_BINARY_ADD, AF_BINARY_MUL, AF_BINARY_MIN, AF_BINARY_MAX = range(4)
+_NP = {f32: np.float32, c32: np.complex64, f64: np.float64, c64: np.complex128, b8: np.int8, s32: np.int32,
+       u32: np.uint32, u8: np.uint8, s64: np.int64, u64: np.uint64, s16: np.int16, u16: np.uint16, f16: np.float16,
+       s8: np.int8}
+_SIZE = {k: np.dtype(v).itemsize for k, v in _NP.items()}
+DTYPE_NAMES = ["f32", "c32", "f64", "c64", "b8", "s32", "u32", "u8", "s64", "u64", "s16", "u16", "f16", "s8"]
+
+
+class AfError(RuntimeError):
+    """af::exception: carries the af_err code and the library's message."""
+
+    def __init__(self, code, message):
+        super().__init__("af_err %d: %s" % (code, message))
+        self.code = code
+        self.message = message
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+    return ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+
+
+lib = _load()
+lib.af_err_to_string.restype = ctypes.c_char_p
+lib.af_get_last_error.restype = None
+_vp = ctypes.c_void_p
+
+
+class af_seq(ctypes.Structure):
+    _fields_ = [("begin", ctypes.c_double), ("end", ctypes.c_double), ("step", ctypes.c_double)]
+
+
+def seq(begin, end, step=1.0):
+    """af::seq(begin, end, step) -- end is inclusive (include/af/seq.h:20-30)."""
+    return af_seq(float(begin), float(end), float(step))
+
+
+span = af_seq(1.0, 1.0, 0.0)  # af_span
+
+
+def _check(err):
+    if err != 0:
+        msg = ctypes.c_char_p()
+        n = ctypes.c_longlong()
+        lib.af_get_last_error(ctypes.byref(msg), ctypes.byref(n))
+        text = msg.value.decode(errors="replace") if msg.value else lib.af_err_to_string(err).decode()
+        if msg.value:
+            lib.af_free_host(msg)
+        raise AfError(err, text)
+
+
+def _dims_arr(dims):
+    return (ctypes.c_longlong * len(dims))(*[int(d) for d in dims])
+
+
+def _code_of(np_dtype, dtype=None):
+    if dtype is not None:
+        return dtype
+    if np_dtype == np.bool_:
+        return b8
+    for code in (f32, c32, f64, c64, s32, u32, u8, s64, u64, s16, u16, f16, s8):
+        if np_dtype == _NP[code]:
+            return code
+    raise TypeError("unsupported dtype %s" % np_dtype)
+
+
+class Array:
+    """Owner of one ``af_array`` handle (af::array, include/af/array.h:37-38)."""
+
+    def __init__(self, handle, keepalive=None):
+        self.handle = _vp(handle) if not isinstance(handle, _vp) else handle
+        self._keepalive = keepalive
+
+    # ---- construction -------------------------------------------------------------------------
+    @staticmethod
+    def from_numpy(a, dtype=None):
+        """af::array(dims, host_ptr): copies a column-major host array to the device (af_create_array)."""
+        a = np.asarray(a)
+        code = _code_of(a.dtype, dtype)
+        if a.ndim == 0:
+            a = a.reshape(1)
+        if a.ndim > 4:
+            raise ValueError("at most 4 dimensions")
+        host = np.asfortranarray(a.view(np.int8) if a.dtype == np.bool_ else a)
+        h = _vp()
+        if host.size == 0:
+            _check(lib.af_create_handle(ctypes.byref(h), host.ndim, _dims_arr(host.shape), code))
+        else:
+            _check(lib.af_create_array(ctypes.byref(h), _vp(host.ctypes.data), host.ndim, _dims_arr(host.shape), code))
+        return Array(h)
+
+    @staticmethod
+    def from_device_ptr(ptr, dims, dtype, keepalive=None):
+        """af_device_array + af_lock_array: wraps foreign device memory (e.g. a torch tensor) WITHOUT copying
+        and without taking ownership (the documented recipe for memory the library must not free)."""
+        h = _vp()
+        _check(lib.af_device_array(ctypes.byref(h), _vp(ptr), len(dims), _dims_arr(dims), dtype))
+        _check(lib.af_lock_array(h))
+        return Array(h, keepalive)
+
+    @staticmethod
+    def from_torch(t, dtype=None):
+        """Zero-copy view of a contiguous CUDA torch tensor; dims are reversed so that torch's last
+        (fastest) axis becomes dim 0, ArrayFire's fastest axis."""
+        import torch
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError("need a contiguous CUDA tensor")
+        table = {torch.float32: f32, torch.float64: f64, torch.int32: s32, torch.int64: s64, torch.uint8: u8,
+                 torch.int8: s8, torch.int16: s16, torch.float16: f16, torch.bool: b8, torch.complex64: c32,
+                 torch.complex128: c64}
+        for name, code in (("uint32", u32), ("uint64", u64), ("uint16", u16)):
+            if hasattr(torch, name):
+                table[getattr(torch, name)] = code
+        code = dtype if dtype is not None else table[t.dtype]
+        dims = list(reversed(t.shape)) or [1]
+        return Array.from_device_ptr(t.data_ptr(), dims, code, keepalive=t)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h is not None and h.value and lib is not None:
+            try:
+                lib.af_release_array(h)
+            except Exception:
+                pass
+
+    # ---- queries --------------------------------------------------------------------------------
+    @property
+    def dims(self):
+        d = [ctypes.c_longlong() for _ in range(4)]
+        _check(lib.af_get_dims(*[ctypes.byref(x) for x in d], self.handle))
+        return tuple(x.value for x in d)
+
+    @property
+    def strides(self):
+        d = [ctypes.c_longlong() for _ in range(4)]
+        _check(lib.af_get_strides(*[ctypes.byref(x) for x in d], self.handle))
+        return tuple(x.value for x in d)
+
+    @property
+    def offset(self):
+        o = ctypes.c_longlong()
+        _check(lib.af_get_offset(ctypes.byref(o), self.handle))
+        return o.value
+
+    @property
+    def dtype(self):
+        t = ctypes.c_int()
+        _check(lib.af_get_type(ctypes.byref(t), self.handle))
+        return t.value
+
+    @property
+    def elements(self):
+        n = ctypes.c_longlong()
+        _check(lib.af_get_elements(ctypes.byref(n), self.handle))
+        return n.value
+
+    @property
+    def numdims(self):
+        n = ctypes.c_uint()
+        _check(lib.af_get_numdims(ctypes.byref(n), self.handle))
+        return n.value
+
+    def is_linear(self):
+        r = ctypes.c_bool()
+        _check(lib.af_is_linear(ctypes.byref(r), self.handle))
+        return r.value
+
+    def device_ptr(self):
+        """af_get_device_ptr (locks the buffer: the caller now shares ownership)."""
+        p = _vp()
+        _check(lib.af_get_device_ptr(ctypes.byref(p), self.handle))
+        return p.value
+
+    def unlock(self):
+        _check(lib.af_unlock_array(self.handle))
+
+    def to_numpy(self):
+        """array::host(): a column-major numpy array of shape dims (synchronises)."""
+        dims, code = self.dims, self.dtype
+        out = np.zeros(dims, dtype=_NP[code], order="F")
+        if out.size:
+            _check(lib.af_get_data_ptr(_vp(out.ctypes.data), self.handle))
+        return out
+
+    def scalar(self):
+        out = np.zeros(1, dtype=_NP[self.dtype])
+        _check(lib.af_get_scalar(_vp(out.ctypes.data), self.handle))
+        return out[0]
+
+    def retain(self):
+        h = _vp()
+        _check(lib.af_retain_array(ctypes.byref(h), self.handle))
+        return Array(h, self._keepalive)
+
+    def copy(self):
+        h = _vp()
+        _check(lib.af_copy_array(ctypes.byref(h), self.handle))
+        return Array(h)
+
+    def index(self, *seqs):
+        """a(seq, seq, ...): a view sharing the parent's buffer (af_index, src/api/c/index.cpp:84-124)."""
+        arr = (af_seq * len(seqs))(*seqs)
+        h = _vp()
+        _check(lib.af_index(ctypes.byref(h), self.handle, len(seqs), arr))
+        return Array(h, self._keepalive)
+
+
+# ---- helpers -------------------------------------------------------------------------------------
+def _fnsd(a, dim):
+    """getFNSD, src/api/cpp/common.hpp:27-38"""
+    if dim >= 0:
+        return dim
+    d = a.dims
+    for i in range(4):
+        if d[i] > 1:
+            return i
+    return 0
+
+
+def _dimwise(fn, a, dim, *extra):
+    h = _vp()
+    _check(fn(ctypes.byref(h), a.handle, ctypes.c_int(_fnsd(a, dim)), *extra))
+    return Array(h)
+
+
+def _all(fn, a, *extra):
+    re, im = ctypes.c_double(), ctypes.c_double()
+    _check(fn(ctypes.byref(re), ctypes.byref(im), a.handle, *extra))
+    if a.dtype in (c32, c64):
+        return complex(re.value, im.value)
+    return re.value
+
+
+# ---- reductions along a dimension (af::sum & co., src/api/cpp/reduce.cpp:17-110) --------------
+def sum(a, dim=-1, nanval=None):
+    if nanval is None:
+        return _dimwise(lib.af_sum, a, dim)
+    h = _vp()  # the nanval overload passes dim through unmodified (reduce.cpp:23-27)
+    _check(lib.af_sum_nan(ctypes.byref(h), a.handle, ctypes.c_int(dim), ctypes.c_double(nanval)))
+    return Array(h)
+
+
+def product(a, dim=-1, nanval=None):
+    if nanval is None:
+        return _dimwise(lib.af_product, a, dim)
+    h = _vp()
+    _check(lib.af_product_nan(ctypes.byref(h), a.handle, ctypes.c_int(dim), ctypes.c_double(nanval)))
+    return Array(h)
+
+
+def min(a, dim=-1):
+    return _dimwise(lib.af_min, a, dim)
+
+
+def max(a, dim=-1):
+    return _dimwise(lib.af_max, a, dim)
+
+
+def count(a, dim=-1):
+    return _dimwise(lib.af_count, a, dim)
+
+
+def all_true(a, dim=-1):
+    return _dimwise(lib.af_all_true, a, dim)
+
+
+def any_true(a, dim=-1):
+    return _dimwise(lib.af_any_true, a, dim)
+
+
+# ---- whole-array reductions (af::sum<T>(a) & co., reduce.cpp:199-346) -----------------------------
+def sum_all(a, nanval=None):
+    if nanval is None:
+        return _all(lib.af_sum_all, a)
+    return _all(lib.af_sum_nan_all, a, ctypes.c_double(nanval))
+
+
+def product_all(a, nanval=None):
+    if nanval is None:
+        return _all(lib.af_product_all, a)
+    return _all(lib.af_product_nan_all, a, ctypes.c_double(nanval))
+
+
+def min_all(a):
+    return _all(lib.af_min_all, a)
+
+
+def max_all(a):
+    return _all(lib.af_max_all, a)
+
+
+def count_all(a):
+    return _all(lib.af_count_all, a)
+
+
+def all_true_all(a):
+    return _all(lib.af_all_true_all, a)
+
+
+def any_true_all(a):
+    return _all(lib.af_any_true_all, a)
+
+
+def _all_array(fn, a, *extra):
+    h = _vp()
+    _check(fn(ctypes.byref(h), a.handle, *extra))
+    return Array(h)
+
+
+def sum_all_array(a, nanval=None):
+    if nanval is None:
+        return _all_array(lib.af_sum_all_array, a)
+    return _all_array(lib.af_sum_nan_all_array, a, ctypes.c_double(nanval))
+
+
+def product_all_array(a, nanval=None):
+    if nanval is None:
+        return _all_array(lib.af_product_all_array, a)
+    return _all_array(lib.af_product_nan_all_array, a, ctypes.c_double(nanval))
+
+
+def min_all_array(a):
+    return _all_array(lib.af_min_all_array, a)
+
+
+def max_all_array(a):
+    return _all_array(lib.af_max_all_array, a)
+
+
+def count_all_array(a):
+    return _all_array(lib.af_count_all_array, a)
+
+
+def all_true_all_array(a):
+    return _all_array(lib.af_all_true_all_array, a)
+
+
+def any_true_all_array(a):
+    return _all_array(lib.af_any_true_all_array, a)
+
+
+# ---- index-returning reductions (af::min/max(val, idx, in, dim), reduce.cpp:167-197) --------------
+def _ireduce(fn, a, dim):
+    v, i = _vp(), _vp()
+    _check(fn(ctypes.byref(v), ctypes.byref(i), a.handle, ctypes.c_int(_fnsd(a, dim))))
+    return Array(v), Array(i)
+
+
+def imin(a, dim=-1):
+    return _ireduce(lib.af_imin, a, dim)
+
+
+def imax(a, dim=-1):
+    return _ireduce(lib.af_imax, a, dim)
+
+
+def _ireduce_all(fn, a):
+    re, im, idx = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint()
+    _check(fn(ctypes.byref(re), ctypes.byref(im), ctypes.byref(idx), a.handle))
+    val = complex(re.value, im.value) if a.dtype in (c32, c64) else re.value
+    return val, idx.value
+
+
+def imin_all(a):
+    return _ireduce_all(lib.af_imin_all, a)
+
+
+def imax_all(a):
+    return _ireduce_all(lib.af_imax_all, a)
+
+
+# ---- scans (af::accum / scan / scanByKey default dim = 0, src/api/cpp/scan.cpp:15-33) --------------
+def accum(a, dim=0):
+    h = _vp()
+    _check(lib.af_accum(ctypes.byref(h), a.handle, ctypes.c_int(dim)))
+    return Array(h)
+
+
+def scan(a, dim=0, op=AF_BINARY_ADD, inclusive_scan=True):
+    h = _vp()
+    _check(lib.af_scan(ctypes.byref(h), a.handle, ctypes.c_int(dim), ctypes.c_int(op), ctypes.c_bool(inclusive_scan)))
+    return Array(h)
+
+
+def scan_by_key(key, a, dim=0, op=AF_BINARY_ADD, inclusive_scan=True):
+    h = _vp()
+    _check(lib.af_scan_by_key(ctypes.byref(h), key.handle, a.handle, ctypes.c_int(dim), ctypes.c_int(op),
+                              ctypes.c_bool(inclusive_scan)))
+    return Array(h)
+
+
+def where(a):
+    h = _vp()
+    _check(lib.af_where(ctypes.byref(h), a.handle))
+    return Array(h)
+
+
+# ---- device ------------------------------------------------------------------------------------------
+def sync(device=-1):
+    _check(lib.af_sync(ctypes.c_int(device)))
+
+
+def set_device(device):
+    _check(lib.af_set_device(ctypes.c_int(device)))
+
+
+def get_device():
+    d = ctypes.c_int()
+    _check(lib.af_get_device(ctypes.byref(d)))
+    return d.value
+
+
+def device_count():
+    n = ctypes.c_int()
+    _check(lib.af_get_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def constant(val, dims, dtype=f32):
+    h = _vp()
+    _check(lib.af_constant(ctypes.byref(h), ctypes.c_double(val), len(dims), _dims_arr(dims), dtype))
+    return Array(h)
+
+
+def info_string():
+    s = ctypes.c_char_p()
+    _check(lib.af_info_string(ctypes.byref(s), ctypes.c_bool(False)))
+    text = s.value.decode()
+    lib.af_free_host(s)
+    return text
+
+
+def get_stream(device=None):
+    """afcu_get_stream: the cudaStream_t every op of `device` is enqueued on (as an int)."""
+    s = _vp()
+    _check(lib.afcu_get_stream(ctypes.byref(s), ctypes.c_int(get_device() if device is None else device)))
+    return s.value or 0
+
+
+def launch_count(reset=False):
+    n = ctypes.c_ulonglong()
+    _check(lib.afx_launch_count(ctypes.byref(n), ctypes.c_bool(reset)))
+    return n.value
+
+
+def device_gc():
+    _check(lib.af_device_gc())

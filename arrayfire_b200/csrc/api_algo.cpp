@@ -1,0 +1,533 @@
+// api_algo.cpp -- the hot-path C entry points: af_sum ... af_where and the afx_* shard helpers.
+//
+// Argument checks, early-outs, dtype promotion and error codes restate the reference's C-API layer:
+//   /root/reference/src/api/c/reduce.cpp:82-121 (reduce_type), 190-228 (reduce_common), 305-378 (reduce_promote),
+//       571-860 (whole-array forms), 918-1000 (ireduce), 1080-1168 (ireduce_all, *_nan_all)
+//   /root/reference/src/api/c/scan.cpp:118-283, where.cpp:34-65
+// Everything below the dispatch is this library's own CUDA path (kernels/*.cu); there is NO CPU fallback:
+// with no usable device every entry point fails with AF_ERR_DRIVER.
+#include <cstdlib>
+
+#include "common.hpp"
+
+using namespace afb;
+
+namespace afb {
+Array *make_dense_copy(const Array &a);
+}
+
+namespace {
+
+struct OpLock {
+    std::lock_guard<std::mutex> g;
+    explicit OpLock(int device) : g(op_mutex(device)) {}
+};
+
+struct Holder {  // deletes a half-built result on exceptions
+    Array *a = nullptr;
+    ~Holder() { delete a; }
+    Array *release() { Array *r = a; a = nullptr; return r; }
+};
+
+// promotion of af_sum / af_product (reduce.cpp:322-371)
+bool sum_promote(af_dtype ti, Op op, Op *eff, af_dtype *to) {
+    *eff = op;
+    switch (ti) {
+        case f32: case f64: case c32: case c64: case u32: case s32: case u64: case s64: *to = ti; return true;
+        case u16: case u8: *to = u32; return true;
+        case s16: case s8: *to = s32; return true;
+        case f16: *to = f32; return true;
+        case b8:
+            if (op == OP_MUL) { *eff = OP_AND; *to = b8; }
+            else { *eff = OP_NOTZERO; *to = u32; }
+            return true;
+    }
+    return false;
+}
+
+enum Family { FAM_PROMOTE, FAM_COMMON, FAM_TYPE };
+
+void resolve(Family fam, Op op, af_dtype ti, Op *eff, af_dtype *to) {
+    *eff = op;
+    switch (fam) {
+        case FAM_PROMOTE:
+            if (!sum_promote(ti, op, eff, to)) AFB_TYPE_ERROR(1, ti);
+            break;
+        case FAM_COMMON: *to = ti; break;
+        case FAM_TYPE: *to = (op == OP_NOTZERO) ? u32 : b8; break;
+    }
+}
+
+// ---- along a dimension -------------------------------------------------------------------------
+af_err reduce_dimwise(af_array *out, const af_array in_h, int dim, Family fam, Op op, bool change_nan, double nanval) {
+    AFB_API_BEGIN
+    AFB_ARG(2, dim >= 0);
+    AFB_ARG(2, dim < 4);
+    AFB_ARG(0, out != nullptr);
+    Array *in = from_handle(in_h);
+    if (dim >= in->ndims()) {  // also covers empty inputs; no promotion (reduce.cpp:314-317)
+        *out = retain(*in);
+        return AF_SUCCESS;
+    }
+    check_same_device(*in);
+    Op eff;
+    af_dtype to;
+    resolve(fam, op, in->info.type, &eff, &to);
+    dim_t od[4] = {in->info.dims[0], in->info.dims[1], in->info.dims[2], in->info.dims[3]};
+    od[dim] = 1;
+    Holder res;
+    res.a = new_array(to, od);
+    {
+        OpLock lk(in->device());
+        LaunchCtx c = ctx_for_active_device();
+        if (!launch_reduce(c, eff, in->info.type, to, view_of(*in), dim, change_nan, nanval, res.a->data()))
+            AFB_TYPE_ERROR(1, in->info.type);
+    }
+    *out = res.release();
+    AFB_API_END
+}
+
+// ---- whole array ---------------------------------------------------------------------------------
+// Runs the reduction into `dst` (device, one element of *to).  Non-linear views with short columns are
+// materialised first so the flattening kernel streams long spans.
+void reduce_all_into(const Array &in, Op eff, af_dtype to, bool change_nan, double nanval, void *dst) {
+    const Array *src = &in;
+    Holder tmp;
+    if (!in.is_linear() && in.info.dims[0] < 4096) {
+        tmp.a = make_dense_copy(in);
+        src = tmp.a;
+    }
+    OpLock lk(in.device());
+    LaunchCtx c = ctx_for_active_device();
+    if (!launch_reduce_all(c, eff, in.info.type, to, view_of(*src), change_nan, nanval, dst))
+        AFB_TYPE_ERROR(1, in.info.type);
+}
+
+double identity_of(Op op) { return (op == OP_MUL || op == OP_AND) ? 1.0 : 0.0; }
+
+void read_scalar(af_dtype t, const void *dev, cudaStream_t s, double *real, double *imag) {
+    alignas(16) unsigned char raw[16];
+    AFB_CUDA(cudaMemcpyAsync(raw, dev, dtype_size(t), cudaMemcpyDeviceToHost, s));
+    AFB_CUDA(cudaStreamSynchronize(s));
+    switch (t) {
+        case f32: *real = *(float *)raw; break;
+        case f64: *real = *(double *)raw; break;
+        case c32: *real = ((float *)raw)[0]; if (imag) *imag = ((float *)raw)[1]; break;
+        case c64: *real = ((double *)raw)[0]; if (imag) *imag = ((double *)raw)[1]; break;
+        case s32: *real = *(int *)raw; break;
+        case u32: *real = *(unsigned *)raw; break;
+        case s64: *real = (double)*(long long *)raw; break;
+        case u64: *real = (double)*(unsigned long long *)raw; break;
+        case s16: *real = *(short *)raw; break;
+        case u16: *real = *(unsigned short *)raw; break;
+        case s8: case b8: *real = *(signed char *)raw; break;
+        case u8: *real = *(unsigned char *)raw; break;
+        case f16: {
+            // IEEE binary16 -> double
+            unsigned short h = *(unsigned short *)raw;
+            int sign = h >> 15, e = (h >> 10) & 31, m = h & 1023;
+            double v;
+            if (e == 0) v = std::ldexp((double)m, -24);
+            else if (e == 31) v = m ? NAN : INFINITY;
+            else v = std::ldexp((double)(m | 1024), e - 25);
+            *real = sign ? -v : v;
+        } break;
+    }
+}
+
+af_err reduce_all_scalar(double *real, double *imag, const af_array in_h, Family fam, Op op, bool change_nan,
+                         double nanval, bool need_ndims) {
+    AFB_API_BEGIN
+    Array *in = from_handle(in_h);
+    if (need_ndims) AFB_ARG(2, in->ndims() > 0);  // reduce.cpp:646
+    AFB_ARG(0, real != nullptr);
+    *real = 0;
+    if (imag) *imag = 0;
+    Op eff;
+    af_dtype to;
+    resolve(fam, op, in->info.type, &eff, &to);
+    const bool cplx = (in->info.type == c32 || in->info.type == c64);
+    if (cplx && fam != FAM_TYPE) AFB_ARG(1, imag != nullptr);
+    if (cplx && fam == FAM_PROMOTE) change_nan = false;  // the scalar API drops nanval for complex (reduce.cpp:762-773)
+    if (in->elements() == 0) {
+        *real = identity_of(eff);
+        return AF_SUCCESS;
+    }
+    check_same_device(*in);
+    Holder res;
+    dim_t one[4] = {1, 1, 1, 1};
+    res.a = new_array(to, one);
+    reduce_all_into(*in, eff, to, change_nan, nanval, res.a->data());
+    read_scalar(to, res.a->data(), stream_of(in->device()), real, imag);
+    AFB_API_END
+}
+
+af_err reduce_all_array(af_array *out, const af_array in_h, Family fam, Op op, bool change_nan, double nanval,
+                        bool need_ndims) {
+    AFB_API_BEGIN
+    AFB_ARG(0, out != nullptr);
+    Array *in = from_handle(in_h);
+    if (need_ndims) AFB_ARG(2, in->ndims() > 0);
+    Op eff;
+    af_dtype to;
+    resolve(fam, op, in->info.type, &eff, &to);
+    check_same_device(*in);
+    Holder res;
+    dim_t one[4] = {1, 1, 1, 1};
+    res.a = new_array(to, one);
+    if (in->elements() == 0) {
+        LaunchCtx c = ctx_for_active_device();
+        launch_fill(c, to, res.a->data(), 1, identity_of(eff), 0.0);
+    } else {
+        reduce_all_into(*in, eff, to, change_nan, nanval, res.a->data());
+    }
+    *out = res.release();
+    AFB_API_END
+}
+
+// ---- ireduce -------------------------------------------------------------------------------------
+af_err ireduce_dimwise(af_array *val, af_array *idx, const af_array in_h, int dim, Op op) {
+    AFB_API_BEGIN
+    AFB_ARG(3, dim >= 0);
+    AFB_ARG(3, dim < 4);
+    AFB_ARG(0, val != nullptr);
+    AFB_ARG(1, idx != nullptr);
+    Array *in = from_handle(in_h);
+    AFB_ARG(2, in->ndims() > 0);
+    check_same_device(*in);
+    if (dim >= in->ndims()) {  // values = input, indices = 0 (reduce.cpp:959-963)
+        Holder loc;
+        loc.a = new_array(u32, in->info.dims);
+        LaunchCtx c = ctx_for_active_device();
+        launch_fill(c, u32, loc.a->data(), loc.a->elements(), 0.0, 0.0);
+        *val = retain(*in);
+        *idx = loc.release();
+        return AF_SUCCESS;
+    }
+    dim_t od[4] = {in->info.dims[0], in->info.dims[1], in->info.dims[2], in->info.dims[3]};
+    od[dim] = 1;
+    Holder res, loc;
+    res.a = new_array(in->info.type, od);
+    loc.a = new_array(u32, od);
+    {
+        OpLock lk(in->device());
+        LaunchCtx c = ctx_for_active_device();
+        if (!launch_ireduce(c, op, in->info.type, view_of(*in), dim, res.a->data(), (unsigned *)loc.a->data()))
+            AFB_TYPE_ERROR(1, in->info.type);
+    }
+    *val = res.release();
+    *idx = loc.release();
+    AFB_API_END
+}
+
+void ireduce_all_into(const Array &in, Op op, void *dval, unsigned *dloc) {
+    const Array *src = &in;
+    Holder tmp;
+    if (!in.is_linear() && in.info.dims[0] < 4096) {
+        tmp.a = make_dense_copy(in);
+        src = tmp.a;
+    }
+    OpLock lk(in.device());
+    LaunchCtx c = ctx_for_active_device();
+    if (!launch_ireduce_all(c, op, in.info.type, view_of(*src), dval, dloc)) AFB_TYPE_ERROR(1, in.info.type);
+}
+
+af_err ireduce_all_scalar(double *real, double *imag, unsigned *loc, const af_array in_h, Op op) {
+    AFB_API_BEGIN
+    Array *in = from_handle(in_h);
+    AFB_ARG(3, in->ndims() > 0);
+    AFB_ARG(0, real != nullptr);
+    AFB_ARG(2, loc != nullptr);
+    *real = 0;
+    if (imag) *imag = 0;
+    const af_dtype t = in->info.type;
+    if (t == f16) AFB_TYPE_ERROR(1, t);  // no f16 case in the reference (reduce.cpp:1095-1131)
+    if (t == c32 || t == c64) AFB_ARG(1, imag != nullptr);
+    check_same_device(*in);
+    Holder res, l;
+    dim_t one[4] = {1, 1, 1, 1};
+    res.a = new_array(t, one);
+    l.a = new_array(u32, one);
+    ireduce_all_into(*in, op, res.a->data(), (unsigned *)l.a->data());
+    cudaStream_t s = stream_of(in->device());
+    AFB_CUDA(cudaMemcpyAsync(loc, l.a->data(), 4, cudaMemcpyDeviceToHost, s));
+    read_scalar(t, res.a->data(), s, real, imag);  // synchronises
+    AFB_API_END
+}
+
+// ---- scans -----------------------------------------------------------------------------------------
+bool scan_promote(af_dtype ti, af_dtype *to) {
+    switch (ti) {
+        case f32: case f64: case c32: case c64: case u32: case s32: case u64: case s64: *to = ti; return true;
+        case u16: case u8: case b8: *to = u32; return true;
+        case s16: case s8: *to = s32; return true;
+        default: return false;
+    }
+}
+
+af_err scan_common(af_array *out, const af_array in_h, int dim, int binop, bool inclusive, bool accum) {
+    AFB_API_BEGIN
+    AFB_ARG(2, dim >= 0);
+    AFB_ARG(2, dim < 4);
+    AFB_ARG(0, out != nullptr);
+    Array *in = from_handle(in_h);
+    if (dim >= in->ndims()) {
+        *out = retain(*in);
+        return AF_SUCCESS;
+    }
+    check_same_device(*in);
+    af_dtype to;
+    if (!scan_promote(in->info.type, &to)) AFB_TYPE_ERROR(1, in->info.type);
+    Op op;
+    if (accum) {
+        op = (in->info.type == b8) ? OP_NOTZERO : OP_ADD;  // scan.cpp:146-148
+    } else {
+        if (binop < 0 || binop > 3) fail(AF_ERR_ARG, "Incorrect binary operation enum for argument number 2");
+        op = (Op)binop;
+    }
+    Holder res;
+    res.a = new_array(to, in->info.dims);
+    {
+        OpLock lk(in->device());
+        LaunchCtx c = ctx_for_active_device();
+        if (!launch_scan(c, op, in->info.type, to, view_of(*in), dim, inclusive, res.a->data(), nullptr))
+            AFB_TYPE_ERROR(1, in->info.type);
+    }
+    *out = res.release();
+    AFB_API_END
+}
+
+bool sbk_promote(af_dtype ti, af_dtype *to) {
+    switch (ti) {
+        case f32: case f64: case c32: case c64: case s32: case u32: case s64: case u64: *to = ti; return true;
+        case s16: case s8: *to = s32; return true;
+        case u16: case u8: case b8: *to = u32; return true;
+        default: return false;
+    }
+}
+
+// shared by af_scan_by_key and afx_scan_shard
+Array *scan_by_key_impl(const Array &key, const Array &in, int dim, int binop, bool inclusive, const void *carry,
+                        const void *carry_key) {
+    for (int i = 0; i < 4; i++) AFB_ARG(2, in.info.dims[i] == key.info.dims[i]);
+    af_dtype to;
+    if (!sbk_promote(in.info.type, &to)) AFB_TYPE_ERROR(1, in.info.type);
+    if (binop < 0 || binop > 3) fail(AF_ERR_ARG, "Incorrect binary operation enum for argument number 3");
+    const af_dtype tk = key.info.type;
+    if (!(tk == s32 || tk == u32 || tk == s64 || tk == u64)) AFB_TYPE_ERROR(1, tk);
+    OpLock lk(in.device());
+    LaunchCtx c = ctx_for_active_device();
+    const Array *vals = &in;
+    Holder cast;
+    if (to != in.info.type) {  // castArray<Ti>(in), scan.cpp:45-58
+        cast.a = new_array(to, in.info.dims);
+        if (!launch_cast(c, in.info.type, to, view_of(in), cast.a->data())) AFB_TYPE_ERROR(1, in.info.type);
+        vals = cast.a;
+    }
+    Holder res;
+    res.a = new_array(to, in.info.dims);
+    if (!launch_scan_by_key(c, (Op)binop, to, tk, view_of(key), view_of(*vals), dim, inclusive, res.a->data(), carry,
+                            carry_key))
+        AFB_TYPE_ERROR(1, in.info.type);
+    return res.release();
+}
+
+// ---- where -------------------------------------------------------------------------------------------
+Array *where_impl(const Array &in, unsigned base, dim_t *count_out) {
+    const af_dtype t = in.info.type;
+    if (t == f16) AFB_TYPE_ERROR(1, t);
+    const dim_t n = in.elements();
+    if (n >= 0xffffffffLL) fail(AF_ERR_SIZE, "af_where: indices are 32-bit, the input has too many elements");
+    const Array *src = &in;
+    Holder tmp;
+    if (!in.is_linear()) {
+        tmp.a = make_dense_copy(in);
+        src = tmp.a;
+    }
+    // worst-case sized output straight from the pool: the kernel writes indices to their final position
+    // and the count comes back once, at the end (the reference syncs mid-pipeline to size the output)
+    Holder big;
+    dim_t cap[4] = {n, 1, 1, 1};
+    big.a = new_array(u32, cap);
+    unsigned long long h_count = 0;
+    {
+        OpLock lk(in.device());
+        LaunchCtx c = ctx_for_active_device();
+        unsigned long long *d_count = (unsigned long long *)c.scratch->dev_scalar;
+        if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), d_count, base)) AFB_TYPE_ERROR(1, t);
+        AFB_CUDA(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, c.stream));
+        AFB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (count_out) *count_out = (dim_t)h_count;
+    const char *e = getenv("AFB200_WHERE_SHRINK_DIV");
+    const dim_t div = e ? atoll(e) : 8;
+    if (h_count == 0 || (div > 0 && (dim_t)h_count < n / div)) {
+        // few hits: hand back an exact-size buffer instead of pinning the worst-case allocation
+        dim_t d[4] = {(dim_t)h_count, 1, 1, 1};
+        Holder exact;
+        exact.a = new_array(u32, d);
+        if (h_count) {
+            cudaStream_t s = stream_of(in.device());
+            AFB_CUDA(cudaMemcpyAsync(exact.a->data(), big.a->data(), (size_t)h_count * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        return exact.release();
+    }
+    big.a->info.dims[0] = (dim_t)h_count;  // keep the over-sized buffer, expose only the hits
+    dense_strides(big.a->info.dims, big.a->info.strides);
+    return big.release();
+}
+
+}  // namespace
+
+extern "C" {
+
+af_err af_sum(af_array *out, const af_array in, const int dim) { return reduce_dimwise(out, in, dim, FAM_PROMOTE, OP_ADD, false, 0); }
+af_err af_sum_nan(af_array *out, const af_array in, const int dim, const double nanval) { return reduce_dimwise(out, in, dim, FAM_PROMOTE, OP_ADD, true, nanval); }
+af_err af_product(af_array *out, const af_array in, const int dim) { return reduce_dimwise(out, in, dim, FAM_PROMOTE, OP_MUL, false, 0); }
+af_err af_product_nan(af_array *out, const af_array in, const int dim, const double nanval) { return reduce_dimwise(out, in, dim, FAM_PROMOTE, OP_MUL, true, nanval); }
+af_err af_min(af_array *out, const af_array in, const int dim) { return reduce_dimwise(out, in, dim, FAM_COMMON, OP_MIN, false, 0); }
+af_err af_max(af_array *out, const af_array in, const int dim) { return reduce_dimwise(out, in, dim, FAM_COMMON, OP_MAX, false, 0); }
+af_err af_count(af_array *out, const af_array in, const int dim) { return reduce_dimwise(out, in, dim, FAM_TYPE, OP_NOTZERO, false, 0); }
+af_err af_all_true(af_array *out, const af_array in, const int dim) { return reduce_dimwise(out, in, dim, FAM_TYPE, OP_AND, false, 0); }
+af_err af_any_true(af_array *out, const af_array in, const int dim) { return reduce_dimwise(out, in, dim, FAM_TYPE, OP_OR, false, 0); }
+
+af_err af_sum_all(double *r, double *i, const af_array in) { return reduce_all_scalar(r, i, in, FAM_PROMOTE, OP_ADD, false, 0, false); }
+af_err af_sum_nan_all(double *r, double *i, const af_array in, const double nanval) { return reduce_all_scalar(r, i, in, FAM_PROMOTE, OP_ADD, true, nanval, false); }
+af_err af_product_all(double *r, double *i, const af_array in) { return reduce_all_scalar(r, i, in, FAM_PROMOTE, OP_MUL, false, 0, false); }
+af_err af_product_nan_all(double *r, double *i, const af_array in, const double nanval) { return reduce_all_scalar(r, i, in, FAM_PROMOTE, OP_MUL, true, nanval, false); }
+af_err af_min_all(double *r, double *i, const af_array in) { return reduce_all_scalar(r, i, in, FAM_COMMON, OP_MIN, false, 0, true); }
+af_err af_max_all(double *r, double *i, const af_array in) { return reduce_all_scalar(r, i, in, FAM_COMMON, OP_MAX, false, 0, true); }
+af_err af_count_all(double *r, double *i, const af_array in) { return reduce_all_scalar(r, i, in, FAM_TYPE, OP_NOTZERO, false, 0, false); }
+af_err af_all_true_all(double *r, double *i, const af_array in) { return reduce_all_scalar(r, i, in, FAM_TYPE, OP_AND, false, 0, false); }
+af_err af_any_true_all(double *r, double *i, const af_array in) { return reduce_all_scalar(r, i, in, FAM_TYPE, OP_OR, false, 0, false); }
+
+af_err af_sum_all_array(af_array *out, const af_array in) { return reduce_all_array(out, in, FAM_PROMOTE, OP_ADD, false, 0, false); }
+af_err af_sum_nan_all_array(af_array *out, const af_array in, const double nanval) { return reduce_all_array(out, in, FAM_PROMOTE, OP_ADD, true, nanval, false); }
+af_err af_product_all_array(af_array *out, const af_array in) { return reduce_all_array(out, in, FAM_PROMOTE, OP_MUL, false, 0, false); }
+af_err af_product_nan_all_array(af_array *out, const af_array in, const double nanval) { return reduce_all_array(out, in, FAM_PROMOTE, OP_MUL, true, nanval, false); }
+af_err af_min_all_array(af_array *out, const af_array in) { return reduce_all_array(out, in, FAM_COMMON, OP_MIN, false, 0, true); }
+af_err af_max_all_array(af_array *out, const af_array in) { return reduce_all_array(out, in, FAM_COMMON, OP_MAX, false, 0, true); }
+af_err af_count_all_array(af_array *out, const af_array in) { return reduce_all_array(out, in, FAM_TYPE, OP_NOTZERO, false, 0, false); }
+af_err af_all_true_all_array(af_array *out, const af_array in) { return reduce_all_array(out, in, FAM_TYPE, OP_AND, false, 0, false); }
+af_err af_any_true_all_array(af_array *out, const af_array in) { return reduce_all_array(out, in, FAM_TYPE, OP_OR, false, 0, false); }
+
+af_err af_imin(af_array *out, af_array *idx, const af_array in, const int dim) { return ireduce_dimwise(out, idx, in, dim, OP_MIN); }
+af_err af_imax(af_array *out, af_array *idx, const af_array in, const int dim) { return ireduce_dimwise(out, idx, in, dim, OP_MAX); }
+af_err af_imin_all(double *r, double *i, unsigned *idx, const af_array in) { return ireduce_all_scalar(r, i, idx, in, OP_MIN); }
+af_err af_imax_all(double *r, double *i, unsigned *idx, const af_array in) { return ireduce_all_scalar(r, i, idx, in, OP_MAX); }
+
+af_err af_accum(af_array *out, const af_array in, const int dim) { return scan_common(out, in, dim, AF_BINARY_ADD, true, true); }
+af_err af_scan(af_array *out, const af_array in, const int dim, af_binary_op op, bool inclusive_scan) {
+    return scan_common(out, in, dim, (int)op, inclusive_scan, false);
+}
+
+af_err af_scan_by_key(af_array *out, const af_array key_h, const af_array in_h, const int dim, af_binary_op op,
+                      bool inclusive_scan) {
+    AFB_API_BEGIN
+    AFB_ARG(2, dim >= 0);
+    AFB_ARG(2, dim < 4);
+    AFB_ARG(0, out != nullptr);
+    Array *in = from_handle(in_h);
+    Array *key = from_handle(key_h);
+    if (dim >= in->ndims()) {
+        *out = retain(*in);
+        return AF_SUCCESS;
+    }
+    check_same_device(*in);
+    check_same_device(*key);
+    *out = scan_by_key_impl(*key, *in, dim, (int)op, inclusive_scan, nullptr, nullptr);
+    AFB_API_END
+}
+
+af_err af_where(af_array *idx, const af_array in_h) {
+    AFB_API_BEGIN
+    AFB_ARG(0, idx != nullptr);
+    Array *in = from_handle(in_h);
+    if (in->ndims() == 0) {  // where.cpp:39-41
+        dim_t d[4] = {0, 1, 1, 1};
+        *idx = new_array(u32, d);
+        return AF_SUCCESS;
+    }
+    check_same_device(*in);
+    *idx = where_impl(*in, 0u, nullptr);
+    AFB_API_END
+}
+
+// ===================================================================================================
+// afx_*: shard-local pieces of the sharded whole-array ops (see include/afb200.h)
+// ===================================================================================================
+af_err afx_reduce_all_partial(void *partial, af_dtype *partial_type, const af_array in_h, int op, bool change_nan,
+                              double nanval) {
+    AFB_API_BEGIN
+    AFB_ARG(0, partial != nullptr);
+    AFB_ARG(3, op >= 0 && op <= 6);
+    Array *in = from_handle(in_h);
+    AFB_ARG(2, in->elements() > 0);
+    check_same_device(*in);
+    const Family fam = (op == OP_ADD || op == OP_MUL) ? FAM_PROMOTE : (op == OP_MIN || op == OP_MAX) ? FAM_COMMON : FAM_TYPE;
+    Op eff;
+    af_dtype to;
+    resolve(fam, (Op)op, in->info.type, &eff, &to);
+    if (partial_type) *partial_type = to;
+    reduce_all_into(*in, eff, to, change_nan, nanval, partial);
+    AFB_API_END
+}
+
+af_err afx_ireduce_all_partial(void *partial_val, unsigned *partial_idx, const af_array in_h, int op) {
+    AFB_API_BEGIN
+    AFB_ARG(0, partial_val != nullptr);
+    AFB_ARG(1, partial_idx != nullptr);
+    AFB_ARG(3, op == OP_MIN || op == OP_MAX);
+    Array *in = from_handle(in_h);
+    AFB_ARG(2, in->ndims() > 0);
+    check_same_device(*in);
+    ireduce_all_into(*in, (Op)op, partial_val, partial_idx);
+    AFB_API_END
+}
+
+af_err afx_scan_shard(af_array *out, const af_array key_h, const af_array in_h, af_binary_op op, bool inclusive_scan,
+                      const void *carry, const void *carry_key) {
+    AFB_API_BEGIN
+    AFB_ARG(0, out != nullptr);
+    Array *in = from_handle(in_h);
+    AFB_ARG(2, in->elements() > 0 && in->elements() == in->info.dims[0]);  // a 1-D shard
+    check_same_device(*in);
+    if (key_h) {
+        Array *key = from_handle(key_h);
+        check_same_device(*key);
+        *out = scan_by_key_impl(*key, *in, 0, (int)op, inclusive_scan, carry_key ? carry : nullptr, carry_key);
+    } else {
+        af_dtype to;
+        if (!scan_promote(in->info.type, &to)) AFB_TYPE_ERROR(1, in->info.type);
+        AFB_ARG(3, (int)op >= 0 && (int)op <= 3);
+        Holder res;
+        res.a = new_array(to, in->info.dims);
+        {
+            OpLock lk(in->device());
+            LaunchCtx c = ctx_for_active_device();
+            if (!launch_scan(c, (Op)op, in->info.type, to, view_of(*in), 0, inclusive_scan, res.a->data(), carry))
+                AFB_TYPE_ERROR(1, in->info.type);
+        }
+        *out = res.release();
+    }
+    AFB_API_END
+}
+
+af_err afx_where_shard(af_array *idx, dim_t *count, const af_array in_h, unsigned base) {
+    AFB_API_BEGIN
+    AFB_ARG(0, idx != nullptr);
+    Array *in = from_handle(in_h);
+    AFB_ARG(2, in->elements() > 0);
+    check_same_device(*in);
+    *idx = where_impl(*in, base, count);
+    AFB_API_END
+}
+
+af_err afx_launch_count(unsigned long long *count, bool reset) {
+    AFB_API_BEGIN
+    AFB_ARG(0, count != nullptr);
+    *count = launches_total(reset);
+    AFB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// common.hpp -- shared host-side declarations of libafb200: the array handle, the
+// error model, the device/stream manager, the memory pool, and the type-erased
+// launcher interface between the C-API layer (api_*.cpp) and the kernels (kernels/*.cu).
+//
+// Reference counterparts (studied for behaviour, not translated):
+//   handle / ArrayInfo   src/backend/common/ArrayInfo.hpp:26-48, src/backend/cuda/Array.hpp:141-309
+//   error model          src/backend/common/err_common.hpp:149-208, src/api/c/error.cpp:19-45
+//   device + stream      src/backend/cuda/platform.cpp:354-408,546-556
+//   memory manager       src/backend/common/DefaultMemoryManager.cpp:158-282
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/afb200.h"
+
+namespace afb {
+
+// ---------------------------------------------------------------------------------------------
+// errors: C++ exceptions inside, af_err + thread-local message at the C boundary
+// ---------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    af_err code;
+    Error(af_err c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] void fail(af_err code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+af_err store_error(af_err code, const char *msg) noexcept;  // sets the thread-local message
+af_err current_exception_to_err() noexcept;                 // the CATCHALL of this library
+
+#define AFB_ARG(index, cond)                                                                        \
+    do {                                                                                            \
+        if (!(cond)) ::afb::fail(AF_ERR_ARG, "%s: invalid argument %d, expected: %s", __func__, index, #cond); \
+    } while (0)
+#define AFB_TYPE_ERROR(index, type) \
+    ::afb::fail(AF_ERR_TYPE, "%s: invalid type (%d) for argument %d", __func__, (int)(type), index)
+#define AFB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            ::afb::fail(e_ == cudaErrorMemoryAllocation ? AF_ERR_NO_MEM : AF_ERR_RUNTIME,           \
+                        "CUDA error %d (%s) at %s:%d: %s", (int)e_, cudaGetErrorName(e_), __FILE__, __LINE__, #call); \
+    } while (0)
+#define AFB_API_BEGIN try {
+#define AFB_API_END                                    \
+    }                                                  \
+    catch (...) { return ::afb::current_exception_to_err(); } \
+    return AF_SUCCESS;
+
+// ---------------------------------------------------------------------------------------------
+// dtype helpers
+// ---------------------------------------------------------------------------------------------
+inline size_t dtype_size(af_dtype t) {
+    switch (t) {
+        case f32: case s32: case u32: return 4;
+        case f64: case c32: case s64: case u64: return 8;
+        case c64: return 16;
+        case b8: case u8: case s8: return 1;
+        case s16: case u16: case f16: return 2;
+    }
+    return 0;
+}
+inline bool dtype_valid(int t) { return t >= 0 && t <= (int)s8; }
+
+// ---------------------------------------------------------------------------------------------
+// devices, streams, scratch
+// ---------------------------------------------------------------------------------------------
+struct Scratch;  // per-device persistent workspace for partials / tickets / tile descriptors
+
+int device_count();
+int active_device();            // thread-local, default AF_CUDA_DEFAULT_DEVICE or 0
+void set_active_device(int d);  // also cudaSetDevice
+cudaStream_t stream_of(int device);
+int sm_count(int device);
+Scratch &scratch_of(int device);
+std::mutex &op_mutex(int device);  // serialises multi-kernel enqueue sequences that share Scratch
+void note_launches(unsigned n);    // launch accounting for afx_launch_count
+unsigned long long launches_total(bool reset);
+std::string take_last_error();     // fetch + clear the calling thread's error message
+void post_launch_check(const char *what);  // cudaGetLastError (+ sync when AF_SYNCHRONOUS_CALLS=1)
+
+// ---------------------------------------------------------------------------------------------
+// memory pool
+// ---------------------------------------------------------------------------------------------
+struct Buffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;       // allocated (rounded) size
+    int device = 0;
+    bool pooled = true;     // came from pool_alloc (false: adopted by af_device_array)
+    bool user_locked = false;  // af_lock_array / af_get_device_ptr: the user owns the lifetime
+    ~Buffer();
+};
+std::shared_ptr<Buffer> pool_alloc(size_t bytes);            // on the active device
+std::shared_ptr<Buffer> adopt_device_ptr(void *ptr, size_t bytes);
+void *pool_alloc_raw(size_t bytes);                          // af_alloc_device
+void pool_free_raw(void *ptr);
+void pool_gc(int device);
+void pool_stats(int device, size_t *alloc_bytes, size_t *alloc_buffers, size_t *lock_bytes, size_t *lock_buffers);
+void pool_set_step(size_t step);
+size_t pool_get_step();
+
+// ---------------------------------------------------------------------------------------------
+// the array handle
+// ---------------------------------------------------------------------------------------------
+// The first bytes mirror the reference's ArrayInfo so that code which peeks at
+// `devId` through an af_array (the unified loader's backend check,
+// src/api/unified/symbol_manager.hpp:90-103) keeps working.
+struct Info {
+    unsigned devId;  // device | (AF_BACKEND_CUDA << 8), ArrayInfo.cpp:48-52,87-99
+    af_dtype type;
+    dim_t dims[4];
+    dim_t offset;  // elements
+    dim_t strides[4];
+    bool is_sparse;
+};
+
+constexpr unsigned kMagic = 0xAFB20001u;
+
+struct Array {
+    Info info;
+    unsigned magic = kMagic;
+    std::shared_ptr<Buffer> buf;  // shared between retained handles and views
+
+    int device() const { return (int)(info.devId & 0xff); }
+    dim_t elements() const { return info.dims[0] * info.dims[1] * info.dims[2] * info.dims[3]; }
+    int ndims() const;     // dim4::ndims semantics (0 for empty, 1 for scalar)
+    bool is_linear() const;
+    const void *data() const { return (const char *)buf->ptr + (size_t)info.offset * dtype_size(info.type); }
+    void *data() { return (char *)buf->ptr + (size_t)info.offset * dtype_size(info.type); }
+};
+
+Array *from_handle(af_array h);              // validates; throws AF_ERR_ARG on null/bad magic
+Array *new_array(af_dtype t, const dim_t dims[4]);  // dense, freshly allocated on the active device
+Array *new_view(const Array &parent, const dim_t dims[4], dim_t offset, const dim_t strides[4]);
+Array *retain(const Array &a);
+void dense_strides(const dim_t dims[4], dim_t strides[4]);
+void check_same_device(const Array &a);      // AF_ERR_DEVICE when the array is not on the active device
+
+// ---------------------------------------------------------------------------------------------
+// type-erased kernel launchers (kernels/*.cu).  Views carry pointers with the offset applied.
+// Internal op codes: ADD..MAX coincide with af_binary_op.
+// ---------------------------------------------------------------------------------------------
+enum Op { OP_ADD = 0, OP_MUL = 1, OP_MIN = 2, OP_MAX = 3, OP_NOTZERO = 4, OP_AND = 5, OP_OR = 6 };
+
+struct View {
+    const void *ptr;
+    dim_t dims[4];
+    dim_t strides[4];
+};
+View view_of(const Array &a);
+
+struct LaunchCtx {
+    int device;
+    cudaStream_t stream;
+    int sms;
+    Scratch *scratch;
+};
+LaunchCtx ctx_for_active_device();
+
+// out: dense array with dims = in.dims but dims[dim] = 1.  Returns false if (op,ti,to) is not instantiated.
+bool launch_reduce(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool change_nan,
+                   double nanval, void *out);
+// out: device pointer to ONE element of `to`
+bool launch_reduce_all(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, bool change_nan,
+                       double nanval, void *out);
+bool launch_ireduce(const LaunchCtx &c, Op op, af_dtype t, const View &in, int dim, void *out_val, unsigned *out_loc);
+bool launch_ireduce_all(const LaunchCtx &c, Op op, af_dtype t, const View &in, void *out_val, unsigned *out_loc);
+// carry / carry_key: optional device pointers (sharded scans); out is dense with in.dims
+bool launch_scan(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool inclusive,
+                 void *out, const void *carry);
+bool launch_scan_by_key(const LaunchCtx &c, Op op, af_dtype t, af_dtype tk, const View &key, const View &in, int dim,
+                        bool inclusive, void *out, const void *carry, const void *carry_key);
+// writes hit indices (+base) to `out` (capacity = elements) and the count to *d_count (device, 8 bytes)
+bool launch_where(const LaunchCtx &c, af_dtype t, const View &in, unsigned *out, unsigned long long *d_count,
+                  unsigned base);
+// dense copy of a strided view (same dtype), value fill, dtype cast (dense -> dense)
+void launch_copy_strided(const LaunchCtx &c, af_dtype t, const View &in, void *out);
+void launch_fill(const LaunchCtx &c, af_dtype t, void *out, dim_t n, double re, double im);
+bool launch_cast(const LaunchCtx &c, af_dtype ti, af_dtype to, const View &in, void *out);
+
+// ---------------------------------------------------------------------------------------------
+// per-device persistent scratch
+// ---------------------------------------------------------------------------------------------
+struct Scratch {
+    int device = -1;
+    void *partials = nullptr;      size_t partials_bytes = 0;   // block partials of split reductions
+    unsigned *tickets = nullptr;   size_t tickets_count = 0;    // self-resetting arrival counters (zeroed once)
+    void *tiles = nullptr;         size_t tiles_bytes = 0;      // decoupled-lookback tile descriptors (scans)
+    void *wtiles = nullptr;        size_t wtiles_bytes = 0;     // packed single-word descriptors (where)
+    unsigned *tile_counter = nullptr;                           // dynamic tile-id ticket (self-resetting)
+    unsigned epoch = 0, wepoch = 0;                             // generation tags of the two descriptor arrays
+    void *host_pinned = nullptr;   size_t host_pinned_bytes = 0;  // D2H landing zone for scalars
+    void *dev_scalar = nullptr;                                 // 64-byte device scalar slot(s)
+
+    void *need_partials(size_t bytes);
+    unsigned *need_tickets(size_t count);
+    void ensure_basics();                            // tile_counter, dev_scalar, host_pinned
+    void *need_tiles(size_t bytes, cudaStream_t s);  // zero-filled on (re)allocation
+    unsigned next_epoch(cudaStream_t s);             // bumps epoch; re-zeroes `tiles` on wrap-around
+    void *need_wtiles(size_t bytes, cudaStream_t s);
+    unsigned next_wepoch(cudaStream_t s);
+};
+
+}  // namespace afb

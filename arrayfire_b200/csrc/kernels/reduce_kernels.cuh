@@ -1,0 +1,454 @@
+// reduce_kernels.cuh -- the three reduction kernels of libafb200, generic over a Policy
+// (plain value reductions and (value,index) reductions share them).
+//
+// What they replace in the reference (behaviour studied, design is new):
+//   reduce_first_kernel / reduce_all_kernel / reduce_dim_kernel
+//       /root/reference/src/backend/cuda/kernel/reduce.hpp:33-111,190-382  (scalar loads, smem tree, 2nd launch)
+//   ireduceFirst / ireduceDim + host-side finish
+//       /root/reference/src/backend/cuda/kernel/ireduce.cuh:19-252, kernel/ireduce.hpp:163-258
+//
+// B200 design:
+//   * span_kernel    -- dim-0 and whole-array reductions of LONG columns.  Each CTA streams a contiguous
+//                       chunk with 128-bit L1-bypassing loads (UNROLL independent loads in flight per
+//                       thread), reduces with warp shuffles, then
+//                         - CTAs of one thread-block CLUSTER combine through distributed shared memory,
+//                         - cluster leaders publish one partial each and the LAST arriver (self-resetting
+//                           ticket) folds the partials in a fixed order -> single launch, deterministic.
+//   * warp_cols_kernel -- dim-0 reductions of SHORT columns: a group of 1..32 lanes per column.
+//   * dim_kernel     -- reductions along dim>0: lanes (x VEC-wide vectors) run along the contiguous dim 0 so
+//                       every warp request is a full 128..512-byte line; the reduced axis is split over the
+//                       warps of a CTA and over the CTAs of a cluster, combined through (distributed) smem.
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "device_ops.cuh"
+
+namespace afb {
+namespace cg = cooperative_groups;
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+// ------------------------------------------------------------------------------------------------
+// policies
+// ------------------------------------------------------------------------------------------------
+struct ValParams {
+    int change_nan;
+    double nanval;
+};
+
+template<int OP, typename Ti, typename To> struct ValPolicy {
+    typedef Ti In;
+    typedef typename compute_of<To>::type Acc;
+    typedef Rule<OP, Ti, Acc> R;
+    typedef ValParams Params;
+    struct Out { To *val; };
+    AFB_DI static Acc init() { return R::init(); }
+    AFB_DI static Acc load(const Params &p, In x, uint) {
+        Acc v = R::pre(x);
+        if (p.change_nan) v = nan_swap<Acc>(v, p.nanval);
+        return v;
+    }
+    AFB_DI static Acc join(Acc a, Acc b) { return R::join(a, b); }
+    AFB_DI static void store(const Out &o, size_t i, Acc a) { o.val[i] = conv<To, Acc>(a); }
+    // fold one 16-byte vector of inputs whose first element has index idx0
+    AFB_DI static Acc fold16(const Params &p, Acc acc, const Vec16 &v, uint idx0) {
+        constexpr int V = VecN<In>::value;
+        if constexpr (OP == OP_NOTZERO && sizeof(In) == 1 && same_t<Acc, uint>::value) {
+            // 4 bytes at a time: per-byte "!= 0" mask, then a population count
+#pragma unroll
+            for (int w = 0; w < 4; w++) acc += __popc(__vcmpne4(v.w[w], 0u)) >> 3;
+            return acc;
+        } else {
+            const In *e = reinterpret_cast<const In *>(&v);
+#pragma unroll
+            for (int k = 0; k < V; k++) acc = join(acc, load(p, e[k], idx0 + k));
+            return acc;
+        }
+    }
+};
+
+struct ArgParams {};
+
+template<int OP, typename T> struct ArgPolicy {
+    typedef T In;
+    typedef Arg<T> Acc;
+    typedef ArgParams Params;
+    struct Out { T *val; uint *loc; };
+    // "no candidate yet": loses every tie against a real element (ireduce)
+    AFB_DI static Acc init() {
+        if (OP == OP_MIN) return Acc{Lim<T>::hi(), 0u};
+        return Acc{Lim<T>::lo(), 0xffffffffu};
+    }
+    AFB_DI static Acc load(const Params &, In x, uint idx) {
+        if (is_nan<T>(x)) {
+            // NaN candidates never win; only the seed (position 0) turns into the identity at index 0
+            if (idx == 0) return Acc{OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(), 0u};
+            return init();
+        }
+        return Acc{x, idx};
+    }
+    AFB_DI static Acc join(Acc a, Acc b) {
+        const double ka = order_key<T>(a.val), kb = order_key<T>(b.val);
+        bool take_b;
+        if (OP == OP_MIN) take_b = (kb < ka) || (kb == ka && b.idx > a.idx);
+        else take_b = (kb > ka) || (kb == ka && b.idx < a.idx);
+        return take_b ? b : a;
+    }
+    AFB_DI static void store(const Out &o, size_t i, Acc a) {
+        o.val[i] = a.val;
+        o.loc[i] = a.idx;
+    }
+    AFB_DI static Acc fold16(const Params &p, Acc acc, const Vec16 &v, uint idx0) {
+        constexpr int V = VecN<In>::value;
+        const In *e = reinterpret_cast<const In *>(&v);
+#pragma unroll
+        for (int k = 0; k < V; k++) acc = join(acc, load(p, e[k], idx0 + k));
+        return acc;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+// a partial written to global memory: at least word-aligned, a whole number of words
+template<typename T> struct alignas(alignof(T) < 4 ? 4 : alignof(T)) Slot {
+    T v;
+};
+// L2-coherent load of a slot written by another SM
+template<typename T> AFB_DI T load_cg(const Slot<T> *p) {
+    constexpr int W = sizeof(Slot<T>) / 4;
+    union U { Slot<T> t; uint32_t w[W]; AFB_DI U() {} } u;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+#pragma unroll
+    for (int i = 0; i < W; i++) u.w[i] = __ldcg(q + i);
+    return u.t.v;
+}
+
+template<typename P> AFB_DI typename P::Acc warp_reduce(typename P::Acc v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = P::join(v, shfl_down(v, d));
+    return v;
+}
+
+// result valid in thread 0; `sm` holds >= 32 Acc
+template<typename P> AFB_DI typename P::Acc block_reduce(typename P::Acc v, typename P::Acc *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_reduce<P>(v);
+    __syncthreads();  // protect `sm` against a previous use
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < nw ? sm[lane] : P::init();
+        v = warp_reduce<P>(v);
+    }
+    return v;
+}
+
+// Every thread of the CTA folds its share of base[lo, hi).  idx_bias + i is the index reported for base[i].
+template<typename P>
+AFB_DI typename P::Acc reduce_span(const typename P::Params &prm, const typename P::In *__restrict__ base, dim_t lo,
+                                   dim_t hi, uint idx_bias, int tid, int nthr) {
+    typedef typename P::In In;
+    typedef typename P::Acc Acc;
+    constexpr int V = VecN<In>::value;
+    Acc acc = P::init();
+    if (hi <= lo) return acc;
+    // scalar head up to the first 16-byte boundary
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(base + lo);
+    dim_t head = (dim_t)(((16 - (addr & 15)) & 15) / sizeof(In));
+    if (head > hi - lo) head = hi - lo;
+    if (tid < head) acc = P::join(acc, P::load(prm, ldg_stream<In>(base + lo + tid), idx_bias + (uint)(lo + tid)));
+    const dim_t vlo = lo + head;
+    const dim_t nvec = (hi - vlo) / V;
+    const Vec16 *vp = reinterpret_cast<const Vec16 *>(base + vlo);
+    dim_t v = tid;
+    for (; v + (dim_t)(kUnroll - 1) * nthr < nvec; v += (dim_t)kUnroll * nthr) {
+        Vec16 r[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++) r[u] = ldg_stream16(vp + v + (dim_t)u * nthr);
+#pragma unroll
+        for (int u = 0; u < kUnroll; u++)
+            acc = P::fold16(prm, acc, r[u], idx_bias + (uint)(vlo + (v + (dim_t)u * nthr) * V));
+    }
+    for (; v < nvec; v += nthr) acc = P::fold16(prm, acc, ldg_stream16(vp + v), idx_bias + (uint)(vlo + v * V));
+    const dim_t tlo = vlo + nvec * V;
+    if (tlo + tid < hi) acc = P::join(acc, P::load(prm, ldg_stream<In>(base + tlo + tid), idx_bias + (uint)(tlo + tid)));
+    return acc;
+}
+
+struct ColGeom {
+    dim_t len;          // elements per column (dims[0])
+    dim_t ncols;        // dims[1]*dims[2]*dims[3]
+    dim_t d1, d2;       // to unravel a column id
+    dim_t s1, s2, s3;   // element strides of dims 1..3
+};
+AFB_DI dim_t col_offset(const ColGeom &g, dim_t c) {
+    const dim_t j = c % g.d1, r = c / g.d1;
+    const dim_t k = r % g.d2, l = r / g.d2;
+    return j * g.s1 + k * g.s2 + l * g.s3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// span_kernel: long columns / whole array
+// ------------------------------------------------------------------------------------------------
+// mode "columns": one output per column; the column is cut into `bpc` chunks, one CTA each
+//                 (grid = ncols * bpc; CTAs of a cluster share a column because csize divides bpc).
+// mode "all":     one output for everything; the work items (column, chunk) are dealt round-robin to a
+//                 persistent grid, every CTA keeps ONE running partial.
+template<typename P>
+struct SpanArgs {
+    const typename P::In *in;
+    ColGeom g;
+    dim_t chunk;        // elements per (column, chunk) work item
+    int bpc;            // chunks per column
+    int all;            // 1: whole-array mode
+    int csize;          // cluster size (1 = no cluster)
+    typename P::Params prm;
+    typename P::Out out;
+    Slot<typename P::Acc> *partials;   // [ncols * bpc / csize]  or  [gridDim.x / csize] in "all" mode
+    uint *tickets;               // [ncols] or [1]
+};
+
+template<typename P>
+__global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
+    typedef typename P::Acc Acc;
+    __shared__ Acc sm[32];
+    __shared__ Acc sm_cluster[8];
+    __shared__ int sm_last;
+    const int tid = threadIdx.x;
+
+    Acc acc = P::init();
+    dim_t col = 0;
+    if (a.all) {
+        const dim_t nwork = a.g.ncols * a.bpc;
+        for (dim_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const dim_t c = w / a.bpc, part = w % a.bpc;
+            const dim_t lo = part * a.chunk, hi = min(lo + a.chunk, a.g.len);
+            acc = P::join(acc, reduce_span<P>(a.prm, a.in + col_offset(a.g, c), lo, hi, (uint)(c * a.g.len), tid, kThreads));
+        }
+    } else {
+        col = blockIdx.x / a.bpc;
+        const dim_t part = blockIdx.x % a.bpc;
+        const dim_t lo = part * a.chunk, hi = min(lo + a.chunk, a.g.len);
+        acc = reduce_span<P>(a.prm, a.in + col_offset(a.g, col), lo, hi, 0u, tid, kThreads);
+    }
+    acc = block_reduce<P>(acc, sm);  // thread 0
+
+    // ---- level 2: CTAs of one cluster combine through distributed shared memory
+    uint nparts = a.all ? gridDim.x : (uint)a.bpc;  // partials per output before clustering
+    uint my_part = a.all ? blockIdx.x : (uint)(blockIdx.x % a.bpc);
+    if (a.csize > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        const unsigned rank = cluster.block_rank();
+        if (tid == 0) {
+            Acc *leader = cluster.map_shared_rank(sm_cluster, 0);
+            leader[rank] = acc;
+        }
+        cluster.sync();
+        if (rank != 0) return;
+        if (tid == 0) {
+            acc = sm_cluster[0];
+            for (int r = 1; r < a.csize; r++) acc = P::join(acc, sm_cluster[r]);
+        }
+        nparts /= a.csize;
+        my_part /= a.csize;
+    }
+
+    // ---- level 3: one partial per (cluster of) CTA(s); the last arriver folds them in index order
+    if (nparts == 1) {
+        if (tid == 0) P::store(a.out, (size_t)col, acc);
+        return;
+    }
+    Slot<Acc> *slots = a.partials + (a.all ? 0 : (size_t)col * nparts);
+    uint *ticket = a.tickets + (a.all ? 0 : col);
+    if (tid == 0) {
+        slots[my_part].v = acc;
+        __threadfence();
+        const uint t = atomicAdd(ticket, 1u);
+        sm_last = (t == nparts - 1);
+    }
+    __syncthreads();
+    if (!sm_last) return;
+    __threadfence();
+    Acc fin = P::init();
+    for (uint i = tid; i < nparts; i += kThreads) fin = P::join(fin, load_cg(slots + i));
+    fin = block_reduce<P>(fin, sm);
+    if (tid == 0) {
+        P::store(a.out, (size_t)col, fin);
+        *ticket = 0u;  // self-reset: the next launch on this stream finds it clean
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp_cols_kernel: short columns, G (power of two, <= 32) lanes per column
+// ------------------------------------------------------------------------------------------------
+template<typename P>
+struct WarpColsArgs {
+    const typename P::In *in;
+    ColGeom g;
+    int group;  // lanes per column
+    typename P::Params prm;
+    typename P::Out out;
+};
+
+template<typename P>
+__global__ void __launch_bounds__(kThreads) warp_cols_kernel(const WarpColsArgs<P> a) {
+    typedef typename P::Acc Acc;
+    typedef typename P::In In;
+    const int G = a.group;
+    const int sub = threadIdx.x % G;
+    const dim_t groups_per_block = kThreads / G;
+    const dim_t ngroups_total = (dim_t)gridDim.x * groups_per_block;
+    const dim_t iters = (a.g.ncols + ngroups_total - 1) / ngroups_total;  // uniform trip count: shuffles stay converged
+    for (dim_t it = 0; it < iters; it++) {
+        const dim_t c = (it * gridDim.x + blockIdx.x) * groups_per_block + threadIdx.x / G;
+        Acc acc = P::init();
+        if (c < a.g.ncols) {
+            const In *base = a.in + col_offset(a.g, c);
+            dim_t i = sub;
+            for (; i + 3 * (dim_t)G < a.g.len; i += 4 * (dim_t)G) {
+                const In x0 = ldg_stream<In>(base + i), x1 = ldg_stream<In>(base + i + G);
+                const In x2 = ldg_stream<In>(base + i + 2 * G), x3 = ldg_stream<In>(base + i + 3 * G);
+                acc = P::join(acc, P::load(a.prm, x0, (uint)i));
+                acc = P::join(acc, P::load(a.prm, x1, (uint)(i + G)));
+                acc = P::join(acc, P::load(a.prm, x2, (uint)(i + 2 * G)));
+                acc = P::join(acc, P::load(a.prm, x3, (uint)(i + 3 * G)));
+            }
+            for (; i < a.g.len; i += G) acc = P::join(acc, P::load(a.prm, ldg_stream<In>(base + i), (uint)i));
+        }
+        for (int d = G >> 1; d > 0; d >>= 1) {
+            Acc o = shfl_down(acc, d);
+            if (sub + d < G) acc = P::join(acc, o);
+        }
+        if (sub == 0 && c < a.g.ncols) P::store(a.out, (size_t)c, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dim_kernel: reduce along dim > 0
+// ------------------------------------------------------------------------------------------------
+// VEC consecutive elements (4, 8 or 16 bytes) in one load
+template<typename In, int VEC> struct alignas(sizeof(In) * VEC >= 16 ? 16 : sizeof(In) * VEC) Pack {
+    In e[VEC];
+};
+template<typename In, int VEC> AFB_DI Pack<In, VEC> load_pack(const In *p) {
+    Pack<In, VEC> r;
+    constexpr int B = (int)sizeof(In) * VEC;
+    static_assert(B == 4 || B == 8 || B == 16 || VEC == 1, "pack must be 4, 8 or 16 bytes");
+    if constexpr (VEC == 1) {
+        r.e[0] = ldg_stream<In>(p);
+    } else if constexpr (B == 16) {
+        const Vec16 v = ldg_stream16(p);
+        r = *reinterpret_cast<const Pack<In, VEC> *>(&v);
+    } else if constexpr (B == 8) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        r = *reinterpret_cast<const Pack<In, VEC> *>(&v);
+    } else {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p));
+        r = *reinterpret_cast<const Pack<In, VEC> *>(&v);
+    }
+    return r;
+}
+// widest pack the dim kernels use: at most 4 elements and at most 16 bytes
+template<typename In> struct DimVec { static constexpr int value = sizeof(In) >= 16 ? 1 : (sizeof(In) == 8 ? 2 : 4); };
+
+struct DimGeom {
+    dim_t d0;           // contiguous extent
+    dim_t len, sd;      // reduced extent and its stride
+    dim_t na, sa;       // first batch dim (extent, input stride)
+    dim_t nb, sb;       // second batch dim
+    dim_t oa, ob;       // output strides of the two batch dims (output stride along dim 0 is 1)
+};
+
+template<typename P>
+struct DimArgs {
+    const typename P::In *in;
+    DimGeom g;
+    int splits;         // CTAs along the reduced axis (= cluster size in y)
+    typename P::Params prm;
+    typename P::Out out;
+};
+
+constexpr int kDimRows = 8;  // warps per CTA; each warp owns every kDimRows-th row of the CTA's slice
+
+template<typename P, int VEC>
+__global__ void __launch_bounds__(32 * kDimRows) dim_kernel(const DimArgs<P> a) {
+    typedef typename P::Acc Acc;
+    typedef typename P::In In;
+    __shared__ Acc sm[kDimRows][32 * VEC + 1];
+    __shared__ Acc sm_cluster[8][32 * VEC];
+    const int lane = threadIdx.x, wy = threadIdx.y;
+    const dim_t x0 = ((dim_t)blockIdx.x * 32 + lane) * VEC;  // first dim-0 element of this thread
+    const int split = blockIdx.y;
+    const dim_t rows_per_split = (a.g.len + a.splits - 1) / a.splits;
+    const dim_t r_lo = split * rows_per_split, r_hi = min(r_lo + rows_per_split, a.g.len);
+
+    for (dim_t batch = blockIdx.z; batch < a.g.na * a.g.nb; batch += gridDim.z) {
+        const dim_t ia = batch % a.g.na, ib = batch / a.g.na;
+        const In *base = a.in + ia * a.g.sa + ib * a.g.sb + x0;
+        Acc acc[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[k] = P::init();
+        if (x0 < a.g.d0) {
+            dim_t r = r_lo + wy;
+            for (; r + 3 * kDimRows < r_hi; r += 4 * kDimRows) {
+                Pack<In, VEC> v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = load_pack<In, VEC>(base + (r + u * kDimRows) * a.g.sd);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int k = 0; k < VEC; k++)
+                        acc[k] = P::join(acc[k], P::load(a.prm, v[u].e[k], (uint)(r + u * kDimRows)));
+            }
+            for (; r < r_hi; r += kDimRows) {
+                const Pack<In, VEC> v = load_pack<In, VEC>(base + r * a.g.sd);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) acc[k] = P::join(acc[k], P::load(a.prm, v.e[k], (uint)r));
+            }
+        }
+        // combine the kDimRows warps of the CTA
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < VEC; k++) sm[wy][lane * VEC + k] = acc[k];
+        __syncthreads();
+        if (wy == 0) {
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                Acc v = sm[0][lane * VEC + k];
+                for (int y = 1; y < kDimRows; y++) v = P::join(v, sm[y][lane * VEC + k]);
+                acc[k] = v;
+            }
+        }
+        // combine the CTAs of the cluster (splits of the reduced axis)
+        if (a.splits > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            const unsigned rank = cluster.block_rank();
+            if (wy == 0) {
+                Acc(*leader)[32 * VEC] = cluster.map_shared_rank(sm_cluster, 0);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) leader[rank][lane * VEC + k] = acc[k];
+            }
+            cluster.sync();
+            if (rank == 0 && wy == 0) {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    Acc v = sm_cluster[0][lane * VEC + k];
+                    for (int s = 1; s < a.splits; s++) v = P::join(v, sm_cluster[s][lane * VEC + k]);
+                    acc[k] = v;
+                }
+            }
+            cluster.sync();  // leader's smem must stay valid until read; also orders the next batch iteration
+            if (rank != 0) continue;
+        }
+        if (wy == 0 && x0 < a.g.d0) {
+            const size_t o = (size_t)(ia * a.g.oa + ib * a.g.ob + x0);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) P::store(a.out, o + k, acc[k]);
+        }
+    }
+}
+
+}  // namespace afb

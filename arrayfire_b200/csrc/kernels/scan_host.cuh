@@ -1,0 +1,158 @@
+// scan_host.cuh -- launch-shape selection for the scan kernels (host side).
+#pragma once
+
+#include "reduce_host.cuh"
+#include "scan_kernels.cuh"
+
+namespace afb {
+
+inline bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+template<int OP, typename Ti, typename To, bool KEYED, typename Tk>
+void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool inclusive, void *out,
+              const void *carry, const void *carry_key) {
+    typedef Rule<OP, Ti, To> R;
+    typedef SOps<R, To, KEYED> S;
+    typedef typename S::State State;
+    const dim_t n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
+    if (n == 0) return;
+    if (dim == 0) {
+        ColGeom g = col_geom(in);
+        constexpr int E = ScanVec<Ti, To>::value;
+        constexpr dim_t TILE = (dim_t)kScanThreads * kScanSlots * E;
+        const dim_t short_len = env_int("AFB200_SHORT_SCAN", 1024);
+        if (!carry && g.len <= short_len && g.ncols >= 32) {
+            WarpScanArgs<Ti, To, Tk> a;
+            a.in = (const Ti *)in.ptr;
+            a.key = KEYED ? (const Tk *)key->ptr : nullptr;
+            a.out = (To *)out;
+            a.g = g;
+            a.ks1 = KEYED ? key->strides[1] : 0;
+            a.ks2 = KEYED ? key->strides[2] : 0;
+            a.ks3 = KEYED ? key->strides[3] : 0;
+            a.inclusive = inclusive ? 1 : 0;
+            dim_t blocks = (g.ncols + kScanWarps - 1) / kScanWarps;
+            const dim_t cap = (dim_t)c.sms * 32;
+            if (blocks > cap) blocks = cap;
+            warp_scan_cols_kernel<OP, Ti, To, KEYED, Tk><<<(unsigned)blocks, kScanThreads, 0, c.stream>>>(a);
+            note_launches(1);
+            post_launch_check("warp_scan_cols_kernel");
+            return;
+        }
+        LookbackArgs<Ti, To, Tk> a;
+        a.in = (const Ti *)in.ptr;
+        a.key = KEYED ? (const Tk *)key->ptr : nullptr;
+        a.out = (To *)out;
+        a.g = g;
+        a.ks1 = KEYED ? key->strides[1] : 0;
+        a.ks2 = KEYED ? key->strides[2] : 0;
+        a.ks3 = KEYED ? key->strides[3] : 0;
+        a.tiles_per_col = (g.len + TILE - 1) / TILE;
+        a.ntiles = a.tiles_per_col * g.ncols;
+        if (a.ntiles >= 0xffffffffLL) fail(AF_ERR_SIZE, "scan: too many tiles");
+        a.inclusive = inclusive ? 1 : 0;
+        const size_t in_al = sizeof(Ti) * E >= 16 ? 16 : sizeof(Ti) * E;
+        const size_t out_al = sizeof(To) * E >= 16 ? 16 : sizeof(To) * E;
+        const size_t key_al = sizeof(Tk) * E >= 16 ? 16 : sizeof(Tk) * E;
+        bool vec_ok = aligned_to(in.ptr, in_al) && aligned_to(out, out_al);
+        if (KEYED) vec_ok = vec_ok && aligned_to(key->ptr, key_al);
+        if (g.ncols > 1) {
+            vec_ok = vec_ok && (g.len % E == 0);
+            for (int i = 1; i < 4; i++) {
+                if (in.dims[i] > 1) vec_ok = vec_ok && (in.strides[i] % E == 0) && (!KEYED || key->strides[i] % E == 0);
+            }
+        }
+        a.vec_ok = vec_ok ? 1 : 0;
+        a.tiles = c.scratch->need_tiles((size_t)a.ntiles * sizeof(TileDesc<State>), c.stream);
+        a.epoch = c.scratch->next_epoch(c.stream);
+        a.tile_counter = c.scratch->tile_counter;
+        a.carry = (const To *)carry;
+        a.carry_key = (const Tk *)carry_key;
+        lookback_kernel<OP, Ti, To, KEYED, Tk><<<(unsigned)a.ntiles, kScanThreads, 0, c.stream>>>(a);
+        note_launches(1);
+        post_launch_check("lookback_kernel");
+        return;
+    }
+    // dim > 0
+    StripScanArgs<Ti, To, Tk> a;
+    a.in = (const Ti *)in.ptr;
+    a.key = KEYED ? (const Tk *)key->ptr : nullptr;
+    a.out = (To *)out;
+    dim_t os[4];
+    dense_strides(in.dims, os);
+    a.d0 = in.dims[0];
+    a.len = in.dims[dim];
+    a.sd = in.strides[dim];
+    a.ksd = KEYED ? key->strides[dim] : 0;
+    a.osd = os[dim];
+    int others[2], m = 0;
+    for (int i = 1; i < 4; i++)
+        if (i != dim) others[m++] = i;
+    a.na = in.dims[others[0]];
+    a.sa = in.strides[others[0]];
+    a.ksa = KEYED ? key->strides[others[0]] : 0;
+    a.osa = os[others[0]];
+    a.nb = in.dims[others[1]];
+    a.sb = in.strides[others[1]];
+    a.ksb = KEYED ? key->strides[others[1]] : 0;
+    a.osb = os[others[1]];
+    a.inclusive = inclusive ? 1 : 0;
+    const dim_t gx = (a.d0 + 31) / 32;
+    dim_t gy = a.na * a.nb;
+    if (gy > 65535) gy = 65535;
+    if (gx > 0x7fffffffLL) fail(AF_ERR_SIZE, "scan: dim 0 too large");
+    strip_scan_kernel<OP, Ti, To, KEYED, Tk><<<dim3((unsigned)gx, (unsigned)gy), dim3(32, kStripY), 0, c.stream>>>(a);
+    note_launches(1);
+    post_launch_check("strip_scan_kernel");
+}
+
+// (Ti -> To) pairs the C API can reach (/root/reference/src/api/c/scan.cpp:133-149,175-215)
+#define AFB_SCAN_PAIRS(X)                                                                             \
+    X(f32, float, f32, float) X(f64, double, f64, double) X(c32, cfloat, c32, cfloat)                 \
+    X(c64, cdouble, c64, cdouble) X(s32, int, s32, int) X(u32, uint, u32, uint) X(s64, intl, s64, intl) \
+    X(u64, uintl, u64, uintl) X(s16, short, s32, int) X(u16, ushort, u32, uint) X(s8, schar, s32, int) \
+    X(u8, uchar, u32, uint) X(b8, b8_t, u32, uint)
+
+#define AFB_SBK_VALS(X)                                                                               \
+    X(f32, float) X(f64, double) X(c32, cfloat) X(c64, cdouble) X(s32, int) X(u32, uint) X(s64, intl) X(u64, uintl)
+
+template<int OP>
+bool scan_family(const LaunchCtx &c, af_dtype ti, af_dtype to, const View &in, int dim, bool inclusive, void *out,
+                 const void *carry) {
+#define X(ci, Ti, co, To)                                                                         \
+    if (ti == ci && to == co) {                                                                   \
+        run_scan<OP, Ti, To, false, int>(c, in, nullptr, dim, inclusive, out, carry, nullptr);    \
+        return true;                                                                              \
+    }
+    AFB_SCAN_PAIRS(X)
+#undef X
+    return false;
+}
+
+// keys are only compared for equality: s32/u32 share the 32-bit kernels, s64/u64 the 64-bit ones
+template<int OP>
+bool scan_by_key_family(const LaunchCtx &c, af_dtype t, af_dtype tk, const View &key, const View &in, int dim,
+                        bool inclusive, void *out, const void *carry, const void *carry_key) {
+    const bool k32 = (tk == s32 || tk == u32), k64 = (tk == s64 || tk == u64);
+    if (!k32 && !k64) return false;
+#define X(code, T)                                                                                     \
+    if (t == code) {                                                                                   \
+        if (k32) run_scan<OP, T, T, true, uint>(c, in, &key, dim, inclusive, out, carry, carry_key);   \
+        else run_scan<OP, T, T, true, uintl>(c, in, &key, dim, inclusive, out, carry, carry_key);      \
+        return true;                                                                                   \
+    }
+    AFB_SBK_VALS(X)
+#undef X
+    return false;
+}
+
+bool scan_add(const LaunchCtx &, af_dtype, af_dtype, const View &, int, bool, void *, const void *);
+bool scan_mul(const LaunchCtx &, af_dtype, af_dtype, const View &, int, bool, void *, const void *);
+bool scan_min(const LaunchCtx &, af_dtype, af_dtype, const View &, int, bool, void *, const void *);
+bool scan_max(const LaunchCtx &, af_dtype, af_dtype, const View &, int, bool, void *, const void *);
+bool sbk_add(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *);
+bool sbk_mul(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *);
+bool sbk_min(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *);
+bool sbk_max(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *);
+
+}  // namespace afb

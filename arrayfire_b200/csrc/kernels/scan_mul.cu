@@ -1,0 +1,8 @@
+// scan_mul.cu -- af_scan / af_accum instantiations for op MUL.
+#include "scan_host.cuh"
+namespace afb {
+bool scan_mul(const LaunchCtx &c, af_dtype ti, af_dtype to, const View &in, int dim, bool inclusive, void *out,
+             const void *carry) {
+    return scan_family<OP_MUL>(c, ti, to, in, dim, inclusive, out, carry);
+}
+}  // namespace afb

@@ -1,0 +1,215 @@
+/*
+ * afb200.h -- C-ABI of libafb200.so, the B200-native backend for ArrayFire's
+ * reduce / scan / scan_by_key / where hot path.
+ *
+ * Every af_* symbol below has the SAME name, argument list, ownership and error
+ * behaviour as the reference symbol it replaces, so the reference's C++ wrapper
+ * (src/api/cpp/{reduce,scan,where,array,device}.cpp) or any C caller can bind to
+ * this library for that path.  Citations are relative to /root/reference.
+ * Types mirror include/af/defines.h (af_err :71-208, af_dtype :210-233,
+ * af_array :243, dim_t :50, af_backend :417-421, af_binary_op :433-438) and
+ * include/af/seq.h:20-30 (af_seq); a translation unit may include EITHER this header
+ * or <arrayfire.h>, not both.
+ *
+ * The afx_* symbols at the end are this library's small extension for sharded
+ * (one-process-per-GPU) whole-array ops: the per-shard partials that are combined
+ * across ranks with NCCL allgather/allreduce by the host layer (arrayfire_b200/sharded.py).
+ */
+#ifndef AFB200_H
+#define AFB200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFAPI __attribute__((visibility("default")))
+
+typedef long long dim_t;
+typedef void *af_array;
+
+typedef enum {
+    AF_SUCCESS = 0,
+    AF_ERR_NO_MEM = 101,
+    AF_ERR_DRIVER = 102,
+    AF_ERR_RUNTIME = 103,
+    AF_ERR_INVALID_ARRAY = 201,
+    AF_ERR_ARG = 202,
+    AF_ERR_SIZE = 203,
+    AF_ERR_TYPE = 204,
+    AF_ERR_DIFF_TYPE = 205,
+    AF_ERR_BATCH = 207,
+    AF_ERR_DEVICE = 208,
+    AF_ERR_NOT_SUPPORTED = 301,
+    AF_ERR_NOT_CONFIGURED = 302,
+    AF_ERR_NONFREE = 303,
+    AF_ERR_NO_DBL = 401,
+    AF_ERR_NO_GFX = 402,
+    AF_ERR_NO_HALF = 403,
+    AF_ERR_LOAD_LIB = 501,
+    AF_ERR_LOAD_SYM = 502,
+    AF_ERR_ARR_BKND_MISMATCH = 503,
+    AF_ERR_INTERNAL = 998,
+    AF_ERR_UNKNOWN = 999
+} af_err;
+
+typedef enum { f32, c32, f64, c64, b8, s32, u32, u8, s64, u64, s16, u16, f16, s8 } af_dtype;
+typedef enum { afDevice, afHost } af_source;
+typedef enum {
+    AF_BACKEND_DEFAULT = 0, AF_BACKEND_CPU = 1, AF_BACKEND_CUDA = 2, AF_BACKEND_OPENCL = 4, AF_BACKEND_ONEAPI = 8
+} af_backend;
+typedef enum { AF_BINARY_ADD = 0, AF_BINARY_MUL = 1, AF_BINARY_MIN = 2, AF_BINARY_MAX = 3 } af_binary_op;
+typedef struct af_seq { double begin, end, step; } af_seq;
+
+/* ===================== hot path: reductions along a dimension ==========================
+ * include/af/algorithm.h:708-776,1095-1140; src/api/c/reduce.cpp:461-497 */
+AFAPI af_err af_sum(af_array *out, const af_array in, const int dim);                         /* reduce.cpp:469 */
+AFAPI af_err af_sum_nan(af_array *out, const af_array in, const int dim, const double nanval); /* reduce.cpp:477 */
+AFAPI af_err af_product(af_array *out, const af_array in, const int dim);                     /* reduce.cpp:473 */
+AFAPI af_err af_product_nan(af_array *out, const af_array in, const int dim, const double nanval); /* reduce.cpp:482 */
+AFAPI af_err af_min(af_array *out, const af_array in, const int dim);                         /* reduce.cpp:461 */
+AFAPI af_err af_max(af_array *out, const af_array in, const int dim);                         /* reduce.cpp:465 */
+AFAPI af_err af_count(af_array *out, const af_array in, const int dim);                       /* reduce.cpp:487 */
+AFAPI af_err af_all_true(af_array *out, const af_array in, const int dim);                    /* reduce.cpp:491 */
+AFAPI af_err af_any_true(af_array *out, const af_array in, const int dim);                    /* reduce.cpp:495 */
+
+/* ===================== hot path: whole-array reductions ================================
+ * src/api/c/reduce.cpp:862-916,1150-1168 */
+AFAPI af_err af_sum_all(double *real, double *imag, const af_array in);
+AFAPI af_err af_sum_nan_all(double *real, double *imag, const af_array in, const double nanval);
+AFAPI af_err af_product_all(double *real, double *imag, const af_array in);
+AFAPI af_err af_product_nan_all(double *real, double *imag, const af_array in, const double nanval);
+AFAPI af_err af_min_all(double *real, double *imag, const af_array in);
+AFAPI af_err af_max_all(double *real, double *imag, const af_array in);
+AFAPI af_err af_count_all(double *real, double *imag, const af_array in);
+AFAPI af_err af_all_true_all(double *real, double *imag, const af_array in);
+AFAPI af_err af_any_true_all(double *real, double *imag, const af_array in);
+AFAPI af_err af_sum_all_array(af_array *out, const af_array in);
+AFAPI af_err af_sum_nan_all_array(af_array *out, const af_array in, const double nanval);
+AFAPI af_err af_product_all_array(af_array *out, const af_array in);
+AFAPI af_err af_product_nan_all_array(af_array *out, const af_array in, const double nanval);
+AFAPI af_err af_min_all_array(af_array *out, const af_array in);
+AFAPI af_err af_max_all_array(af_array *out, const af_array in);
+AFAPI af_err af_count_all_array(af_array *out, const af_array in);
+AFAPI af_err af_all_true_all_array(af_array *out, const af_array in);
+AFAPI af_err af_any_true_all_array(af_array *out, const af_array in);
+
+/* ===================== hot path: index-returning reductions ============================
+ * src/api/c/reduce.cpp:994-1000 (ireduce_common :949-992), :1140-1148 (ireduce_all_common :1080-1138) */
+AFAPI af_err af_imin(af_array *out, af_array *idx, const af_array in, const int dim);
+AFAPI af_err af_imax(af_array *out, af_array *idx, const af_array in, const int dim);
+AFAPI af_err af_imin_all(double *real, double *imag, unsigned *idx, const af_array in);
+AFAPI af_err af_imax_all(double *real, double *imag, unsigned *idx, const af_array in);
+
+/* ===================== hot path: scans =================================================
+ * src/api/c/scan.cpp:118-157 (af_accum), :159-223 (af_scan), :225-283 (af_scan_by_key) */
+AFAPI af_err af_accum(af_array *out, const af_array in, const int dim);
+AFAPI af_err af_scan(af_array *out, const af_array in, const int dim, af_binary_op op, bool inclusive_scan);
+AFAPI af_err af_scan_by_key(af_array *out, const af_array key, const af_array in, const int dim, af_binary_op op,
+                            bool inclusive_scan);
+
+/* ===================== hot path: stream compaction =====================================
+ * src/api/c/where.cpp:34-65 */
+AFAPI af_err af_where(af_array *idx, const af_array in);
+
+/* ===================== array lifecycle around the path =================================
+ * src/api/c/array.cpp:39-475, data.cpp:45, index.cpp:84-124 */
+AFAPI af_err af_create_array(af_array *arr, const void *const data, const unsigned ndims, const dim_t *const dims,
+                             const af_dtype type);                                           /* array.cpp:39 */
+AFAPI af_err af_create_handle(af_array *arr, const unsigned ndims, const dim_t *const dims, const af_dtype type);
+AFAPI af_err af_copy_array(af_array *arr, const af_array in);
+AFAPI af_err af_write_array(af_array arr, const void *data, const size_t bytes, af_source src);
+AFAPI af_err af_get_data_ptr(void *data, const af_array arr);
+AFAPI af_err af_release_array(af_array arr);
+AFAPI af_err af_retain_array(af_array *out, const af_array in);
+AFAPI af_err af_get_data_ref_count(int *use_count, const af_array in);
+AFAPI af_err af_eval(af_array in);
+AFAPI af_err af_get_elements(dim_t *elems, const af_array arr);
+AFAPI af_err af_get_type(af_dtype *type, const af_array arr);
+AFAPI af_err af_get_dims(dim_t *d0, dim_t *d1, dim_t *d2, dim_t *d3, const af_array arr);
+AFAPI af_err af_get_numdims(unsigned *result, const af_array arr);
+AFAPI af_err af_is_empty(bool *result, const af_array arr);
+AFAPI af_err af_is_scalar(bool *result, const af_array arr);
+AFAPI af_err af_is_vector(bool *result, const af_array arr);
+AFAPI af_err af_get_scalar(void *output_value, const af_array arr);
+AFAPI af_err af_get_strides(dim_t *s0, dim_t *s1, dim_t *s2, dim_t *s3, const af_array arr);   /* internal.cpp */
+AFAPI af_err af_get_offset(dim_t *offset, const af_array arr);                               /* internal.cpp */
+AFAPI af_err af_is_linear(bool *result, const af_array arr);                                 /* internal.cpp */
+AFAPI af_err af_constant(af_array *arr, const double val, const unsigned ndims, const dim_t *const dims,
+                         const af_dtype type);                                               /* data.cpp:45 */
+AFAPI af_err af_index(af_array *out, const af_array in, const unsigned ndims, const af_seq *const index); /* index.cpp:84 */
+AFAPI af_err af_get_size_of(size_t *size, af_dtype type);
+
+/* ===================== device / memory / error =========================================
+ * src/api/c/device.cpp:57-405, memory.cpp:54-370, error.cpp:19-45, include/af/cuda.h:50-75 */
+AFAPI af_err af_init(void);
+AFAPI af_err af_info(void);
+AFAPI af_err af_info_string(char **str, const bool verbose);
+AFAPI af_err af_get_device_count(int *num_of_devices);
+AFAPI af_err af_set_device(const int device);
+AFAPI af_err af_get_device(int *device);
+AFAPI af_err af_sync(const int device);
+AFAPI af_err af_get_dbl_support(bool *available, const int device);
+AFAPI af_err af_get_half_support(bool *available, const int device);
+AFAPI af_err af_alloc_device(void **ptr, const dim_t bytes);
+AFAPI af_err af_free_device(void *ptr);
+AFAPI af_err af_alloc_device_v2(void **ptr, const dim_t bytes);
+AFAPI af_err af_free_device_v2(void *ptr);
+AFAPI af_err af_alloc_pinned(void **ptr, const dim_t bytes);
+AFAPI af_err af_free_pinned(void *ptr);
+AFAPI af_err af_alloc_host(void **ptr, const dim_t bytes);
+AFAPI af_err af_free_host(void *ptr);
+AFAPI af_err af_device_array(af_array *arr, void *data, const unsigned ndims, const dim_t *const dims,
+                             const af_dtype type);
+AFAPI af_err af_device_mem_info(size_t *alloc_bytes, size_t *alloc_buffers, size_t *lock_bytes, size_t *lock_buffers);
+AFAPI af_err af_print_mem_info(const char *msg, const int device_id);
+AFAPI af_err af_device_gc(void);
+AFAPI af_err af_set_mem_step_size(const size_t step_bytes);
+AFAPI af_err af_get_mem_step_size(size_t *step_bytes);
+AFAPI af_err af_lock_array(const af_array arr);
+AFAPI af_err af_unlock_array(const af_array arr);
+AFAPI af_err af_lock_device_ptr(const af_array arr);
+AFAPI af_err af_unlock_device_ptr(const af_array arr);
+AFAPI af_err af_is_locked_array(bool *res, const af_array arr);
+AFAPI af_err af_get_device_ptr(void **ptr, const af_array arr);
+AFAPI void af_get_last_error(char **msg, dim_t *len);                                        /* error.cpp:19-37 */
+AFAPI const char *af_err_to_string(const af_err err);                                        /* error.cpp:39-45 */
+AFAPI af_err af_get_version(int *major, int *minor, int *patch);
+AFAPI af_err af_get_backend_id(af_backend *backend, const af_array in);
+AFAPI af_err af_get_device_id(int *device, const af_array in);
+AFAPI af_err af_get_active_backend(af_backend *backend);
+AFAPI af_err af_get_backend_count(unsigned *num_backends);
+AFAPI af_err af_get_available_backends(int *backends);
+AFAPI af_err af_set_backend(const af_backend bknd);
+AFAPI af_err afcu_get_stream(void **stream /* cudaStream_t* */, int id);                     /* cuda.h:50 */
+AFAPI af_err afcu_get_native_id(int *nativeid, int id);                                      /* cuda.h:63 */
+AFAPI af_err afcu_set_native_id(int nativeid);                                               /* cuda.h:75 */
+
+/* ===================== afx_*: sharded whole-array extension ============================
+ * New functionality (the reference has no multi-GPU path).  One process
+ * per GPU holds the shard [rank*N/G, (rank+1)*N/G) of a flattened array; each call below
+ * computes the shard-local piece ON THE DEVICE, leaving its O(1) partial in `partial`
+ * (device memory, so the host layer can hand it to NCCL without a sync). */
+
+/* partial <- whole-shard reduction with the promoted accumulation type of af_<op>_all;
+ * op: 0 sum, 1 product, 2 min, 3 max, 4 count, 5 all_true, 6 any_true.  *partial_type gets its dtype. */
+AFAPI af_err afx_reduce_all_partial(void *partial, af_dtype *partial_type, const af_array in, int op,
+                                    bool change_nan, double nanval);
+/* (value, shard-local linear index) of imin (op 2) / imax (op 3) over the shard */
+AFAPI af_err afx_ireduce_all_partial(void *partial_val, unsigned *partial_idx, const af_array in, int op);
+/* scan along dim 0 of a 1-D shard whose running value BEFORE the shard is *carry (device pointer to one
+ * element of the output dtype, or NULL for the identity).  With `key` non-NULL it is a segmented scan and
+ * the carry applies only while the key equals *carry_key (the last key of the previous shard). */
+AFAPI af_err afx_scan_shard(af_array *out, const af_array key, const af_array in, af_binary_op op,
+                            bool inclusive_scan, const void *carry, const void *carry_key);
+/* af_where over a shard with every index offset by `base` (= rank*N/G); returns the hit count too */
+AFAPI af_err afx_where_shard(af_array *idx, dim_t *count, const af_array in, unsigned base);
+/* number of CUDA kernels this library launched on the calling thread's device since the last reset */
+AFAPI af_err afx_launch_count(unsigned long long *count, bool reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFB200_H */

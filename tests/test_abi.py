@@ -1,0 +1,85 @@
+"""C-ABI checks that need no GPU: libafb200.so loads and exports every symbol include/afb200.h declares,
+argument validation that happens before any device work returns the reference's error codes, and the
+product never links or loads anything under oracle/."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HDR = os.path.join(ROOT, "include", "afb200.h")
+LIB = os.path.join(ROOT, "arrayfire_b200", "libafb200.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    return ctypes.CDLL(LIB)
+
+
+def declared_symbols():
+    text = open(HDR).read()
+    return sorted(set(re.findall(r"AFAPI\s+[\w\s\*]+?\b(af[xcu]*_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_hot_path():
+    syms = declared_symbols()
+    for s in ("af_sum", "af_sum_nan", "af_product", "af_min", "af_max", "af_count", "af_all_true", "af_any_true",
+              "af_sum_all", "af_min_all", "af_max_all", "af_count_all", "af_sum_all_array", "af_imin", "af_imax",
+              "af_imin_all", "af_imax_all", "af_accum", "af_scan", "af_scan_by_key", "af_where", "af_create_array",
+              "af_release_array", "af_get_data_ptr", "af_index", "af_get_last_error", "afcu_get_stream"):
+        assert s in syms, s
+    assert len(syms) > 100
+
+
+def test_library_exports_every_declared_symbol(lib):
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_no_extra_dependencies_on_the_oracle(lib):
+    out = subprocess.check_output(["ldd", LIB]).decode()
+    assert "oracle" not in out and "afref" not in out
+    for src in os.listdir(os.path.join(ROOT, "arrayfire_b200", "csrc")):
+        p = os.path.join(ROOT, "arrayfire_b200", "csrc", src)
+        if os.path.isfile(p):
+            assert "oracle" not in open(p).read().replace("parity oracle", ""), src
+    assert "oracle" not in open(os.path.join(ROOT, "arrayfire_b200", "__init__.py")).read()
+
+
+def test_error_codes_without_a_device(lib):
+    """null handles / bad args are rejected before any CUDA call, with the reference's af_err values"""
+    lib.af_err_to_string.restype = ctypes.c_char_p
+    out = ctypes.c_void_p()
+    assert lib.af_sum(ctypes.byref(out), None, 0) == 202          # AF_ERR_ARG: null array
+    assert lib.af_sum(ctypes.byref(out), None, 7) == 202          # dim out of range
+    assert lib.af_release_array(None) == 0                        # releasing a null handle is fine
+    msg, n = ctypes.c_char_p(), ctypes.c_longlong()
+    lib.af_sum(ctypes.byref(out), None, 9)
+    lib.af_get_last_error.restype = None
+    lib.af_get_last_error(ctypes.byref(msg), ctypes.byref(n))
+    assert n.value > 0 and b"invalid argument" in msg.value
+    lib.af_get_last_error(ctypes.byref(msg), ctypes.byref(n))     # fetched + cleared
+    assert n.value == 0
+    assert lib.af_err_to_string(204) == b"Function does not support this data type"
+    maj, mi, pa = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.af_get_version(ctypes.byref(maj), ctypes.byref(mi), ctypes.byref(pa)) == 0 and (maj.value, mi.value) == (3, 10)
+
+
+def test_no_cpu_fallback(lib):
+    """without a usable CUDA device the product fails loudly (AF_ERR_DRIVER), it never computes on the CPU"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    arr = ctypes.c_void_p()
+    dims = (ctypes.c_longlong * 1)(4)
+    data = (ctypes.c_float * 4)(1, 2, 3, 4)
+    assert lib.af_create_array(ctypes.byref(arr), data, 1, dims, 0) == 102  # AF_ERR_DRIVER
+    assert lib.af_init() == 102

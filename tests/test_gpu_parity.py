@@ -1,0 +1,289 @@
+"""`-m gpu` parity tests: the CUDA path, called through the C-ABI of libafb200.so, against the oracle.
+
+Bit-exact for integer/byte/index work, min/max values, ireduce indices, count/where output and integer
+scans.  Floating-point sums/scans are checked (a) BIT-EXACT on inputs whose every partial sum is exactly
+representable (any association order then gives the same bits), and (b) within 1e-5 (f32) / 1e-12 (f64)
+relative of an f64/long-double truth on generic data -- the tolerances BASELINE.json's north_star states.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.gpu_util import gpu_available, rand_data, random_subview, same_bits, to_gpu
+
+pytestmark = pytest.mark.gpu
+
+ALL = [po.F32, po.F64, po.C32, po.C64, po.S32, po.U32, po.S64, po.U64, po.S16, po.U16, po.S8, po.U8, po.B8, po.F16]
+NOHALF = [c for c in ALL if c != po.F16]
+IS_FLOAT = {po.F32, po.F64, po.C32, po.C64, po.F16}
+
+# shapes chosen to hit every kernel regime (see arrayfire_b200/csrc/kernels/*_host.cuh)
+SHAPES_SMALL = [(1,), (7,), (1000,), (5, 3), (1, 9), (33, 1, 4), (4, 5, 3, 2), (2, 1, 1, 3), (257, 70), (40, 300)]
+SHAPES_BIG = [(70001,), (5000, 3), (3000, 100), (200003, 3), (130, 1000), (4, 50001), (96, 64, 2, 3), (1 << 20,)]
+
+
+@pytest.fixture(scope="module")
+def af():
+    if not gpu_available():
+        pytest.skip("no CUDA device")
+    import arrayfire_b200
+    return arrayfire_b200
+
+
+@pytest.fixture(scope="module")
+def orc(port_oracle):
+    return port_oracle
+
+
+def views_of(rng, base):
+    yield base, None
+    if base.size > 1:
+        sl = random_subview(rng, base.shape)
+        if base[sl].size:
+            yield base[sl], sl
+
+
+def d4(a):
+    return a.reshape(po.dims4(a.shape), order="F")
+
+
+@pytest.mark.parametrize("code", ALL)
+def test_reduce_dimwise_small(af, orc, code):
+    rng = np.random.default_rng(1000 + code)
+    for shape in SHAPES_SMALL:
+        base = rand_data(rng, code, shape, nan_frac=0.1, exact=True)
+        for x, sl in views_of(rng, base):
+            g = to_gpu(af, base, sl, dtype=code)
+            for dim in range(4):
+                for name in ("sum", "product", "min", "max", "count", "all_true", "any_true"):
+                    if name == "product" and code in IS_FLOAT:
+                        continue  # long float products are not exactly representable; see test_float_sum_accuracy
+                    t, want = getattr(orc, name)(x, dim, dtype=code)
+                    got = getattr(af, name)(g, dim)
+                    assert got.dtype == t, (name, shape, dim)
+                    same_bits(got.to_numpy(), d4(want), "%s %s dim%d view=%s" % (name, shape, dim, sl))
+                t, want = orc.sum_nan(x, dim, 2.0, dtype=code)
+                same_bits(af.sum(g, dim, nanval=2.0).to_numpy(), d4(want), "sum_nan %s dim%d" % (shape, dim))
+
+
+@pytest.mark.parametrize("code", [po.F32, po.S32, po.U8, po.F64, po.S16, po.C32, po.B8, po.U64])
+def test_reduce_dimwise_big(af, orc, code):
+    rng = np.random.default_rng(2000 + code)
+    for shape in SHAPES_BIG:
+        base = rand_data(rng, code, shape, nan_frac=0.01, exact=True)
+        for x, sl in views_of(rng, base):
+            g = to_gpu(af, base, sl, dtype=code)
+            for dim in range(len(shape)):
+                for name in ("sum", "min", "max", "count", "any_true", "all_true"):
+                    t, want = getattr(orc, name)(x, dim, dtype=code)
+                    got = getattr(af, name)(g, dim)
+                    assert got.dtype == t
+                    same_bits(got.to_numpy(), d4(want), "%s %s dim%d view=%s" % (name, shape, dim, sl))
+
+
+@pytest.mark.parametrize("code", ALL)
+def test_reduce_all(af, orc, code):
+    rng = np.random.default_rng(3000 + code)
+    for shape in SHAPES_SMALL + [(70001,), (300, 1000), (1 << 21,)]:
+        base = rand_data(rng, code, shape, nan_frac=0.0, exact=True)
+        for x, sl in views_of(rng, base):
+            g = to_gpu(af, base, sl, dtype=code)
+            for name in ("sum_all", "min_all", "max_all", "count_all", "all_true_all", "any_true_all"):
+                t, want = getattr(orc, name)(x, dtype=code)
+                got = getattr(af, name)(g)
+                w = want[0]
+                if code in (po.C32, po.C64) and name in ("sum_all", "min_all", "max_all"):
+                    assert got == complex(w), (name, shape, got, w)
+                else:
+                    assert got == float(np.real(w)), (name, shape, got, w)
+            # *_all_array keeps the promoted dtype (no trip through double)
+            t, want = orc.sum_all(x, dtype=code, scalar_api=False)
+            arr = af.sum_all_array(g)
+            assert arr.dtype == t and arr.dims == (1, 1, 1, 1)
+            same_bits(arr.to_numpy().reshape(1), want, "sum_all_array %s" % (shape,))
+
+
+@pytest.mark.parametrize("code", [po.F32, po.F64, po.C32, po.F16])
+def test_float_sum_accuracy(af, orc, code):
+    """generic data: within 1e-5 (f32, f16->f32) / 1e-12 (f64) relative of a high-precision truth."""
+    rng = np.random.default_rng(4000 + code)
+    n = 1 << 22
+    if code == po.C32:
+        x = (rng.random(n) + 1j * rng.random(n)).astype(np.complex64)
+        truth = complex(np.sum(x.real.astype(np.float64)), np.sum(x.imag.astype(np.float64)))
+    else:
+        x = rng.random(n).astype(po.NP_OF[code])
+        truth = float(np.sum(x.astype(np.longdouble)))
+    got = af.sum_all(af.Array.from_numpy(x, dtype=code))
+    tol = 1e-12 if code == po.F64 else 1e-5
+    assert abs(got - truth) <= tol * abs(truth), (got, truth)
+    m = np.asfortranarray(x.reshape((1 << 11, 1 << 11), order="F"))
+    for dim in (0, 1):
+        got = af.sum(af.Array.from_numpy(m, dtype=code), dim).to_numpy().reshape(-1)
+        want = m.astype(np.complex128 if code == po.C32 else np.float64).sum(axis=dim)
+        np.testing.assert_allclose(got.astype(want.dtype), want, rtol=tol)
+        sc = af.accum(af.Array.from_numpy(m, dtype=code), dim).to_numpy() if code != po.F16 else None
+        if sc is not None:
+            want = np.cumsum(m.astype(np.complex128 if code == po.C32 else np.float64), axis=dim)
+            np.testing.assert_allclose(sc.reshape(m.shape, order="F").astype(want.dtype), want, rtol=tol * 4)
+    if code == po.C32:
+        p = (0.5 + rng.random(64) + 0.1j).astype(np.complex64)
+    else:
+        p = (0.5 + rng.random(64)).astype(po.NP_OF[code])
+    got = af.product_all(af.Array.from_numpy(p, dtype=code))
+    want = np.prod(p.astype(np.complex128 if code == po.C32 else np.float64))
+    assert abs(got - want) <= 1e-4 * abs(want)
+
+
+@pytest.mark.parametrize("code", ALL)
+def test_ireduce(af, orc, code):
+    rng = np.random.default_rng(5000 + code)
+    for shape in SHAPES_SMALL + [(70001,), (5000, 3), (130, 1000), (4, 50001)]:
+        for nan_frac in (0.0, 0.3):
+            if nan_frac and code not in IS_FLOAT:
+                continue
+            base = rand_data(rng, code, shape, nan_frac=nan_frac, small=True)
+            for x, sl in views_of(rng, base):
+                g = to_gpu(af, base, sl, dtype=code)
+                for dim in range(4):
+                    for name in ("imin", "imax"):
+                        t, wv, wl = getattr(orc, name)(x, dim, dtype=code)
+                        gv, gl = getattr(af, name)(g, dim)
+                        assert gv.dtype == t and gl.dtype == po.U32
+                        same_bits(gl.to_numpy(), d4(wl), "%s idx %s dim%d view=%s" % (name, shape, dim, sl))
+                        same_bits(gv.to_numpy(), d4(wv), "%s val %s dim%d view=%s" % (name, shape, dim, sl))
+                if code != po.F16:
+                    for name in ("imin_all", "imax_all"):
+                        wv, wl = getattr(orc, name)(x, dtype=code)
+                        gv, gl = getattr(af, name)(g)
+                        assert gl == wl, (name, shape, sl, gl, wl)
+                        assert gv == (complex(wv) if code in (po.C32, po.C64) else float(wv)), (name, shape)
+
+
+def test_ireduce_all_nan_rows(af, orc):
+    """all-NaN lines return (identity, 0); a NaN seed with later values behaves like the serial loop"""
+    x = np.full((5, 4), np.nan, np.float32, order="F")
+    x[2, 1] = 3.0
+    x[4, 2] = np.inf
+    x[0, 3] = -np.inf
+    g = af.Array.from_numpy(x)
+    for name in ("imin", "imax"):
+        for dim in (0, 1):
+            t, wv, wl = getattr(orc, name)(x, dim)
+            gv, gl = getattr(af, name)(g, dim)
+            same_bits(gl.to_numpy(), d4(wl), name)
+            same_bits(gv.to_numpy(), d4(wv), name)
+
+
+@pytest.mark.parametrize("code", NOHALF)
+def test_scan(af, orc, code):
+    rng = np.random.default_rng(6000 + code)
+    shapes = SHAPES_SMALL + [(70001,), (5000, 3), (130, 1000), (3, 20000), (2, 3, 5000)]
+    for shape in shapes:
+        base = rand_data(rng, code, shape, nan_frac=0.05, exact=True)
+        for x, sl in views_of(rng, base):
+            g = to_gpu(af, base, sl, dtype=code)
+            for dim in range(4):
+                t, want = orc.accum(x, dim, dtype=code)
+                got = af.accum(g, dim)
+                assert got.dtype == t
+                same_bits(got.to_numpy(), d4(want), "accum %s dim%d view=%s" % (shape, dim, sl))
+                for op in range(4):
+                    if op == po.AF_BINARY_MUL and (code in IS_FLOAT):
+                        continue
+                    for incl in (True, False):
+                        t, want = orc.scan(x, dim, op, incl, dtype=code)
+                        got = af.scan(g, dim, op, incl)
+                        assert got.dtype == t
+                        same_bits(got.to_numpy(), d4(want), "scan op%d incl%d %s dim%d view=%s" % (op, incl, shape, dim, sl))
+
+
+@pytest.mark.parametrize("code", NOHALF)
+def test_scan_by_key(af, orc, code):
+    rng = np.random.default_rng(7000 + code)
+    shapes = [(1,), (7,), (1000,), (5, 3), (33, 1, 4), (4, 5, 3, 2), (70001,), (5000, 3), (130, 1000), (3, 20000)]
+    for shape in shapes:
+        base = rand_data(rng, code, shape, nan_frac=0.05, exact=True)
+        n = int(np.prod(shape))
+        for kcode in (po.S32, po.U64):
+            # runs of random length so segments cross vector / warp / tile boundaries
+            runs = rng.integers(1, 40 if n < 5000 else 3000, n)
+            keys = np.repeat(rng.integers(0, 5, n), runs)[:n].astype(po.NP_OF[kcode])
+            keys = np.asfortranarray(keys.reshape(shape, order="F"))
+            sl = random_subview(rng, shape) if n > 1 else None
+            for xs in (None, sl):
+                if xs is None and sl is None and False:
+                    continue
+                x = base if xs is None else base[xs]
+                k = keys if xs is None else keys[xs]
+                if x.size == 0:
+                    continue
+                g = to_gpu(af, base, xs, dtype=code)
+                gk = to_gpu(af, keys, xs, dtype=kcode)
+                for dim in range(min(len(shape), 2) + 1):
+                    for op in (0, 2, 3):
+                        for incl in (True, False):
+                            t, want = orc.scan_by_key(k, x, dim, op, incl, dtype=code, key_dtype=kcode)
+                            got = af.scan_by_key(gk, g, dim, op, incl)
+                            assert got.dtype == t
+                            same_bits(got.to_numpy(), d4(want), "sbk op%d incl%d %s dim%d view=%s" % (op, incl, shape, dim, xs))
+                if sl is None:
+                    break
+
+
+@pytest.mark.parametrize("code", NOHALF)
+def test_where(af, orc, code):
+    rng = np.random.default_rng(8000 + code)
+    for shape in SHAPES_SMALL + [(70001,), (300, 1000), (1 << 21,)]:
+        for density in (0.5, 0.01, 0.0, 1.0):
+            base = rand_data(rng, code, shape, nan_frac=0.0, small=True)
+            mask = rng.random(base.shape) < density
+            one = np.ones((), base.dtype)
+            base = np.asfortranarray(np.where(mask, np.where(base == 0, one, base), 0 * one).astype(base.dtype))
+            for x, sl in views_of(rng, base):
+                g = to_gpu(af, base, sl, dtype=code)
+                want = orc.where(x, dtype=code)
+                got = af.where(g)
+                assert got.dtype == po.U32 and got.dims == (want.size, 1, 1, 1), (shape, density, got.dims, want.size)
+                same_bits(got.to_numpy().reshape(-1), want, "where %s p=%g view=%s" % (shape, density, sl))
+                assert af.count_all(g) == want.size
+
+
+def test_where_nan_counts_as_nonzero(af, orc):
+    x = np.array([0, np.nan, 1, 0, -0.0, np.inf], np.float32)
+    got = af.where(af.Array.from_numpy(x)).to_numpy().reshape(-1)
+    assert got.tolist() == orc.where(x).tolist() == [1, 2, 5]
+
+
+def test_argument_errors(af):
+    a = af.Array.from_numpy(np.ones((4, 3), np.float32, order="F"))
+    for fn in (af.sum, af.min, af.count, af.accum):
+        with pytest.raises(af.AfError) as e:
+            fn(a, 4)
+        assert e.value.code == 202  # AF_ERR_ARG
+    with pytest.raises(af.AfError) as e:
+        af.scan(a, 0, 7, True)
+    assert e.value.code == 202
+    k = af.Array.from_numpy(np.ones((4, 2), np.int32, order="F"))
+    with pytest.raises(af.AfError) as e:
+        af.scan_by_key(k, a, 0)
+    assert e.value.code == 202  # key dims must match
+    kf = af.Array.from_numpy(np.ones((4, 3), np.float32, order="F"))
+    with pytest.raises(af.AfError) as e:
+        af.scan_by_key(kf, a, 0)
+    assert e.value.code == 204  # AF_ERR_TYPE: float keys
+    h = af.Array.from_numpy(np.ones(4, np.float16))
+    with pytest.raises(af.AfError) as e:
+        af.where(h)
+    assert e.value.code == 204
+    with pytest.raises(af.AfError) as e:
+        af.imax_all(h)
+    assert e.value.code == 204
+    # dim >= ndims returns the input unpromoted
+    u = af.Array.from_numpy(np.arange(6, dtype=np.uint8).reshape((2, 3), order="F"))
+    r = af.sum(u, 2)
+    assert r.dtype == po.U8 and r.dims == (2, 3, 1, 1)
+    # empty input
+    e0 = af.Array.from_numpy(np.zeros((0,), np.float32))
+    assert af.where(e0).elements == 0 and af.sum_all(e0) == 0.0 and af.product_all(e0) == 1.0
+    assert af.sum(e0, 0).elements == 0
