@@ -24,6 +24,10 @@ inline void reduce_one(const LaunchCtx &c, const View &in, int dim, bool all, bo
     X(f32, float) X(f64, double) X(c32, cfloat) X(c64, cdouble) X(s32, int) X(u32, uint) X(s64, intl) \
     X(u64, uintl) X(s16, short) X(u16, ushort) X(s8, schar) X(u8, uchar) X(b8, b8_t) X(f16, __half)
 
+#define AFB_REAL_TYPES(X)                                                                             \
+    X(f32, float) X(f64, double) X(s32, int) X(u32, uint) X(s64, intl) X(u64, uintl) X(s16, short)    \
+    X(u16, ushort) X(s8, schar) X(u8, uchar) X(b8, b8_t) X(f16, __half)
+
 #define AFB_SUM_PAIRS(X)                                                                              \
     X(f32, float, f32, float) X(f64, double, f64, double) X(c32, cfloat, c32, cfloat)                 \
     X(c64, cdouble, c64, cdouble) X(s32, int, s32, int) X(u32, uint, u32, uint) X(s64, intl, s64, intl) \

@@ -76,7 +76,9 @@ template<int OP, typename T> struct ArgPolicy {
     typedef Arg<T> Acc;
     typedef ArgParams Params;
     struct Out { T *val; uint *loc; };
-    // "no candidate yet": loses every tie against a real element (ireduce)
+    // Internally element i carries rank i+1, so that "no candidate yet" (rank 0 for min, UINT_MAX for max)
+    // loses every tie against a real element -- distinct values can share an ordering key (b8 compares
+    // `v > 0`, 64-bit integers compare as double, complex compares magnitudes).
     AFB_DI static Acc init() {
         if (OP == OP_MIN) return Acc{Lim<T>::hi(), 0u};
         return Acc{Lim<T>::lo(), 0xffffffffu};
@@ -84,22 +86,51 @@ template<int OP, typename T> struct ArgPolicy {
     AFB_DI static Acc load(const Params &, In x, uint idx) {
         if (is_nan<T>(x)) {
             // NaN candidates never win; only the seed (position 0) turns into the identity at index 0
-            if (idx == 0) return Acc{OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(), 0u};
+            if (idx == 0) return Acc{OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(), 1u};
             return init();
         }
-        return Acc{x, idx};
+        return Acc{x, idx + 1u};
     }
     AFB_DI static Acc join(Acc a, Acc b) {
         const double ka = order_key<T>(a.val), kb = order_key<T>(b.val);
         bool take_b;
-        if (OP == OP_MIN) take_b = (kb < ka) || (kb == ka && b.idx > a.idx);
-        else take_b = (kb > ka) || (kb == ka && b.idx < a.idx);
+        if (OP == OP_MIN) take_b = (kb < ka) || (kb == ka && b.idx > a.idx);   // min keeps the LAST equal position
+        else take_b = (kb > ka) || (kb == ka && b.idx < a.idx);                // max keeps the FIRST
         return take_b ? b : a;
     }
     AFB_DI static void store(const Out &o, size_t i, Acc a) {
         o.val[i] = a.val;
-        o.loc[i] = a.idx;
+        o.loc[i] = a.idx - 1u;
     }
+    AFB_DI static Acc fold16(const Params &p, Acc acc, const Vec16 &v, uint idx0) {
+        constexpr int V = VecN<In>::value;
+        const In *e = reinterpret_cast<const In *>(&v);
+#pragma unroll
+        for (int k = 0; k < V; k++) acc = join(acc, load(p, e[k], idx0 + k));
+        return acc;
+    }
+};
+
+// Complex min / max: the reference keeps the running value on a magnitude tie
+// (`abs(x) < abs(acc) ? x : acc`, cpu/math.cpp:30-40), i.e. the FIRST element of smallest/largest magnitude --
+// and the identity itself if nothing beats it.  A parallel reduction reproduces that by carrying the position:
+// ties go to the smaller position, the identity sits at position 0 and element i at position i+1.
+template<int OP, typename T> struct FirstPolicy {
+    typedef T In;
+    typedef Arg<T> Acc;
+    typedef ValParams Params;
+    struct Out { T *val; };
+    AFB_DI static T ident() { return OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(); }
+    AFB_DI static Acc init() { return Acc{ident(), 0u}; }
+    AFB_DI static Acc load(const Params &, In x, uint idx) { return Acc{is_nan<T>(x) ? ident() : x, idx + 1u}; }
+    AFB_DI static Acc join(Acc a, Acc b) {
+        const auto ka = mag(a.val), kb = mag(b.val);
+        bool take_b;
+        if (OP == OP_MIN) take_b = (kb < ka) || (kb == ka && b.idx < a.idx);
+        else take_b = (kb > ka) || (kb == ka && b.idx < a.idx);
+        return take_b ? b : a;
+    }
+    AFB_DI static void store(const Out &o, size_t i, Acc a) { o.val[i] = a.val; }
     AFB_DI static Acc fold16(const Params &p, Acc acc, const Vec16 &v, uint idx0) {
         constexpr int V = VecN<In>::value;
         const In *e = reinterpret_cast<const In *>(&v);
