@@ -214,6 +214,15 @@ class Array:
             _check(lib.af_get_data_ptr(_vp(out.ctypes.data), self.handle))
         return out
 
+    def host_into(self, out):
+        """array::host(ptr): copy into a caller-provided host buffer (e.g. pinned memory); synchronises."""
+        n = self.elements * _SIZE[self.dtype]
+        if out.nbytes < n or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("host buffer too small or not contiguous")
+        if n:
+            _check(lib.af_get_data_ptr(_vp(out.ctypes.data), self.handle))
+        return out
+
     def scalar(self):
         out = np.zeros(1, dtype=_NP[self.dtype])
         _check(lib.af_get_scalar(_vp(out.ctypes.data), self.handle))

@@ -308,7 +308,7 @@ bool sbk_promote(af_dtype ti, af_dtype *to) {
 
 // shared by af_scan_by_key and afx_scan_shard
 Array *scan_by_key_impl(const Array &key, const Array &in, int dim, int binop, bool inclusive, const void *carry,
-                        const void *carry_key) {
+                        const void *carry_key, void *summary = nullptr) {
     for (int i = 0; i < 4; i++) AFB_ARG(2, in.info.dims[i] == key.info.dims[i]);
     af_dtype to;
     if (!sbk_promote(in.info.type, &to)) AFB_TYPE_ERROR(1, in.info.type);
@@ -327,7 +327,7 @@ Array *scan_by_key_impl(const Array &key, const Array &in, int dim, int binop, b
     Holder res;
     res.a = new_array(to, in.info.dims);
     if (!launch_scan_by_key(c, (Op)binop, to, tk, view_of(key), view_of(*vals), dim, inclusive, res.a->data(), carry,
-                            carry_key))
+                            carry_key, summary))
         AFB_TYPE_ERROR(1, in.info.type);
     return res.release();
 }
@@ -510,6 +510,35 @@ af_err afx_scan_shard(af_array *out, const af_array key_h, const af_array in_h, 
         }
         *out = res.release();
     }
+    AFB_API_END
+}
+
+af_err afx_scan_shard_local(af_array *out, void *summary, const af_array key_h, const af_array in_h, af_binary_op op,
+                            bool inclusive_scan) {
+    AFB_API_BEGIN
+    AFB_ARG(0, out != nullptr);
+    AFB_ARG(1, summary != nullptr);
+    AFB_ARG(2, key_h != nullptr);
+    Array *in = from_handle(in_h);
+    Array *key = from_handle(key_h);
+    AFB_ARG(3, in->elements() > 0 && in->elements() == in->info.dims[0]);  // a 1-D shard
+    check_same_device(*in);
+    check_same_device(*key);
+    *out = scan_by_key_impl(*key, *in, 0, (int)op, inclusive_scan, nullptr, nullptr, summary);
+    AFB_API_END
+}
+
+af_err afx_scan_shard_fixup(af_array out_h, const void *carry, dim_t count, af_binary_op op) {
+    AFB_API_BEGIN
+    AFB_ARG(1, carry != nullptr);
+    AFB_ARG(3, (int)op >= 0 && (int)op <= 3);
+    Array *out = from_handle(out_h);
+    AFB_ARG(2, count >= 0 && count <= out->elements());
+    AFB_ARG(0, out->is_linear());
+    check_same_device(*out);
+    OpLock lk(out->device());
+    LaunchCtx c = ctx_for_active_device();
+    if (!launch_scan_fixup(c, (Op)op, out->info.type, out->data(), count, carry)) AFB_TYPE_ERROR(0, out->info.type);
     AFB_API_END
 }
 

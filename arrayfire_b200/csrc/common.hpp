@@ -176,7 +176,9 @@ bool launch_ireduce_all(const LaunchCtx &c, Op op, af_dtype t, const View &in, v
 bool launch_scan(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool inclusive,
                  void *out, const void *carry);
 bool launch_scan_by_key(const LaunchCtx &c, Op op, af_dtype t, af_dtype tk, const View &key, const View &in, int dim,
-                        bool inclusive, void *out, const void *carry, const void *carry_key);
+                        bool inclusive, void *out, const void *carry, const void *carry_key, void *summary);
+// out[i] = op(*carry_host, out[i]) for i < count, in place (cross-shard fix-up of a by-key scan)
+bool launch_scan_fixup(const LaunchCtx &c, Op op, af_dtype t, void *out, dim_t count, const void *carry_host);
 // writes hit indices (+base) to `out` (capacity = elements) and the count to *d_count (device, 8 bytes)
 bool launch_where(const LaunchCtx &c, af_dtype t, const View &in, unsigned *out, unsigned long long *d_count,
                   unsigned base);

@@ -10,7 +10,7 @@ inline bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintp
 
 template<int OP, typename Ti, typename To, bool KEYED, typename Tk>
 void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool inclusive, void *out,
-              const void *carry, const void *carry_key) {
+              const void *carry, const void *carry_key, void *summary) {
     typedef Rule<OP, Ti, To> R;
     typedef SOps<R, To, KEYED> S;
     typedef typename S::State State;
@@ -21,7 +21,7 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
         constexpr int E = ScanVec<Ti, To>::value;
         constexpr dim_t TILE = (dim_t)kScanThreads * kScanSlots * E;
         const dim_t short_len = env_int("AFB200_SHORT_SCAN", 1024);
-        if (!carry && g.len <= short_len && g.ncols >= 32) {
+        if (!carry && !summary && g.len <= short_len && g.ncols >= 32) {
             WarpScanArgs<Ti, To, Tk> a;
             a.in = (const Ti *)in.ptr;
             a.key = KEYED ? (const Tk *)key->ptr : nullptr;
@@ -68,6 +68,12 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
         a.tile_counter = c.scratch->tile_counter;
         a.carry = (const To *)carry;
         a.carry_key = (const Tk *)carry_key;
+        a.summary = (g.ncols == 1) ? summary : nullptr;
+        if (a.summary && carry) fail(AF_ERR_INTERNAL, "scan: shard summary and carry-in are mutually exclusive");
+        if (a.summary) {  // the last tile writes the tail; first_head starts as "none" (~0)
+            AFB_CUDA(cudaMemsetAsync(summary, 0, 24, c.stream));
+            AFB_CUDA(cudaMemsetAsync((char *)summary + 24, 0xff, 8, c.stream));
+        }
         lookback_kernel<OP, Ti, To, KEYED, Tk><<<(unsigned)a.ntiles, kScanThreads, 0, c.stream>>>(a);
         note_launches(1);
         post_launch_check("lookback_kernel");
@@ -121,7 +127,7 @@ bool scan_family(const LaunchCtx &c, af_dtype ti, af_dtype to, const View &in, i
                  const void *carry) {
 #define X(ci, Ti, co, To)                                                                         \
     if (ti == ci && to == co) {                                                                   \
-        run_scan<OP, Ti, To, false, int>(c, in, nullptr, dim, inclusive, out, carry, nullptr);    \
+        run_scan<OP, Ti, To, false, int>(c, in, nullptr, dim, inclusive, out, carry, nullptr, nullptr);    \
         return true;                                                                              \
     }
     AFB_SCAN_PAIRS(X)
@@ -132,13 +138,13 @@ bool scan_family(const LaunchCtx &c, af_dtype ti, af_dtype to, const View &in, i
 // keys are only compared for equality: s32/u32 share the 32-bit kernels, s64/u64 the 64-bit ones
 template<int OP>
 bool scan_by_key_family(const LaunchCtx &c, af_dtype t, af_dtype tk, const View &key, const View &in, int dim,
-                        bool inclusive, void *out, const void *carry, const void *carry_key) {
+                        bool inclusive, void *out, const void *carry, const void *carry_key, void *summary) {
     const bool k32 = (tk == s32 || tk == u32), k64 = (tk == s64 || tk == u64);
     if (!k32 && !k64) return false;
 #define X(code, T)                                                                                     \
     if (t == code) {                                                                                   \
-        if (k32) run_scan<OP, T, T, true, uint>(c, in, &key, dim, inclusive, out, carry, carry_key);   \
-        else run_scan<OP, T, T, true, uintl>(c, in, &key, dim, inclusive, out, carry, carry_key);      \
+        if (k32) run_scan<OP, T, T, true, uint>(c, in, &key, dim, inclusive, out, carry, carry_key, summary);   \
+        else run_scan<OP, T, T, true, uintl>(c, in, &key, dim, inclusive, out, carry, carry_key, summary);      \
         return true;                                                                                   \
     }
     AFB_SBK_VALS(X)
@@ -150,9 +156,9 @@ bool scan_add(const LaunchCtx &, af_dtype, af_dtype, const View &, int, bool, vo
 bool scan_mul(const LaunchCtx &, af_dtype, af_dtype, const View &, int, bool, void *, const void *);
 bool scan_min(const LaunchCtx &, af_dtype, af_dtype, const View &, int, bool, void *, const void *);
 bool scan_max(const LaunchCtx &, af_dtype, af_dtype, const View &, int, bool, void *, const void *);
-bool sbk_add(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *);
-bool sbk_mul(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *);
-bool sbk_min(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *);
-bool sbk_max(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *);
+bool sbk_add(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *, void *);
+bool sbk_mul(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *, void *);
+bool sbk_min(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *, void *);
+bool sbk_max(const LaunchCtx &, af_dtype, af_dtype, const View &, const View &, int, bool, void *, const void *, const void *, void *);
 
 }  // namespace afb

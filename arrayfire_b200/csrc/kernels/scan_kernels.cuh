@@ -116,6 +116,10 @@ struct LookbackArgs {
     uint *tile_counter;
     const To *carry;    // optional running value before position 0 (sharded scans; single column only)
     const Tk *carry_key;  // keyed: the carry applies while key == *carry_key
+    // optional shard summary (single column only), device memory, 32 bytes:
+    //   [0,16) reduction of the last open segment (whole shard for a plain scan), carry excluded
+    //   [16,20) u32: a segment head occurs in the shard   [24,32) u64: position of the first head (~0 if none)
+    void *summary;
 };
 
 template<int OP, typename Ti, typename To, bool KEYED, typename Tk>
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(kScanThreads) lookback_kernel(const LookbackAr
     constexpr int TILE = kScanThreads * U * E;
 
     __shared__ State sm_warp[kScanWarps];
+    __shared__ uint sm_head[kScanWarps];
     __shared__ State sm_tile_prefix;
     __shared__ uint sm_tile;
 
@@ -227,6 +232,14 @@ __global__ void __launch_bounds__(kScanThreads) lookback_kernel(const LookbackAr
 
     // ---- CTA level
     if (lane == 0) sm_warp[warp] = warp_total;
+    if (KEYED && a.summary) {  // first segment head of the tile, as an offset from tile_lo
+        uint first = 0xffffffffu;
+#pragma unroll
+        for (int u = U - 1; u >= 0; u--)
+            if (heads[u]) first = (uint)(warp * (U * 32 * E) + (u * 32 + lane) * E + (__ffs(heads[u]) - 1));
+        first = __reduce_min_sync(0xffffffffu, first);
+        if (lane == 0) sm_head[warp] = first;
+    }
     __syncthreads();
     State warp_excl = S::identity(), tile_total = S::identity();
 #pragma unroll
@@ -293,6 +306,24 @@ __global__ void __launch_bounds__(kScanThreads) lookback_kernel(const LookbackAr
             }
         }
         if (lane == 0) sm_tile_prefix = excl;
+        if (a.summary && lane == 0) {
+            if (KEYED) {
+                uint first = 0xffffffffu;
+#pragma unroll
+                for (int w = 0; w < kScanWarps; w++) first = min(first, sm_head[w]);
+                if (first != 0xffffffffu)
+                    atomicMin(reinterpret_cast<unsigned long long *>((char *)a.summary + 24),
+                              (unsigned long long)(tile_lo + first));
+            }
+            if (tcol == a.tiles_per_col - 1) {
+                // the state at the end of the shard (summary mode is launched without a carry-in)
+                const State fin = S::join(excl, tile_total);
+                *reinterpret_cast<Slot<To> *>(a.summary) = Slot<To>{S::value(fin)};
+                uint flag = 0;
+                if constexpr (KEYED) flag = fin.flag ? 1u : 0u;
+                *reinterpret_cast<uint *>((char *)a.summary + 16) = flag;
+            }
+        }
     }
     __syncthreads();
     const State before_warp = S::join(sm_tile_prefix, warp_excl);

@@ -137,6 +137,204 @@ class Group:
         import torch
         if self.world == 1:
             return payload.reshape(1, -1)
-        out = torch.empty((self.world, payload.numel()), dtype=torch.uint8, device=payload.device)
+        out = torch.empty(self.world * payload.numel(), dtype=torch.uint8, device=payload.device)
         self.dist.all_gather_into_tensor(out, payload)
+        return out.reshape(self.world, -1)
+
+
+# af_dtype code -> numpy dtype (b8 as int8), mirrors arrayfire_b200._NP without importing the library
+_NP_OF = {0: np.float32, 1: np.complex64, 2: np.float64, 3: np.complex128, 4: np.int8, 5: np.int32, 6: np.uint32,
+          7: np.uint8, 8: np.int64, 9: np.uint64, 10: np.int16, 11: np.uint16, 12: np.float16, 13: np.int8}
+_B8 = 4
+_BINOP_TO_RED = {0: OP_SUM, 1: OP_PRODUCT, 2: OP_MIN, 3: OP_MAX}
+SUMMARY_BYTES = 32   # layout of afx_scan_shard_local's summary, include/afb200.h
+PAYLOAD_BYTES = 64
+
+
+class LocalGpu:
+    """shard-local primitives on this rank's GPU: the afx_* entry points of libafb200 (include/afb200.h).
+    Every method leaves its O(1) partial in a uint8 torch tensor on the device, enqueued on the library's
+    stream, so the NCCL all-gather that follows needs no host synchronisation."""
+
+    def __init__(self):
+        import ctypes
+
+        import torch
+
+        import arrayfire_b200 as af
+        self.af, self.torch, self.ct = af, torch, ctypes
+        self.dev = torch.device("cuda", af.get_device())
+        self.stream = torch.cuda.ExternalStream(af.get_stream(), device=self.dev)
+
+    def payload(self):
+        return self.torch.zeros(PAYLOAD_BYTES, dtype=self.torch.uint8, device=self.dev)
+
+    def on_stream(self):
+        return self.torch.cuda.stream(self.stream)
+
+    def elements(self, a):
+        return a.elements
+
+    def dtype(self, a):
+        return a.dtype
+
+    def reduce_partial(self, buf, a, op):
+        """buf[0:16] <- reduction of the shard; returns the af_dtype code of the partial"""
+        af, ct = self.af, self.ct
+        t = ct.c_int()
+        af._check(af.lib.afx_reduce_all_partial(ct.c_void_p(buf.data_ptr()), ct.byref(t), a.handle, ct.c_int(op),
+                                                ct.c_bool(False), ct.c_double(0.0)))
+        return t.value
+
+    def ireduce_partial(self, buf, a, op):
+        """buf[0:16] <- value, buf[16:20] <- shard-local u32 index"""
+        af, ct = self.af, self.ct
+        af._check(af.lib.afx_ireduce_all_partial(ct.c_void_p(buf.data_ptr()), ct.c_void_p(buf.data_ptr() + 16), a.handle,
+                                                 ct.c_int(op)))
+
+    def scan_with_carry(self, a, binop, inclusive, carry_bytes):
+        """scan of the shard seeded with the running value of the lower ranks (host bytes or None)"""
+        af, ct = self.af, self.ct
+        h = ct.c_void_p()
+        carry_ptr = None
+        if carry_bytes is not None:
+            c = self.torch.frombuffer(bytearray(carry_bytes), dtype=self.torch.uint8).to(self.dev, non_blocking=False)
+            self._keep = c
+            carry_ptr = ct.c_void_p(c.data_ptr())
+        af._check(af.lib.afx_scan_shard(ct.byref(h), None, a.handle, ct.c_int(binop), ct.c_bool(inclusive), carry_ptr, None))
+        return af.Array(h)
+
+    def scan_by_key_local(self, buf, key, a, binop, inclusive):
+        """carry-less segmented scan; buf[0:32] <- summary, buf[32:40] <- first key, buf[40:48] <- last key"""
+        af, ct = self.af, self.ct
+        h = ct.c_void_p()
+        af._check(af.lib.afx_scan_shard_local(ct.byref(h), ct.c_void_p(buf.data_ptr()), key.handle, a.handle, ct.c_int(binop),
+                                              ct.c_bool(inclusive)))
+        kb = af._SIZE[key.dtype]
+        kv = self.bytes_view(key)
+        buf[32:32 + kb] = kv[:kb]
+        buf[40:40 + kb] = kv[-kb:]
+        return af.Array(h)
+
+    def scan_fixup(self, out, carry_bytes, count, binop):
+        af, ct = self.af, self.ct
+        raw = (ct.c_ubyte * 16)(*bytearray(carry_bytes.ljust(16, b"\0")))
+        af._check(af.lib.afx_scan_shard_fixup(out.handle, raw, ct.c_longlong(count), ct.c_int(binop)))
+
+    def where_shard(self, a, base):
+        af, ct = self.af, self.ct
+        h, n = ct.c_void_p(), ct.c_longlong()
+        af._check(af.lib.afx_where_shard(ct.byref(h), ct.byref(n), a.handle, ct.c_uint(base)))
+        return af.Array(h), n.value
+
+    def bytes_view(self, a):
+        """uint8 torch view of a linear array's device memory (no copy)"""
+        ptr = a.device_ptr()
+        a.unlock()
+        n = a.elements * self.af._SIZE[a.dtype]
+
+        class _Holder:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+        return self.torch.as_tensor(_Holder(), device=self.dev)
+
+    def host_scalar_payload(self, value_bytes):
+        buf = self.torch.zeros(PAYLOAD_BYTES, dtype=self.torch.uint8)
+        buf[:len(value_bytes)] = self.torch.frombuffer(bytearray(value_bytes), dtype=self.torch.uint8)
+        return buf.to(self.dev)
+
+
+class ShardedOps:
+    """Whole-array ops over an array sharded across the ranks of a process group.  `local` supplies the
+    shard-local primitives (LocalGpu in production; the CPU tests plug in an oracle-backed stand-in and the
+    gloo backend, tests/test_sharded_gloo.py) -- the packing, the all-gather and the rank-ordered combine
+    below are the same code in both cases."""
+
+    def __init__(self, dist=None, local=None):
+        self.local = local if local is not None else LocalGpu()
+        self.group = Group(dist)
+        self.rank, self.world = self.group.rank, self.group.world
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _gather(self, buf):
+        """[world, PAYLOAD_BYTES] uint8 numpy array of every rank's payload (one collective, one D2H)"""
+        with self.local.on_stream():
+            g = self.group.all_gather_bytes(buf)
+            return g.cpu().numpy()
+
+    # -- reductions ----------------------------------------------------------------------------------
+    def reduce_all(self, op, a):
+        """af_<op>_all over the global array; the scalar comes back as the promoted numpy type"""
+        buf = self.local.payload()
+        code = self.local.reduce_partial(buf, a, _AFX_OP[op])
+        g = self._gather(buf)
+        dt = np.dtype(_NP_OF[code])
+        parts = np.array([g[r, :dt.itemsize].view(dt)[0] for r in range(self.world)], dtype=dt)
+        return fold_partials(op, parts)
+
+    def ireduce_all(self, op, a, base):
+        """(value, GLOBAL u32 index) of af_imin_all / af_imax_all; `base` is this shard's global offset"""
+        buf = self.local.payload()
+        self.local.ireduce_partial(buf, a, _AFX_OP[op])
+        import torch
+        buf[24:32] = torch.frombuffer(bytearray(np.uint64(base).tobytes()), dtype=torch.uint8).to(buf.device)
+        g = self._gather(buf)
+        code = self.local.dtype(a)
+        dt = np.dtype(_NP_OF[code])
+        vals = [g[r, :dt.itemsize].view(dt)[0] for r in range(self.world)]
+        gidx = [int(g[r, 16:20].view(np.uint32)[0]) + int(g[r, 24:32].view(np.uint64)[0]) for r in range(self.world)]
+        v, i = fold_arg(op, vals, gidx, is_b8=(code == _B8))
+        return v, i & 0xffffffff
+
+    # -- scans -----------------------------------------------------------------------------------------
+    def scan(self, a, binop, inclusive):
+        """af_scan along the flattened axis: shard totals are exchanged first, then every shard is scanned
+        once with its carry-in (the second read of a shard that fits the 126 MB L2 is served from L2)."""
+        buf = self.local.payload()
+        red = _BINOP_TO_RED[binop]
+        code = self.local.reduce_partial(buf, a, _AFX_OP[red])
+        g = self._gather(buf)
+        dt = np.dtype(_NP_OF[code])
+        out_dt = np.dtype(_NP_OF[scan_out_type(self.local.dtype(a))])
+        totals = np.array([g[r, :dt.itemsize].view(dt)[0] for r in range(self.world)], dtype=dt).astype(out_dt)
+        carry = exclusive_fold(binop, totals, self.rank)
+        return self.local.scan_with_carry(a, binop, inclusive, None if carry is None else np.asarray(carry, out_dt).tobytes())
+
+    def scan_by_key(self, key, a, binop, inclusive):
+        """af_scan_by_key along the flattened axis: local carry-less scan, one all-gather of the shard
+        summaries, fix-up of the first segment only."""
+        buf = self.local.payload()
+        out = self.local.scan_by_key_local(buf, key, a, binop, inclusive)
+        g = self._gather(buf)
+        out_dt = np.dtype(_NP_OF[sbk_out_type(self.local.dtype(a))])
+        kdt = np.dtype(_NP_OF[self.local.dtype(key)])
+        tails = [g[r, :out_dt.itemsize].view(out_dt)[0] for r in range(self.world)]
+        single = [int(g[r, 16:20].view(np.uint32)[0]) == 0 for r in range(self.world)]
+        first_keys = [g[r, 32:32 + kdt.itemsize].view(kdt)[0] for r in range(self.world)]
+        last_keys = [g[r, 40:40 + kdt.itemsize].view(kdt)[0] for r in range(self.world)]
+        carry = segmented_carry(binop, np.asarray(tails, out_dt), single, first_keys, last_keys, self.rank)
+        if carry is not None:
+            first_head = int(g[self.rank, 24:32].view(np.uint64)[0])
+            count = min(first_head, self.local.elements(a))
+            self.local.scan_fixup(out, np.asarray(carry, out_dt).tobytes(), count, binop)
         return out
+
+    # -- compaction ------------------------------------------------------------------------------------
+    def where(self, a, base):
+        """af_where: returns (this shard's indices [global numbering], offset of the slice in the global
+        output, global hit count).  The output stays sharded."""
+        idx, n = self.local.where_shard(a, base)
+        g = self._gather(self.local.host_scalar_payload(np.int64(n).tobytes()))
+        counts = [int(g[r, :8].view(np.int64)[0]) for r in range(self.world)]
+        off, total = where_offsets(counts)
+        return idx, int(off[self.rank]), total
+
+
+_AFX_OP = {OP_SUM: 0, OP_PRODUCT: 1, OP_MIN: 2, OP_MAX: 3, OP_COUNT: 4, OP_ALL: 5, OP_ANY: 6}
+
+
+def scan_out_type(code):
+    """output dtype of af_scan / af_accum (/root/reference/src/api/c/scan.cpp:133-149)"""
+    return {10: 5, 13: 5, 11: 6, 7: 6, 4: 6}.get(code, code)
+
+
+sbk_out_type = scan_out_type  # af_scan_by_key casts narrow integers the same way (scan.cpp:244-276)

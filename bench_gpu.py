@@ -1,0 +1,380 @@
+"""bench_gpu.py -- the GPU arm of bench.py (kept separate so `bench.py --impl reference` never imports torch.cuda).
+
+Per rank: build the synthetic inputs of BASELINE.json's configs C1..C5 in HBM, run W warm-up steps and K timed
+steps of the suite through libafb200's C-ABI (arrayfire_b200), time them with CUDA events recorded on the
+library's own stream (afcu_get_stream), take the max over ranks, print ONE JSON line on rank 0.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+from bench import (OP_ORDER, SEED, ClockSampler, algorithmic_bytes, log, run_cpu, workload)
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+# ops whose dominant launch is span_kernel (the whole-array / long-column streaming reduction)
+SPAN_OPS = ["C3.sum_f32", "C3.sum_s32", "C3.imax_f32", "C1.sum_f32", "C5.count"]
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs, generated on the device (per rank: its shard of the sharded configs)
+# ------------------------------------------------------------------------------------------------
+def make_inputs(torch, w, rank, world, dev):
+    """returns dict of torch tensors (device).  Whole-array configs hold the rank's contiguous shard of the
+    GLOBAL array (strong scaling); C2 holds the rank's column / row block."""
+    from arrayfire_b200.sharded import shard_bounds
+    g = torch.Generator(device=dev)
+    g.manual_seed(SEED + 7919 * rank)
+
+    def small_ints(n):  # integer-valued floats in {-4..4}: every partial sum is exact
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        step = 1 << 28
+        for lo in range(0, n, step):
+            m = min(step, n - lo)
+            out[lo:lo + m] = torch.randint(-4, 5, (m,), generator=g, device=dev, dtype=torch.int8).to(torch.float32)
+        return out
+
+    def shard(n):
+        lo, hi = shard_bounds(n, world, rank)
+        return hi - lo, lo
+
+    d = {}
+    n1, b1 = shard(w["C1"]["n"])
+    d["x1"], d["x1_base"] = small_ints(n1), b1
+    rows, cols = w["C2"]["rows"], w["C2"]["cols"]
+    # dim-0 reductions keep whole columns: the rank owns a block of columns; dim-1 reductions a block of rows.
+    c_lo, c_hi = shard_bounds(cols, world, rank)
+    r_lo, r_hi = shard_bounds(rows, world, rank)
+    d["m2_cols"] = small_ints(rows * (c_hi - c_lo))          # column-major [rows, c_hi-c_lo]
+    d["m2_cols_dims"] = (rows, c_hi - c_lo)
+    d["m2_rows"] = small_ints((r_hi - r_lo) * cols)          # column-major [r_hi-r_lo, cols]
+    d["m2_rows_dims"] = (r_hi - r_lo, cols)
+    n3, b3 = shard(w["C3"]["n"])
+    d["x3"], d["x3_base"] = small_ints(n3), b3
+    i3 = torch.empty(n3, dtype=torch.int32, device=dev)
+    u3 = torch.empty(n3, dtype=torch.float32, device=dev)
+    step = 1 << 28
+    for lo in range(0, n3, step):
+        m = min(step, n3 - lo)
+        i3[lo:lo + m] = torch.randint(-1000, 1001, (m,), generator=g, device=dev, dtype=torch.int32)
+        u3[lo:lo + m] = torch.randint(0, 1 << 24, (m,), generator=g, device=dev, dtype=torch.int32).to(torch.float32) / float(1 << 24)
+    d["i3"], d["u3"] = i3, u3
+    n4, b4 = shard(w["C4"]["n"])
+    d["v4"] = torch.randint(-15, 15, (n4,), generator=g, device=dev, dtype=torch.int32)
+    nruns = n4 // 256 + 2
+    lens = torch.randint(1, 1025, (nruns,), generator=g, device=dev, dtype=torch.int64)
+    # run ids are globally distinct per rank except that the first run of rank r continues the last key of
+    # rank r-1 (a run crossing the shard boundary), so the cross-GPU carry path is exercised
+    ids = torch.arange(nruns, device=dev, dtype=torch.int32) + (rank * (nruns - 1))
+    d["k4"] = torch.repeat_interleave(ids, lens)[:n4].contiguous()
+    del lens, ids
+    n5, b5 = shard(w["C5"]["n"])
+    d["c5_base"] = b5
+    for name, p in (("m50", 0.5), ("m01", 0.01)):
+        out = torch.empty(n5, dtype=torch.uint8, device=dev)
+        for lo in range(0, n5, step):
+            m = min(step, n5 - lo)
+            nz = torch.randint(1, 256, (m,), generator=g, device=dev, dtype=torch.int16).to(torch.uint8)
+            keep = torch.rand(m, generator=g, device=dev) < p
+            out[lo:lo + m] = torch.where(keep, nz, torch.zeros_like(nz))
+        d[name] = out
+    torch.cuda.synchronize()
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# the suite: name -> callable returning (result object or None); device-resident inputs
+# ------------------------------------------------------------------------------------------------
+def build_suite(af, torch, d, rank, world, group):
+    A = af.Array
+    x1 = A.from_torch(d["x1"])
+    m2c = A.from_device_ptr(d["m2_cols"].data_ptr(), d["m2_cols_dims"], af.f32, keepalive=d["m2_cols"])
+    m2r = A.from_device_ptr(d["m2_rows"].data_ptr(), d["m2_rows_dims"], af.f32, keepalive=d["m2_rows"])
+    x3, i3, u3 = A.from_torch(d["x3"]), A.from_torch(d["i3"]), A.from_torch(d["u3"])
+    k4, v4 = A.from_torch(d["k4"]), A.from_torch(d["v4"])
+    m50, m01 = A.from_torch(d["m50"]), A.from_torch(d["m01"])
+    keep = [x1, m2c, m2r, x3, i3, u3, k4, v4, m50, m01]
+    if world == 1:
+        suite = {
+            "C1.sum_f32": lambda: af.sum_all(x1),
+            "C1.scan_f32": lambda: af.accum(x1, 0),
+            "C2.sum_dim0": lambda: af.sum(m2c, 0),
+            "C2.sum_dim1": lambda: af.sum(m2r, 1),
+            "C2.max_dim0": lambda: af.max(m2c, 0),
+            "C2.max_dim1": lambda: af.max(m2r, 1),
+            "C3.sum_f32": lambda: af.sum_all(x3),
+            "C3.sum_s32": lambda: af.sum_all(i3),
+            "C3.imax_f32": lambda: af.imax_all(u3),
+            "C4.scan_by_key_s32": lambda: af.scan_by_key(k4, v4, 0, af.AF_BINARY_ADD, False),
+            "C5.where_50": lambda: af.where(m50),
+            "C5.where_01": lambda: af.where(m01),
+            "C5.count": lambda: af.count_all(m50),
+        }
+    else:
+        from arrayfire_b200 import sharded as sh
+        ops = sh.ShardedOps(group)
+        suite = {
+            "C1.sum_f32": lambda: ops.reduce_all(sh.OP_SUM, x1),
+            "C1.scan_f32": lambda: ops.scan(x1, af.AF_BINARY_ADD, True),
+            "C2.sum_dim0": lambda: af.sum(m2c, 0),       # partitioned along the non-reduced axis: no communication
+            "C2.sum_dim1": lambda: af.sum(m2r, 1),
+            "C2.max_dim0": lambda: af.max(m2c, 0),
+            "C2.max_dim1": lambda: af.max(m2r, 1),
+            "C3.sum_f32": lambda: ops.reduce_all(sh.OP_SUM, x3),
+            "C3.sum_s32": lambda: ops.reduce_all(sh.OP_SUM, i3),
+            "C3.imax_f32": lambda: ops.ireduce_all(sh.OP_MAX, u3, d["x3_base"]),
+            "C4.scan_by_key_s32": lambda: ops.scan_by_key(k4, v4, af.AF_BINARY_ADD, False),
+            "C5.where_50": lambda: ops.where(m50, d["c5_base"]),
+            "C5.where_01": lambda: ops.where(m01, d["c5_base"]),
+            "C5.count": lambda: ops.reduce_all(sh.OP_COUNT, m50),
+        }
+    return suite, keep
+
+
+def where_count(res):
+    """hit count of a where result (single-GPU Array or sharded (Array, offset, total) tuple)"""
+    if isinstance(res, tuple):
+        return int(res[2])
+    return int(res.elements)
+
+
+# ------------------------------------------------------------------------------------------------
+# end-to-end arm: HOST buffers in, results read back to the host, all inside the timed region
+# ------------------------------------------------------------------------------------------------
+class E2E:
+    """The same suite through the public API with pinned HOST inputs: af_create_array (H2D) -> op ->
+    af_get_data_ptr / scalar (D2H) every step."""
+
+    def __init__(self, af, torch, d, world):
+        self.af, self.torch = af, torch
+        self.h = {}
+        for k in ("x1", "m2_cols", "m2_rows", "x3", "i3", "u3", "k4", "v4", "m50", "m01"):
+            t = torch.empty(d[k].shape, dtype=d[k].dtype, pin_memory=True)
+            t.copy_(d[k])
+            self.h[k] = t.numpy()
+        torch.cuda.synchronize()
+        self.dims = {"m2_cols": d["m2_cols_dims"], "m2_rows": d["m2_rows_dims"]}
+        n_out = max(d["v4"].numel(), d["m50"].numel(), d["x1"].numel())
+        self.out = torch.empty(n_out, dtype=torch.int32, pin_memory=True).numpy()  # landing zone for array results
+        self.h2d = 0
+        self.d2h = 0
+
+    def _up(self, k):
+        a = self.h[k]
+        self.h2d += a.nbytes
+        if k in self.dims:
+            a = a.reshape(self.dims[k], order="F")
+        return self.af.Array.from_numpy(a)
+
+    def _down(self, arr):
+        n = arr.elements * 4
+        self.d2h += n
+        arr.host_into(self.out.view(np.uint8)[:max(n, 1)])
+
+    def step(self):
+        af = self.af
+        self.h2d = self.d2h = 0
+        counts = {}
+        self._down(af.sum(self._up("m2_cols"), 0))
+        af.sum_all(self._up("x3")); self.d2h += 4
+        self._down(af.sum(self._up("m2_rows"), 1))
+        af.sum_all(self._up("i3")); self.d2h += 4
+        self._down(af.max(self._up("m2_cols"), 0))
+        af.imax_all(self._up("u3")); self.d2h += 8
+        self._down(af.max(self._up("m2_rows"), 1))
+        self._down(af.scan_by_key(self._up("k4"), self._up("v4"), 0, af.AF_BINARY_ADD, False))
+        x1 = self._up("x1")
+        af.sum_all(x1); self.d2h += 4
+        m50 = self._up("m50")
+        r = af.where(m50); counts["C5.where_50"] = r.elements; self._down(r)
+        self._down(af.accum(x1, 0))
+        r = af.where(self._up("m01")); counts["C5.where_01"] = r.elements; self._down(r)
+        af.count_all(m50); self.d2h += 4
+        return counts
+
+
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            log("bench.py: --gpus %d needs torchrun (one rank per GPU); running 1 GPU" % args.gpus)
+            args.gpus = 1
+        else:
+            args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the GPU arm has no CPU fallback; use --impl reference)")
+    # one visible device per process keeps libafb200's device 0 == this rank's GPU
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("AF_CUDA_DEFAULT_DEVICE", str(local))
+    import arrayfire_b200 as af
+    af.set_device(local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist
+    lib_stream = torch.cuda.ExternalStream(af.get_stream(local), device=dev)
+
+    w = workload(args.scale)
+    t0 = time.time()
+    d = make_inputs(torch, w, rank, world, dev)
+    log("[rank %d] inputs ready in %.1f s" % (rank, time.time() - t0))
+    suite, keep = build_suite(af, torch, d, rank, world, group)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    counts = {}
+    last = {}
+
+    def step(events=None):
+        for name in OP_ORDER:
+            if events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record(lib_stream)
+            r = suite[name]()
+            if events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(lib_stream)
+                events.append((name, e0, e1))
+            if name.startswith("C5.where"):
+                counts[name] = where_count(r)
+            last[name] = r
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    af.launch_count(reset=True)
+    events = []
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record(lib_stream)
+    for _ in range(args.steps):
+        step(events)
+    end.record(lib_stream)
+    barrier()
+    launches = af.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = start.elapsed_time(end)
+    per_op_ms = {}
+    for name, e0, e1 in events:
+        per_op_ms[name] = per_op_ms.get(name, 0.0) + e0.elapsed_time(e1)
+
+    # max over ranks (device time), where counts summed over ranks
+    if world > 1:
+        t = torch.tensor([ms_total] + [per_op_ms[n] for n in OP_ORDER], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
+        per_op_ms = {n: float(t[1 + i]) for i, n in enumerate(OP_ORDER)}
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    ab = algorithmic_bytes(w, counts)   # global sizes; counts are global totals in the sharded path
+    total_bytes = sum(ab.values())
+    value = total_bytes * args.steps / (ms_total * 1e-3) / 1e9
+    ops = {}
+    for n in OP_ORDER:
+        ms = per_op_ms[n] / args.steps
+        ops[n] = {"ms": round(ms, 4), "GBps": round(ab[n] / (ms * 1e-3) / 1e9, 1)}
+    peak, peak_src = measured_peak()
+    span_bytes = sum(ab[n] for n in SPAN_OPS)
+    span_ms = sum(per_op_ms[n] for n in SPAN_OPS) / args.steps
+    achieved = span_bytes / world / (span_ms * 1e-3) / 1e9   # per GPU
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None,
+                "kernel": "span_kernel (whole-array / long-column streaming reduction): " + ", ".join(SPAN_OPS),
+                "peak_source": peak_src, "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                "how": "algorithmic bytes of the span ops / CUDA-event time of those API calls (includes the scalar D2H)"}
+    prof = os.path.join(ROOT, "profiles", "r01_span_kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get("traffic_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end-to-end arm (host buffers) ------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        t0 = time.time()
+        runner = E2E(af, torch, d, world)
+        log("[rank %d] pinned host copies ready in %.1f s" % (rank, time.time() - t0))
+        ksteps = max(1, min(args.steps, 5))
+        runner.step()   # warm the pool for the host-path allocations
+        barrier()
+        t0 = time.perf_counter()
+        e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_start.record(lib_stream)
+        for _ in range(ksteps):
+            runner.step()
+        e_end.record(lib_stream)
+        barrier()
+        e_ms = e_start.elapsed_time(e_end)
+        if world > 1:
+            t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t[0])
+        # under N > 1 the e2e arm runs each rank's shard independently (no combine); bytes are per-rank sums
+        e_bytes = total_bytes if world == 1 else total_bytes
+        e2e = {"value": round(e_bytes * ksteps / (e_ms * 1e-3) / 1e9, 2), "unit": "GB/s",
+               "h2d_bytes_per_step": int(runner.h2d) * world, "d2h_bytes_per_step": int(runner.d2h) * world,
+               "steps": ksteps, "ms_per_step": round(e_ms / ksteps, 2),
+               "how": "pinned host inputs -> af_create_array (H2D) -> op -> af_get_data_ptr / scalar (D2H), every step"}
+        del runner
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu, _, _ = run_cpu(3, 1, 1.0 / 64, "reference CPU path (serial, 1 worker thread like libafcpu)")
+            cpu["value"] = round(cpu["value"], 3)
+        except Exception as ex:  # the checker is optional for the GPU arm
+            cpu = {"value": None, "unit": "GB/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        line = {
+            "metric": "effective_GBps_reduce_scan_where", "value": round(value, 1), "unit": "GB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/s32/u8",
+            "data": "synthetic",
+            "config": {"workload": "C1..C5 suite of BASELINE.json, every op once per step: sum+inclusive scan 2^26 f32; "
+                                   "sum/max dim0+dim1 8192x8192 f32; sum_all f32/s32 + imax_all f32 2^30; scan_by_key excl "
+                                   "add 2^28 s32; where 50%/1% + count 2^30 u8",
+                       "scale": args.scale, "l2": "every input (>=256 MiB) exceeds the 126 MB L2 and ops are interleaved so "
+                                                  "no input is re-read while resident",
+                       "sharding": "none" if world == 1 else "whole-array ops sharded along the flattened axis (global sizes "
+                                   "fixed), per-shard partials combined with one NCCL all-gather per op; C2 partitioned "
+                                   "along the non-reduced axis"},
+            "bytes_per_step": int(total_bytes), "ops": ops, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "where_counts": counts,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0

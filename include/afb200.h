@@ -204,6 +204,15 @@ AFAPI af_err afx_ireduce_all_partial(void *partial_val, unsigned *partial_idx, c
  * the carry applies only while the key equals *carry_key (the last key of the previous shard). */
 AFAPI af_err afx_scan_shard(af_array *out, const af_array key, const af_array in, af_binary_op op,
                             bool inclusive_scan, const void *carry, const void *carry_key);
+/* Segmented scan of a 1-D shard WITHOUT carry-in, plus its 32-byte summary in device memory `summary`:
+ *   [0,16)  reduction of the shard's last open segment (one element of the output dtype)
+ *   [16,20) u32, 1 if the shard contains a segment head (0: the whole shard is one run)
+ *   [24,32) u64, position of the first segment head (~0 if none)
+ * The host layer all-gathers (summary, first key, last key) and repairs the first segment with the call below. */
+AFAPI af_err afx_scan_shard_local(af_array *out, void *summary, const af_array key, const af_array in,
+                                  af_binary_op op, bool inclusive_scan);
+/* out[i] = op(*carry, out[i]) for i < count, in place; carry is a HOST pointer to one element of out's dtype */
+AFAPI af_err afx_scan_shard_fixup(af_array out, const void *carry, dim_t count, af_binary_op op);
 /* af_where over a shard with every index offset by `base` (= rank*N/G); returns the hit count too */
 AFAPI af_err afx_where_shard(af_array *idx, dim_t *count, const af_array in, unsigned base);
 /* number of CUDA kernels this library launched on the calling thread's device since the last reset */
