@@ -197,6 +197,8 @@ struct Scratch {
     void *tiles = nullptr;         size_t tiles_bytes = 0;      // decoupled-lookback tile descriptors (scans)
     void *wtiles = nullptr;        size_t wtiles_bytes = 0;     // packed single-word descriptors (where)
     unsigned *tile_counter = nullptr;                           // dynamic tile-id ticket (self-resetting)
+    unsigned long long *chain_ticket = nullptr;                 // monotone 64-bit ticket of the persistent chained kernels
+    unsigned long long chain_base = 0;                          // host mirror: its value once all enqueued launches are done
     unsigned epoch = 0, wepoch = 0;                             // generation tags of the two descriptor arrays
     void *host_pinned = nullptr;   size_t host_pinned_bytes = 0;  // D2H landing zone for scalars
     void *dev_scalar = nullptr;                                 // 64-byte device scalar slot(s)

@@ -256,6 +256,10 @@ template<> AFB_DI __half ldg_stream<__half>(const __half *p) { return __ushort_a
 // elements per 16-byte vector
 template<typename T> struct VecN { static constexpr int value = 16 / (int)sizeof(T); };
 
+// A look-back poll that has not seen its predecessor after this many tries (several seconds) is a protocol
+// bug, not a slow neighbour: trap, so that the launch fails loudly instead of hanging the device.
+constexpr unsigned kSpinLimit = 1u << 25;
+
 // acquire / release flags for tile descriptors and tickets
 AFB_DI uint ld_acquire(const uint *p) {
     uint v;

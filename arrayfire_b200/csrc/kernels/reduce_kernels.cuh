@@ -69,6 +69,25 @@ template<int OP, typename Ti, typename To> struct ValPolicy {
     }
 };
 
+// Types whose own ordering coincides with the order of the `double` key the reference compares
+// (cpu/kernel/ireduce.hpp:21-27): the conversion to double is exact and monotonic for them.  64-bit integers
+// (lossy conversion), b8 (compares v > 0) and complex (magnitudes) stay on the generic path.
+template<typename T> struct NativeOrder { static constexpr bool value = false; };
+#define AFB_NATIVE_ORDER(T)                                                        \
+    template<> struct NativeOrder<T> {                                              \
+        static constexpr bool value = true;                                         \
+        typedef T Cmp;                                                              \
+        AFB_DI static T cmp(T v) { return v; }                                      \
+    };
+AFB_NATIVE_ORDER(float) AFB_NATIVE_ORDER(double) AFB_NATIVE_ORDER(int) AFB_NATIVE_ORDER(uint)
+AFB_NATIVE_ORDER(short) AFB_NATIVE_ORDER(ushort) AFB_NATIVE_ORDER(schar) AFB_NATIVE_ORDER(uchar)
+#undef AFB_NATIVE_ORDER
+template<> struct NativeOrder<__half> {
+    static constexpr bool value = true;
+    typedef float Cmp;
+    AFB_DI static float cmp(__half v) { return __half2float(v); }
+};
+
 struct ArgParams {};
 
 template<int OP, typename T> struct ArgPolicy {
@@ -100,14 +119,44 @@ template<int OP, typename T> struct ArgPolicy {
     }
     AFB_DI static void store(const Out &o, size_t i, Acc a) {
         o.val[i] = a.val;
-        o.loc[i] = a.idx - 1u;
+        uint idx = a.idx - 1u;
+        if constexpr (NativeOrder<T>::value) {
+            // the streaming fast path below never records an element that merely EQUALS the identity (max) and
+            // leaves "no candidate" when nothing was recorded.  In both cases the reference's answer is 0:
+            // a result equal to the identity means every element is the identity or NaN, and element 0 -- the
+            // seed, turned into the identity if NaN -- wins (max: first occurrence; min: the non-strict
+            // compare below has already recorded the last one, if any).
+            if (OP == OP_MAX && !(order_key<T>(a.val) > order_key<T>(Lim<T>::lo()))) idx = 0u;
+            if (OP == OP_MIN && a.idx == 0u) idx = 0u;
+        }
+        o.loc[i] = idx;
     }
     AFB_DI static Acc fold16(const Params &p, Acc acc, const Vec16 &v, uint idx0) {
         constexpr int V = VecN<In>::value;
         const In *e = reinterpret_cast<const In *>(&v);
+        if constexpr (NativeOrder<T>::value) {
+            // Elements arrive in increasing index order and the type's own compare orders exactly like the
+            // reference's (double) key, so one compare per element suffices: strict '>' keeps the FIRST maximum,
+            // '<=' keeps the LAST minimum; NaN fails both.  (2 instead of ~12 instructions per element: the
+            // generic path made imax compute-bound, sm__throughput 81 % in profiles/r01a_first_pass.md.)
+            typedef typename NativeOrder<T>::Cmp C;
+            C best = NativeOrder<T>::cmp(acc.val);
+            T bval = acc.val;
+            uint bidx = acc.idx;
 #pragma unroll
-        for (int k = 0; k < V; k++) acc = join(acc, load(p, e[k], idx0 + k));
-        return acc;
+            for (int k = 0; k < V; k++) {
+                const C x = NativeOrder<T>::cmp(e[k]);
+                const bool take = (OP == OP_MAX) ? (x > best) : (x <= best);
+                best = take ? x : best;
+                bval = take ? e[k] : bval;
+                bidx = take ? idx0 + k + 1u : bidx;
+            }
+            return Acc{bval, bidx};
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; k++) acc = join(acc, load(p, e[k], idx0 + k));
+            return acc;
+        }
     }
 };
 

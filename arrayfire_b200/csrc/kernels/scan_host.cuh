@@ -2,6 +2,7 @@
 #pragma once
 
 #include "reduce_host.cuh"
+#include "chain_kernels.cuh"
 #include "scan_kernels.cuh"
 
 namespace afb {
@@ -38,6 +39,70 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
             note_launches(1);
             post_launch_check("warp_scan_cols_kernel");
             return;
+        }
+        // ---- persistent TMA-fed chained scan: needs 16-byte aligned columns of in / key / out
+        {
+            constexpr int UC = KEYED ? 4 : 8;
+            constexpr dim_t CT = (dim_t)kChainConsumers * UC * E;
+            bool ok = aligned_to(in.ptr, 16) && aligned_to(out, 16) && (!KEYED || aligned_to(key->ptr, 16));
+            if (g.ncols > 1) {
+                ok = ok && ((g.len * sizeof(To)) % 16 == 0);
+                for (int i = 1; i < 4; i++) {
+                    if (in.dims[i] > 1) {
+                        ok = ok && ((in.strides[i] * sizeof(Ti)) % 16 == 0);
+                        if (KEYED) ok = ok && ((key->strides[i] * sizeof(Tk)) % 16 == 0);
+                    }
+                }
+            }
+            if (ok && g.len >= CT && !env_int("AFB200_NO_CHAIN", 0)) {
+                typedef ChainSmem<Ti, Tk, KEYED, (int)CT> Lay;
+                auto kern = chain_scan_kernel<OP, Ti, To, KEYED, Tk, UC>;
+                static int resident[64] = {0};  // CTAs per SM, per device (0: not configured yet)
+                const int dv = c.device & 63;
+                if (!resident[dv]) {
+                    AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::total));
+                    int nb = 0;
+                    AFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kChainThreads, Lay::total));
+                    resident[dv] = nb > 0 ? nb : 1;
+                }
+                ChainScanArgs<Ti, To, Tk> a;
+                a.in = (const Ti *)in.ptr;
+                a.key = KEYED ? (const Tk *)key->ptr : nullptr;
+                a.out = (To *)out;
+                a.g = g;
+                a.ks1 = KEYED ? key->strides[1] : 0;
+                a.ks2 = KEYED ? key->strides[2] : 0;
+                a.ks3 = KEYED ? key->strides[3] : 0;
+                a.tiles_per_col = (g.len + CT - 1) / CT;
+                a.ntiles = a.tiles_per_col * g.ncols;
+                a.inclusive = inclusive ? 1 : 0;
+                a.summary = (g.ncols == 1) ? summary : nullptr;
+                if (a.summary && carry) fail(AF_ERR_INTERNAL, "scan: shard summary and carry-in are mutually exclusive");
+                if (a.summary) {
+                    AFB_CUDA(cudaMemsetAsync(summary, 0, 24, c.stream));
+                    AFB_CUDA(cudaMemsetAsync((char *)summary + 24, 0xff, 8, c.stream));
+                }
+                if (sizeof(To) == 4) {
+                    a.descs = c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
+                    a.gen = c.scratch->next_wepoch(c.stream);
+                } else {
+                    a.descs = c.scratch->need_tiles((size_t)a.ntiles * sizeof(TileDesc<State>), c.stream);
+                    a.gen = c.scratch->next_epoch(c.stream);
+                }
+                a.carry = (const To *)carry;
+                a.carry_key = (const Tk *)carry_key;
+                int ctas = env_int("AFB200_CHAIN_CTAS_PER_SM", resident[dv]);
+                if (ctas > resident[dv]) ctas = resident[dv];
+                dim_t grid = (dim_t)c.sms * ctas;
+                if (grid > a.ntiles) grid = a.ntiles;
+                a.ticket = c.scratch->chain_ticket;
+                a.ticket_base = c.scratch->chain_base;
+                c.scratch->chain_base += (unsigned long long)a.ntiles + (unsigned long long)grid;  // every CTA draws one past the end
+                kern<<<(unsigned)grid, kChainThreads, Lay::total, c.stream>>>(a);
+                note_launches(1);
+                post_launch_check("chain_scan_kernel");
+                return;
+            }
         }
         LookbackArgs<Ti, To, Tk> a;
         a.in = (const Ti *)in.ptr;

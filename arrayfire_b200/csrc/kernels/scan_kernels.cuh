@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kScanThreads) lookback_kernel(const LookbackAr
                 const bool valid = mine >= first;
                 uint st = 0;
                 if (valid) {
-                    do { st = ld_acquire(&descs[mine].status); } while ((st & ~3u) != tag || (st & 3u) == TILE_INVALID);
+                    { uint spins = 0; do { st = ld_acquire(&descs[mine].status); if (++spins > kSpinLimit) __trap(); } while ((st & ~3u) != tag || (st & 3u) == TILE_INVALID); }
                 }
                 const bool is_prefix = valid && (st & 3u) == TILE_PREFIX;
                 const uint pmask = __ballot_sync(0xffffffffu, is_prefix);

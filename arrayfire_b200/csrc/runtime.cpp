@@ -362,6 +362,8 @@ void Scratch::ensure_basics() {
     cudaStream_t s = stream_of(device);
     AFB_CUDA(cudaMalloc((void **)&tile_counter, 256));
     AFB_CUDA(cudaMemsetAsync(tile_counter, 0, 256, s));
+    chain_ticket = reinterpret_cast<unsigned long long *>(tile_counter + 32);  // same 256-byte block, own 128-byte line
+    chain_base = 0;
     AFB_CUDA(cudaMalloc(&dev_scalar, 4096));
     AFB_CUDA(cudaMemsetAsync(dev_scalar, 0, 4096, s));
     AFB_CUDA(cudaMallocHost(&host_pinned, 4096));
@@ -381,7 +383,7 @@ void *Scratch::need_wtiles(size_t bytes, cudaStream_t s) {
 }
 
 unsigned Scratch::next_wepoch(cudaStream_t s) {
-    if (++wepoch >= (1u << 30) - 1) {
+    if (++wepoch >= (1u << 29) - 1) {  // 29 bits: the packed descriptors keep a flag bit below the generation
         AFB_CUDA(cudaMemsetAsync(wtiles, 0, wtiles_bytes, s));
         wepoch = 1;
     }
