@@ -1,0 +1,552 @@
+// pipe_kernels.cuh -- the software-pipelined, TMA-in / TMA-out single-pass scan of libafb200 (4-byte types).
+//
+// Why it exists (profiles/r01b_*.md): the first persistent chained scan (chain_kernels.cuh) kept every warp of
+// a CTA on the CTA barrier while warp 0 walked the look-back chain -- ncu showed 65-70 % of the stall samples on
+// `barrier`, 10-13 us per tile, 15-28 % of DRAM peak -- and spent 22-60 thread-instructions per element on
+// per-slot shuffle scans.  This kernel removes both costs:
+//
+//   * ONE CTA per SM: 8 compute warps + 1 control warp.  Tiles are drawn by monotone ticket (a tile only ever
+//     waits for tiles with smaller tickets, whose CTAs are already running), staged into a ring of shared-memory
+//     stages by bulk-async copies (TMA, mbarrier complete_tx) several tiles ahead, transformed IN PLACE in shared
+//     memory and written back by bulk-async stores: no thread ever issues a global load/store on the fast path.
+//   * blocked register layout: a thread owns EPT consecutive elements (EPT*4 bytes is an ODD number of 16-byte
+//     vectors, so the 128-bit shared-memory accesses of a quarter-warp are conflict-free): one serial scan per
+//     thread + ONE shuffle scan per warp per tile (~3-10 instructions per element instead of 22-60).
+//   * the look-back is taken off the critical path: pass 1 of tile i (local scan, warp totals) is followed by
+//     pass 2 of tile i-1 (add the resolved prefix), so the control warp has a whole tile period to resolve tile
+//     i's prefix; the compute warps never wait on the CTA barrier at all (mbarriers only).
+//   * look-back windows are 256 tiles wide (8 packed 64-bit descriptors per lane, value + generation + flag +
+//     status in one relaxed load): one L2 round trip covers every tile in flight on the 148 SMs.
+//   * by-key scans stop the look-back at the first predecessor that contains a segment head.
+//
+// Semantics: /root/reference/src/backend/cpu/kernel/scan.hpp:37-72, scan_by_key.hpp:43-86.
+#pragma once
+
+#include "chain_kernels.cuh"
+
+namespace afb {
+
+// ------------------------------------------------------------------------------------------------
+// more bulk-copy / mbarrier PTX
+// ------------------------------------------------------------------------------------------------
+AFB_DI void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes) : "memory");
+}
+AFB_DI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template<int N> AFB_DI void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+AFB_DI void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+AFB_DI void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+constexpr int kPipeWindow = 8;   // 32-descriptor chunks per look-back window (window = 256 tiles)
+
+// ------------------------------------------------------------------------------------------------
+// look-back over packed 64-bit descriptors, executed by one full warp.
+// Returns (in every lane) the fold of all tiles in [first, tile) -- or, for segmented states, of the tiles
+// after the nearest segment head.  `first` is the first tile of the column: it always publishes TILE_PREFIX.
+//
+// Chunk q of a window holds the 32 tiles at distance 32q+1 .. 32q+32 behind `look`, lane l the one at distance
+// 32q+l+1: every warp-wide load is ONE coalesced 256-byte request.  (The first version gave each lane 8
+// consecutive descriptors: 256 sector requests per poll and CTA, all 148 CTAs on the same ~25 L2 lines --
+// measured 2800 cycles per poll, 11 polls per tile.)
+// ------------------------------------------------------------------------------------------------
+template<typename S, typename Codec, bool KEYED>
+AFB_DI typename S::State lookback_resolve(const unsigned long long *pd, long long tile, long long first, uint tag, int lane,
+                                          unsigned long long *npolls = nullptr) {
+    typedef typename S::State State;
+    State excl = S::identity();
+    long long look = tile - 1;   // newest tile not folded yet
+    while (true) {
+        unsigned long long d[kPipeWindow];
+        int qstop = kPipeWindow, P = 32;   // chunk / lane of the descriptor that ends the look-back (if any)
+        uint spins = 0;
+        while (true) {
+#pragma unroll
+            for (int q = 0; q < kPipeWindow; q++) {
+                const long long t = look - 32 * q - lane;
+                d[q] = 0ULL;
+                if (t >= first) d[q] = ld_relaxed64(pd + t);
+            }
+            bool resolved = true;
+            qstop = kPipeWindow;
+            P = 32;
+#pragma unroll
+            for (int q = 0; q < kPipeWindow; q++) {
+                const uint lo = (uint)d[q];
+                const bool ok = ((lo & ~7u) == tag) && ((lo & 3u) != TILE_INVALID);
+                bool ends = ok && ((lo & 3u) == TILE_PREFIX);
+                if (KEYED) ends = ends || (ok && (lo & 4u));
+                const uint smask = __ballot_sync(0xffffffffu, ends);
+                const uint bmask = __ballot_sync(0xffffffffu, !ok);
+                if (resolved && qstop == kPipeWindow) {      // still walking back (warp-uniform)
+                    const int p = smask ? (__ffs(smask) - 1) : 32;
+                    const uint newer = (p >= 32) ? 0xffffffffu : ((1u << p) - 1u);
+                    if (bmask & newer) resolved = false;      // a descriptor in front of the stop is not published yet
+                    else if (p < 32) { qstop = q; P = p; }
+                }
+            }
+            if (npolls) (*npolls)++;
+            if (resolved) break;
+            if (++spins > kSpinLimit) __trap();
+        }
+        // ordered fold, oldest first: chunks from the stopping one (or the last) down to chunk 0
+        State acc = S::identity();
+#pragma unroll
+        for (int q = kPipeWindow - 1; q >= 0; q--) {
+            if (q <= qstop) {                                 // warp-uniform
+                State v = S::identity();
+                if (q < qstop || lane <= P) v = Codec::unpack(d[q]);
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {         // lane + dd holds an EARLIER tile than lane
+                    State o = shfl_down(v, dd);
+                    if (lane + dd < 32) v = S::join(o, v);
+                }
+                acc = S::join(acc, shfl_idx(v, 0));
+            }
+        }
+        excl = S::join(acc, excl);
+        if (qstop < kPipeWindow) break;
+        look -= 32 * kPipeWindow;
+    }
+    return excl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pipe_scan_kernel
+// ------------------------------------------------------------------------------------------------
+// Warp roles of the (single) CTA of an SM:
+//   warps 0..NW-1  compute: pass 1 of tile i (local scan in place, warp totals), then pass 2 of tile i-D
+//                  (add the value carried into the warp's chunk); mbarriers only, never a CTA-wide barrier
+//   warp NW        look-back: publishes the aggregate of tile j as soon as its warp totals exist, and
+//                  resolves tile j-1 -- whose predecessors published their aggregates a whole tile period
+//                  earlier, so one poll (one loaded L2 round trip, ~1 us on a saturated B200) normally suffices
+//   warp NW+1      DMA (one thread): draws tile tickets two ahead, keeps the bulk loads STAGES-D-1 tiles ahead
+//                  of pass 1 and writes finished tiles back with bulk stores
+// Every synchronous L2 round trip (ticket atomic, descriptor poll) costs ~2000 cycles under full HBM load
+// (measured); the roles are split so that none of them sits on the compute warps' path.
+constexpr int kPipeWarps = 12;                      // compute warps
+constexpr int kPipeThreads = 32 * (kPipeWarps + 2); // + look-back warp + DMA warp
+constexpr int kPipeLag = 2;                         // D: pass 2 runs D tiles behind pass 1
+constexpr int kPipeRing = 4;                        // per-tile barrier / scratch ring (> D + 1)
+
+template<typename Ti, typename To, typename Tk>
+struct PipeScanArgs {
+    const Ti *in;
+    const Tk *key;
+    To *out;
+    ColGeom g;
+    dim_t ks1, ks2, ks3;
+    dim_t tiles_per_col;
+    dim_t ntiles;
+    int inclusive;
+    uint gen;
+    unsigned long long *descs;
+    unsigned long long *ticket;
+    unsigned long long ticket_base;
+    const To *carry;
+    const Tk *carry_key;
+    void *summary;
+    unsigned long long *debug;   // optional per-CTA cycle counters (AFB200_PIPE_DEBUG=1), 16 words per CTA
+};
+
+template<bool KEYED, int EPT, int STAGES> struct PipeLayout {
+    static constexpr int TILE = kPipeWarps * 32 * EPT;
+    static constexpr int KPAD = 4;                                  // key elements kept in front of the tile
+    static constexpr int KSTAGES = KEYED ? STAGES - kPipeLag - 1 : 0;   // keys are dead after pass 1
+    static constexpr size_t val_bytes = (size_t)TILE * 4;
+    static constexpr size_t key_stage_bytes = ((size_t)TILE * 4 + KPAD * 4 + 127) / 128 * 128;
+    static constexpr size_t total = val_bytes * STAGES + key_stage_bytes * KSTAGES + 128;
+    static_assert(val_bytes % 128 == 0, "value stages must stay 128-byte aligned");
+};
+
+template<int OP, typename Ti, typename To, bool KEYED, typename Tk, int EPT, int STAGES>
+__global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeScanArgs<Ti, To, Tk> a) {
+    static_assert(sizeof(Ti) == 4 && sizeof(To) == 4 && sizeof(Tk) == 4, "pipe scan: 4-byte values and keys");
+    static_assert(EPT % 4 == 0 && ((EPT / 4) & 1) == 1 && EPT <= 32, "EPT*4 bytes must be an odd number of 16-byte vectors");
+    typedef Rule<OP, Ti, To> R;
+    typedef SOps<R, To, KEYED> S;
+    typedef typename S::State State;
+    typedef DescCodec<S, To, KEYED> Codec;
+    typedef PipeLayout<KEYED, EPT, STAGES> Lay;
+    constexpr int TILE = Lay::TILE;
+    constexpr int NV = EPT / 4;
+    constexpr int WCHUNK = 32 * EPT;
+    constexpr int KPAD = Lay::KPAD;
+    constexpr int NW = kPipeWarps, D = kPipeLag, RING = kPipeRing;
+    constexpr int KST = Lay::KSTAGES > 0 ? Lay::KSTAGES : 1;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *val_base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    unsigned char *key_base = val_base + Lay::val_bytes * STAGES;
+    __shared__ uint64_t full_bar[STAGES];
+    __shared__ uint64_t p1_bar[RING], lb_bar[RING], p2_bar[RING];
+    __shared__ long long sm_tile_id[STAGES];
+    __shared__ int sm_valid[STAGES];             // valid elements of the tile; TILE: staged / stored by bulk copies
+    __shared__ State sm_wtot[RING][NW];
+    __shared__ uint sm_wfh[RING][NW];            // first segment head inside the warp's chunk (WCHUNK: none)
+    __shared__ To sm_wp[RING][NW];               // value carried into each warp's chunk
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) mbar_init(&full_bar[s], 1);
+#pragma unroll
+        for (int b = 0; b < RING; b++) {
+            mbar_init(&p1_bar[b], NW);
+            mbar_init(&lb_bar[b], 1);
+            mbar_init(&p2_bar[b], NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    ColGeom kg = a.g;
+    kg.s1 = a.ks1; kg.s2 = a.ks2; kg.s3 = a.ks3;
+    const uint tag = a.gen << 3;
+
+    if (warp == NW + 1) {
+        // =========================================================================== DMA warp (one thread)
+        if (lane != 0) return;
+        auto draw = [&]() -> long long { return (long long)(atomicAdd(a.ticket, 1ULL) - a.ticket_base); };
+        long long pub = 0;        // tiles published so far; tile n uses value stage n % STAGES, key stage n % KST
+        long long n_live = -1;    // number of real tiles of this CTA, known once the end ticket has been drawn
+        auto publish = [&](long long n, long long tile) {
+            const int s = (int)(n % STAGES);
+            sm_tile_id[s] = tile;
+            if (tile >= a.ntiles) {
+                sm_valid[s] = 0;
+                mbar_arrive(&full_bar[s]);
+                return;
+            }
+            const dim_t col = tile / a.tiles_per_col, tcol = tile % a.tiles_per_col;
+            const dim_t tile_lo = tcol * TILE;
+            const dim_t left = a.g.len - tile_lo;
+            const int valid = left >= TILE ? TILE : (int)left;
+            sm_valid[s] = valid;
+            if (valid == TILE) {
+                fence_proxy_async();
+                const uint32_t kb = KEYED ? (uint32_t)(TILE * 4 + (tile_lo > 0 ? KPAD * 4 : 0)) : 0u;
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)Lay::val_bytes + kb);
+                bulk_g2s(val_base + (size_t)s * Lay::val_bytes, a.in + col_offset(a.g, col) + tile_lo, (uint32_t)Lay::val_bytes, &full_bar[s]);
+                if (KEYED) {
+                    const Tk *ksrc = a.key + col_offset(kg, col) + tile_lo;
+                    unsigned char *kdst = key_base + (size_t)(n % KST) * Lay::key_stage_bytes;
+                    if (tile_lo > 0) bulk_g2s(kdst, ksrc - KPAD, kb, &full_bar[s]);   // key[tile_lo-1] lands in the pad
+                    else bulk_g2s(kdst + KPAD * 4, ksrc, kb, &full_bar[s]);
+                }
+            } else {
+                mbar_arrive(&full_bar[s]);   // ragged last tile of a column: the compute warps copy it themselves
+            }
+        };
+        // Tickets are drawn two tiles ahead of their use (the atomic's round trip is ~1 us under load) and at most
+        // two per tile period, never a whole ring at once: a CTA that drew STAGES consecutive tickets would own
+        // STAGES consecutive tiles, and since every tile waits for its predecessor's aggregate the CTAs would start
+        // one after the other.
+        long long tk0 = draw(), tk1 = draw();
+        bool drawing = true;
+        auto publish_next = [&]() {
+            const long long t = tk0;
+            tk0 = tk1;
+            publish(pub, t);
+            pub++;
+            if (t >= a.ntiles) { drawing = false; n_live = pub - 1; }
+            else tk1 = draw();
+        };
+        publish_next();
+        if (drawing) publish_next();
+        for (long long j = 0;; j++) {
+            if (j >= D) {
+                const long long n = j - D;            // pass 2 of tile n is the next to finish
+                if (!drawing && n >= n_live) break;
+                mbar_wait(&p2_bar[n % RING], (uint32_t)((n / RING) & 1));
+                const int sp = (int)(n % STAGES);
+                if (sm_valid[sp] == TILE) {
+                    const long long tp = sm_tile_id[sp];
+                    const dim_t col = tp / a.tiles_per_col, tcol = tp % a.tiles_per_col;
+                    bulk_s2g(a.out + col * a.g.len + tcol * TILE, val_base + (size_t)sp * Lay::val_bytes, (uint32_t)Lay::val_bytes);
+                }
+                bulk_commit();
+                bulk_wait_read<1>();                  // stores of tiles <= n-1 have finished reading shared memory
+            }
+            // tile m may be published once the store of tile m - STAGES has drained: m - STAGES <= j - D - 1
+            for (int burst = 0; drawing && burst < 2 && pub <= j + STAGES - D - 1; burst++) publish_next();
+        }
+        bulk_wait_all();
+        return;
+    }
+
+    if (warp == NW) {
+        // =========================================================================== look-back warp
+        unsigned long long dbg[4] = {0, 0, 0, 0};
+        const long long t_start = clock64();
+        bool pending = false;         // tile j-1 published an aggregate and still needs its prefix
+        long long p_tile = 0;
+        int p_slot = 0;
+        State p_wexc = S::identity(), p_total = S::identity();
+        // prefix known: hand the per-warp carries to pass 2 (and fill the shard summary)
+        auto finalize = [&](long long tile, int slot, State excl, State wexc, State total) {
+            const dim_t tcol = tile % a.tiles_per_col;
+            if (a.summary) {
+                if (KEYED) {
+                    uint fh = (lane < NW) ? sm_wfh[slot][lane] : (uint)WCHUNK;
+                    uint pos = fh < (uint)WCHUNK ? (uint)(lane * WCHUNK) + fh : 0xffffffffu;
+                    pos = __reduce_min_sync(0xffffffffu, pos);
+                    if (lane == 0 && pos != 0xffffffffu)
+                        atomicMin(reinterpret_cast<unsigned long long *>((char *)a.summary + 24),
+                                  (unsigned long long)(tcol * TILE + pos));
+                }
+                if (lane == 0 && tcol == a.tiles_per_col - 1) {
+                    const State fin = S::join(excl, total);
+                    *reinterpret_cast<Slot<To> *>(a.summary) = Slot<To>{S::value(fin)};
+                    uint flag = 0;
+                    if constexpr (KEYED) flag = fin.flag ? 1u : 0u;
+                    *reinterpret_cast<uint *>((char *)a.summary + 16) = flag;
+                }
+            }
+            if (lane < NW) sm_wp[slot][lane] = S::value(S::join(excl, wexc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lb_bar[slot]);
+        };
+        for (long long j = 0;; j++) {
+            const int s = (int)(j % STAGES), slot = (int)(j % RING);
+            mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
+            const long long tile = sm_tile_id[s];
+            const bool live = tile < a.ntiles;
+            bool pending_cur = false;
+            State wexc = S::identity(), tile_total = S::identity();
+            if (live) {
+                const dim_t tcol = tile % a.tiles_per_col;
+                mbar_wait(&p1_bar[slot], (uint32_t)((j / RING) & 1));
+                State st = (lane < NW) ? sm_wtot[slot][lane] : S::identity();
+#pragma unroll
+                for (int dd = 1; dd < NW; dd <<= 1) {
+                    State o = shfl_up(st, dd);
+                    if (lane >= dd) st = S::join(o, st);
+                }
+                tile_total = shfl_idx(st, NW - 1);
+                wexc = shfl_up(st, 1);
+                if (lane == 0) wexc = S::identity();
+                if (tcol == 0) {
+                    State excl = S::identity();
+                    if (a.carry) excl = S::lift(*a.carry, false);
+                    if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(S::join(excl, tile_total), tag, TILE_PREFIX));
+                    finalize(tile, slot, excl, wexc, tile_total);
+                } else {
+                    if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(tile_total, tag, TILE_AGGREGATE));
+                    pending_cur = true;
+                }
+                dbg[3]++;
+            }
+            if (pending) {
+                const long long c0 = clock64();
+                const dim_t tcol = p_tile % a.tiles_per_col;
+                const State excl = lookback_resolve<S, Codec, KEYED>(a.descs, p_tile, p_tile - tcol, tag, lane, a.debug ? &dbg[2] : nullptr);
+                if (lane == 0) st_relaxed64(&a.descs[p_tile], Codec::pack(S::join(excl, p_total), tag, TILE_PREFIX));
+                finalize(p_tile, p_slot, excl, p_wexc, p_total);
+                dbg[1] += clock64() - c0;
+            }
+            if (!live) break;
+            pending = pending_cur;
+            p_tile = tile;
+            p_slot = slot;
+            p_wexc = wexc;
+            p_total = tile_total;
+        }
+        if (a.debug && lane == 0) {
+            dbg[0] = clock64() - t_start;
+            for (int q = 0; q < 4; q++) a.debug[blockIdx.x * 16 + q] = dbg[q];
+        }
+        return;
+    }
+
+    // =============================================================================== compute warps
+    const int t = warp * 32 + lane;          // 0 .. NW*32-1
+    const int base = t * EPT;                // first element of this thread inside the tile
+    uint fh0 = WCHUNK, fh1 = WCHUNK, fh2 = WCHUNK;   // first head of the warp's chunk in tiles i, i-1, i-2
+    unsigned long long cw_full = 0, cw_lb = 0, cw_p1 = 0, cw_p2 = 0;
+    bool ended = false;
+    long long n_live = 0;                    // valid once `ended`
+    for (long long i = 0;; i++) {
+        long long k0 = clock64();
+        if (!ended) {
+            const int s = (int)(i % STAGES), b = (int)(i % RING);
+            mbar_wait(&full_bar[s], (uint32_t)((i / STAGES) & 1));
+            cw_full += clock64() - k0;
+            k0 = clock64();
+            const long long tile = sm_tile_id[s];
+            if (tile >= a.ntiles) {
+                ended = true;
+                n_live = i;
+            } else {
+                // ---------------------------------------------------------------- pass 1 of tile i
+                const int valid = sm_valid[s];
+                const dim_t col = tile / a.tiles_per_col, tcol = tile % a.tiles_per_col;
+                const dim_t tile_lo = tcol * TILE;
+                To *sv = reinterpret_cast<To *>(val_base + (size_t)s * Lay::val_bytes);
+                Tk *sk = reinterpret_cast<Tk *>(key_base + (size_t)(i % KST) * Lay::key_stage_bytes) + KPAD;
+                if (valid != TILE) {
+                    // ragged tile: plain cooperative copy (elements past the end cannot influence stored outputs,
+                    // and are masked to the identity below so that the tile total stays exact)
+                    const Ti *gin = a.in + col_offset(a.g, col) + tile_lo;
+                    for (int e = t; e < valid; e += NW * 32) reinterpret_cast<Ti *>(sv)[e] = ldg_stream<Ti>(gin + e);
+                    if (KEYED) {
+                        const Tk *gk = a.key + col_offset(kg, col) + tile_lo;
+                        for (int e = t; e < valid; e += NW * 32) sk[e] = __ldg(gk + e);
+                        if (t == 0 && tile_lo > 0) sk[-1] = __ldg(gk - 1);
+                    }
+                    named_bar_sync(1, NW * 32);
+                }
+                Ti v[EPT];
+#pragma unroll
+                for (int j = 0; j < NV; j++) {
+                    const Vec16 q = *reinterpret_cast<const Vec16 *>(reinterpret_cast<const Ti *>(sv) + base + 4 * j);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[4 * j + k] = reinterpret_cast<const Ti *>(&q)[k];
+                }
+                uint hb = 0u;   // bit k: element k of this thread starts a segment
+                if (KEYED) {
+                    Tk kk[EPT];
+#pragma unroll
+                    for (int j = 0; j < NV; j++) {
+                        // keys sit KPAD elements into their buffer: still 16-byte aligned
+                        const Vec16 q = *reinterpret_cast<const Vec16 *>(sk + base + 4 * j);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) kk[4 * j + k] = reinterpret_cast<const Tk *>(&q)[k];
+                    }
+                    Tk kprev;
+                    if (base > 0 || tile_lo > 0) kprev = sk[base - 1];
+                    else kprev = a.carry_key ? *a.carry_key : kk[0];   // position 0 of a column: a head only against the carry key
+#pragma unroll
+                    for (int k = 0; k < EPT; k++) {
+                        const bool head = kk[k] != (k == 0 ? kprev : kk[k - 1]);
+                        hb |= (head ? 1u : 0u) << k;
+                    }
+                    if (valid != TILE) {
+                        const int nv = valid - base;   // heads past the end do not exist
+                        hb = nv <= 0 ? 0u : (nv >= 32 ? hb : (hb & ((1u << nv) - 1u)));
+                    }
+                }
+                // ---- serial scan inside the thread
+                To x[EPT];
+                To run = R::init();
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+                    To e = R::pre(v[k]);
+                    if (valid != TILE && base + k >= valid) e = R::init();
+                    if (k == 0) run = e;
+                    else if (KEYED) run = ((hb >> k) & 1u) ? e : R::join(run, e);
+                    else run = R::join(run, e);
+                    x[k] = run;
+                }
+                // ---- one shuffle scan per warp
+                State inc;
+                if constexpr (KEYED) inc = State{run, hb != 0u ? 1 : 0};
+                else inc = run;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    State o = shfl_up(inc, dd);
+                    if (lane >= dd) inc = S::join(o, inc);
+                }
+                State exc = shfl_up(inc, 1);
+                if (lane == 0) exc = S::identity();
+                if (lane == 31) sm_wtot[b][warp] = inc;
+                const To ev = S::value(exc);
+                if (KEYED) {
+                    uint pos = hb ? (uint)(lane * EPT + (__ffs(hb) - 1)) : (uint)WCHUNK;
+                    pos = __reduce_min_sync(0xffffffffu, pos);
+                    fh0 = pos;
+                    if (lane == 0) sm_wfh[b][warp] = pos;
+                }
+                // the warp total is all the look-back warp needs: let it publish while the outputs are formed
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p1_bar[b]);
+                // ---- local results (everything except the value carried into the warp's chunk), in place
+                To o[EPT];
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+                    // open(k): no segment head among elements 0..k of this thread
+                    if (a.inclusive) {
+                        const bool open = !KEYED || (hb & ((2u << k) - 1u)) == 0u;
+                        o[k] = open ? R::join(ev, x[k]) : x[k];
+                    } else {
+                        if (k == 0) o[k] = ev;
+                        else {
+                            const bool open = !KEYED || (hb & ((1u << k) - 1u)) == 0u;
+                            o[k] = open ? R::join(ev, x[k - 1]) : x[k - 1];
+                        }
+                        if (KEYED && ((hb >> k) & 1u)) o[k] = R::init();
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NV; j++) {
+                    Vec16 q;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) reinterpret_cast<To *>(&q)[k] = o[4 * j + k];
+                    *reinterpret_cast<Vec16 *>(sv + base + 4 * j) = q;
+                }
+                cw_p1 += clock64() - k0;
+            }
+        }
+        if (i >= D) {
+            // ---------------------------------------------------------------- pass 2 of tile n = i - D
+            const long long n = i - D;
+            if (ended && n >= n_live) break;
+            const int sp = (int)(n % STAGES), bp = (int)(n % RING);
+            k0 = clock64();
+            mbar_wait(&lb_bar[bp], (uint32_t)((n / RING) & 1));
+            cw_lb += clock64() - k0;
+            k0 = clock64();
+            const To wp = sm_wp[bp][warp];
+            const int valid = sm_valid[sp];
+            To *sv = reinterpret_cast<To *>(val_base + (size_t)sp * Lay::val_bytes);
+            // elements of this thread that are still "open" towards the warp's left edge
+            int nadd = EPT;
+            if (KEYED) {
+                const int d = (int)fh2 - lane * EPT;
+                nadd = d < 0 ? 0 : (d > EPT ? EPT : d);
+            }
+            if (valid == TILE) {
+                if (nadd > 0) {
+#pragma unroll
+                    for (int j = 0; j < NV; j++) {
+                        Vec16 q = *reinterpret_cast<const Vec16 *>(sv + base + 4 * j);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            To &e = reinterpret_cast<To *>(&q)[k];
+                            if (!KEYED || 4 * j + k < nadd) e = R::join(wp, e);
+                        }
+                        *reinterpret_cast<Vec16 *>(sv + base + 4 * j) = q;
+                    }
+                }
+                fence_proxy_async();   // make the generic-proxy writes (both passes) visible to the bulk store
+            } else {
+                const long long tp = sm_tile_id[sp];
+                const dim_t col = tp / a.tiles_per_col, tcol = tp % a.tiles_per_col;
+                To *gout = a.out + col * a.g.len + tcol * TILE;
+#pragma unroll
+                for (int k = 0; k < EPT; k++) {
+                    if (base + k < valid) {
+                        To e = sv[base + k];
+                        if (k < nadd) e = R::join(wp, e);
+                        gout[base + k] = e;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p2_bar[bp]);
+            cw_p2 += clock64() - k0;
+        } else if (ended && n_live == 0) {
+            break;
+        }
+        fh2 = fh1;
+        fh1 = fh0;
+    }
+    if (a.debug && t == 0) {
+        a.debug[blockIdx.x * 16 + 8] = cw_full;
+        a.debug[blockIdx.x * 16 + 9] = cw_lb;
+        a.debug[blockIdx.x * 16 + 10] = cw_p1;
+        a.debug[blockIdx.x * 16 + 11] = cw_p2;
+    }
+}
+
+}  // namespace afb

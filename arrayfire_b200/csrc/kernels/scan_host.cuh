@@ -3,6 +3,7 @@
 
 #include "reduce_host.cuh"
 #include "chain_kernels.cuh"
+#include "pipe_kernels.cuh"
 #include "scan_kernels.cuh"
 
 namespace afb {
@@ -52,6 +53,69 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
                         ok = ok && ((in.strides[i] * sizeof(Ti)) % 16 == 0);
                         if (KEYED) ok = ok && ((key->strides[i] * sizeof(Tk)) % 16 == 0);
                     }
+                }
+            }
+            // ---- 4-byte values (and keys): software-pipelined TMA-in / TMA-out kernel, one CTA per SM
+            if constexpr (sizeof(Ti) == 4 && sizeof(To) == 4 && sizeof(Tk) == 4) {
+                constexpr int EPT = KEYED ? 12 : 20;
+                constexpr int ST = 7;
+                typedef PipeLayout<KEYED, EPT, ST> PL;
+                if (ok && g.len >= 4 * (dim_t)PL::TILE && !env_int("AFB200_NO_PIPE", 0)) {
+                    auto kern = pipe_scan_kernel<OP, Ti, To, KEYED, Tk, EPT, ST>;
+                    static bool configured[64] = {false};
+                    const int dv = c.device & 63;
+                    if (!configured[dv]) {
+                        AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::total));
+                        configured[dv] = true;
+                    }
+                    PipeScanArgs<Ti, To, Tk> a;
+                    a.in = (const Ti *)in.ptr;
+                    a.key = KEYED ? (const Tk *)key->ptr : nullptr;
+                    a.out = (To *)out;
+                    a.g = g;
+                    a.ks1 = KEYED ? key->strides[1] : 0;
+                    a.ks2 = KEYED ? key->strides[2] : 0;
+                    a.ks3 = KEYED ? key->strides[3] : 0;
+                    a.tiles_per_col = (g.len + PL::TILE - 1) / PL::TILE;
+                    a.ntiles = a.tiles_per_col * g.ncols;
+                    a.inclusive = inclusive ? 1 : 0;
+                    a.summary = (g.ncols == 1) ? summary : nullptr;
+                    if (a.summary && carry) fail(AF_ERR_INTERNAL, "scan: shard summary and carry-in are mutually exclusive");
+                    if (a.summary) {
+                        AFB_CUDA(cudaMemsetAsync(summary, 0, 24, c.stream));
+                        AFB_CUDA(cudaMemsetAsync((char *)summary + 24, 0xff, 8, c.stream));
+                    }
+                    a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
+                    a.gen = c.scratch->next_wepoch(c.stream);
+                    a.carry = (const To *)carry;
+                    a.carry_key = (const Tk *)carry_key;
+                    dim_t grid = (dim_t)c.sms;
+                    if (grid > a.ntiles) grid = a.ntiles;
+                    a.ticket = c.scratch->chain_ticket;
+                    a.ticket_base = c.scratch->chain_base;
+                    c.scratch->chain_base += (unsigned long long)a.ntiles + 2ULL * (unsigned long long)grid;  // two tickets in flight per CTA
+                    static unsigned long long *dbg_buf = nullptr;
+                    const bool dbg = env_int("AFB200_PIPE_DEBUG", 0) != 0;
+                    if (dbg && !dbg_buf) AFB_CUDA(cudaMalloc(&dbg_buf, 1024 * 16 * 8));
+                    a.debug = dbg ? dbg_buf : nullptr;
+                    if (dbg) AFB_CUDA(cudaMemsetAsync(dbg_buf, 0, 1024 * 16 * 8, c.stream));
+                    kern<<<(unsigned)grid, kPipeThreads, PL::total, c.stream>>>(a);
+                    note_launches(1);
+                    post_launch_check("pipe_scan_kernel");
+                    if (dbg) {
+                        static unsigned long long h[1024 * 16];
+                        AFB_CUDA(cudaStreamSynchronize(c.stream));
+                        AFB_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+                        const char *names[12] = {"lb_total", "lb_resolve", "polls", "tiles", "-", "-",
+                                                 "-", "-", "cmp_wait_full", "cmp_wait_lb", "cmp_p1", "cmp_p2"};
+                        fprintf(stderr, "[pipe_scan debug] grid=%d ntiles=%lld keyed=%d\n", (int)grid, (long long)a.ntiles, (int)KEYED);
+                        for (int q = 0; q < 12; q++) {
+                            double sum = 0, mx = 0;
+                            for (int b = 0; b < (int)grid; b++) { double v = (double)h[b * 16 + q]; sum += v; if (v > mx) mx = v; }
+                            fprintf(stderr, "   %-14s mean %.0f  max %.0f\n", names[q], sum / (double)grid, mx);
+                        }
+                    }
+                    return;
                 }
             }
             if (ok && g.len >= CT && !env_int("AFB200_NO_CHAIN", 0)) {

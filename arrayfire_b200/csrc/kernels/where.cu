@@ -383,10 +383,241 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_where_kernel(const Cha
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// pipe_where_kernel: the software-pipelined compaction (same skeleton as pipe_scan_kernel, pipe_kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+// One CTA per SM: kPW_Warps compute warps + 1 control warp.  Pass 1 of tile i turns every 16-byte vector into
+// a bit mask (kept in shared memory) and counts; the control warp publishes the tile count, resolves the tile's
+// output offset with the 256-wide packed look-back and refills the ring; pass 2 of tile i-1 (executed after pass
+// 1 of tile i, so the look-back latency is hidden) compacts 512 bytes of input at a time through a per-warp
+// strip and flushes it with coalesced stores.  No CTA-wide barrier on the fast path.
+constexpr int kPW_Warps = 16;
+constexpr int kPW_U = 4;        // 512-byte slots per warp per tile
+constexpr int kPW_Stages = 4;
+constexpr int kPW_Threads = 32 * (kPW_Warps + 1);
+
+template<typename T> struct PipeWhereLayout {
+    static constexpr int E = VecN<T>::value;
+    static constexpr int NVEC = kPW_Warps * kPW_U * 32;          // 16-byte vectors per tile
+    static constexpr int TILE = NVEC * E;                        // elements per tile
+    static constexpr size_t stage_bytes = (size_t)NVEC * 16;     // 32 KB
+    static constexpr size_t strip_bytes = (size_t)kPW_Warps * 32 * E * sizeof(uint);
+    static constexpr size_t mask_bytes = (size_t)2 * NVEC * sizeof(unsigned short);
+    static constexpr size_t total = stage_bytes * kPW_Stages + strip_bytes + mask_bytes + 128;
+};
+
+template<typename T>
+__global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainWhereArgs<T> a) {
+    typedef PipeWhereLayout<T> Lay;
+    typedef Rule<OP_ADD, uint, uint> R;
+    typedef SOps<R, uint, false> S;
+    typedef DescCodec<S, uint, false> Codec;
+    constexpr int E = Lay::E;
+    constexpr int TILE = Lay::TILE;
+    constexpr int U = kPW_U, NW = kPW_Warps, ST = kPW_Stages;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *stage_base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint *strips = reinterpret_cast<uint *>(stage_base + Lay::stage_bytes * ST);
+    unsigned short *masks = reinterpret_cast<unsigned short *>(stage_base + Lay::stage_bytes * ST + Lay::strip_bytes);
+    __shared__ uint64_t full_bar[ST];
+    __shared__ uint64_t p1_bar[2], lb_bar[2];
+    __shared__ long long sm_tile_id[ST];
+    __shared__ uint sm_wtot[2][NW];
+    __shared__ uint sm_wp[2][NW];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < ST; s++) mbar_init(&full_bar[s], 1);
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&p1_bar[b], NW);
+            mbar_init(&lb_bar[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint tag = a.gen << 3;
+
+    if (warp == NW) {
+        // =========================================================================== control warp
+        long long next_ticket = 0;
+        bool drawing = true;
+        auto draw = [&]() -> long long { return (long long)(atomicAdd(a.ticket, 1ULL) - a.ticket_base); };
+        auto publish = [&](int s, long long tile) {
+            sm_tile_id[s] = tile;
+            if (tile >= a.ntiles) {
+                mbar_arrive(&full_bar[s]);
+                return;
+            }
+            const dim_t tile_lo = tile * TILE;
+            if (tile_lo + TILE <= a.n) {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)Lay::stage_bytes);
+                bulk_g2s(stage_base + (size_t)s * Lay::stage_bytes, a.in + tile_lo, (uint32_t)Lay::stage_bytes, &full_bar[s]);
+            } else {
+                mbar_arrive(&full_bar[s]);   // ragged last tile: copied (zero-padded) by the compute warps
+            }
+        };
+        // tickets are drawn one tile period apart, never a whole ring at once (see pipe_scan_kernel)
+        long long pub = 0;
+        auto publish_next = [&]() {
+            const long long t = next_ticket;
+            publish((int)(pub % ST), t);
+            pub++;
+            if (t >= a.ntiles) drawing = false;
+            else next_ticket = draw();
+        };
+        if (lane == 0) {
+            next_ticket = draw();
+            publish_next();
+            if (drawing) publish_next();
+        }
+        __syncwarp();
+        for (uint j = 0;; j++) {
+            const int s = j % ST, b = j & 1;
+            long long tile = 0;
+            if (lane == 0) tile = sm_tile_id[s];                 // lane 0 wrote it (and will overwrite it below)
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            if (tile >= a.ntiles) break;
+            mbar_wait(&p1_bar[b], (j >> 1) & 1);
+            // pass 1 has turned the stage of tile j into masks: tiles up to j + ST may be in the ring
+            if (lane == 0) {
+                for (int burst = 0; drawing && burst < 2 && pub <= (long long)j + ST; burst++) publish_next();
+            }
+            uint st = (lane < NW) ? sm_wtot[b][lane] : 0u;
+#pragma unroll
+            for (int dd = 1; dd < NW; dd <<= 1) {
+                const uint o = __shfl_up_sync(0xffffffffu, st, dd);
+                if (lane >= dd) st += o;
+            }
+            const uint tile_total = __shfl_sync(0xffffffffu, st, NW - 1);
+            uint wexc = __shfl_up_sync(0xffffffffu, st, 1);
+            if (lane == 0) wexc = 0u;
+            uint excl = 0u;
+            if (tile == 0) {
+                if (lane == 0) st_relaxed64(&a.descs[0], Codec::pack(tile_total, tag, TILE_PREFIX));
+            } else {
+                if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(tile_total, tag, TILE_AGGREGATE));
+                excl = lookback_resolve<S, Codec, false>(a.descs, tile, 0, tag, lane);
+                if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(excl + tile_total, tag, TILE_PREFIX));
+            }
+            if (lane < NW) sm_wp[b][lane] = excl + wexc;
+            if (lane == 0 && tile == a.ntiles - 1) *a.total = (unsigned long long)excl + tile_total;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lb_bar[b]);
+            __syncwarp();
+        }
+        return;
+    }
+
+    // =============================================================================== compute warps
+    uint *strip = strips + warp * (32 * E);
+    long long tile_prev = 0;
+    for (uint i = 0;; i++) {
+        const int s = i % ST, b = i & 1;
+        mbar_wait(&full_bar[s], (i / ST) & 1);
+        const long long tile = sm_tile_id[s];
+        const bool live = tile < a.ntiles;
+        if (live) {
+            // ---------------------------------------------------------------- pass 1 of tile i: masks + counts
+            const dim_t tile_lo = tile * TILE;
+            unsigned char *stg = stage_base + (size_t)s * Lay::stage_bytes;
+            if (tile_lo + TILE > a.n) {
+                T *dst = reinterpret_cast<T *>(stg);
+                const int valid = (int)(a.n - tile_lo);
+                for (int e = warp * 32 + lane; e < TILE; e += NW * 32) {
+                    if (e < valid) dst[e] = ldg_stream<T>(a.in + tile_lo + e);
+                    else memset(&dst[e], 0, sizeof(T));
+                }
+                named_bar_sync(1, NW * 32);
+            }
+            unsigned short *mk = masks + (size_t)b * Lay::NVEC;
+            uint cnt = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int q = (warp * U + u) * 32 + lane;
+                const Vec16 v = *reinterpret_cast<const Vec16 *>(stg + (size_t)q * 16);
+                const uint m = nonzero_mask<T>(v);
+                mk[q] = (unsigned short)m;
+                cnt += __popc(m);
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) sm_wtot[b][warp] = cnt;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p1_bar[b]);
+        }
+        if (i >= 1) {
+            // ---------------------------------------------------------------- pass 2 of tile i-1: compaction
+            const int bp = (i - 1) & 1;
+            mbar_wait(&lb_bar[bp], ((i - 1) >> 1) & 1);
+            const dim_t tile_lo = tile_prev * TILE;
+            const unsigned short *mk = masks + (size_t)bp * Lay::NVEC;
+            uint gpos = sm_wp[bp][warp];
+#pragma unroll 1
+            for (int u = 0; u < U; u++) {
+                const int q = (warp * U + u) * 32 + lane;
+                uint m = mk[q];
+                const uint c = __popc(m);
+                uint inc = c;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint o = __shfl_up_sync(0xffffffffu, inc, dd);
+                    if (lane >= dd) inc += o;
+                }
+                const uint total = __shfl_sync(0xffffffffu, inc, 31);
+                if (total == 0u) continue;        // warp-uniform
+                uint o = inc - c;
+                const uint first = a.base + (uint)(tile_lo + (dim_t)q * E);
+                while (m) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    strip[o++] = first + k;
+                }
+                __syncwarp();
+                for (uint r = lane; r < total; r += 32) a.out[gpos + r] = strip[r];
+                __syncwarp();
+                gpos += total;
+            }
+        }
+        if (!live) break;
+        tile_prev = tile;
+    }
+}
+
 template<typename T>
 static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base) {
     const dim_t n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
     constexpr dim_t CT = (dim_t)kChainThreads * kCW_U * VecN<T>::value;
+    if (aligned_to(in.ptr, 16) && n >= 4 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
+        typedef PipeWhereLayout<T> PL;
+        auto kern = pipe_where_kernel<T>;
+        static bool configured[64] = {false};
+        const int dv = c.device & 63;
+        if (!configured[dv]) {
+            AFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::total));
+            configured[dv] = true;
+        }
+        ChainWhereArgs<T> a;
+        a.in = (const T *)in.ptr;
+        a.n = n;
+        a.out = out;
+        a.total = d_count;
+        a.ntiles = (n + PL::TILE - 1) / PL::TILE;
+        a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
+        a.gen = c.scratch->next_wepoch(c.stream);
+        a.base = base;
+        dim_t grid = (dim_t)c.sms;
+        if (grid > a.ntiles) grid = a.ntiles;
+        a.ticket = c.scratch->chain_ticket;
+        a.ticket_base = c.scratch->chain_base;
+        c.scratch->chain_base += (unsigned long long)a.ntiles + (unsigned long long)grid;
+        kern<<<(unsigned)grid, kPW_Threads, PL::total, c.stream>>>(a);
+        note_launches(1);
+        post_launch_check("pipe_where_kernel");
+        return;
+    }
     if (aligned_to(in.ptr, 16) && n >= CT && !env_int("AFB200_NO_CHAIN", 0)) {
         constexpr size_t smem = (size_t)CT * sizeof(T) * kChainStages + 8 * 32 * VecN<T>::value * sizeof(uint) + 128;
         auto kern = chain_where_kernel<T>;

@@ -287,3 +287,103 @@ def test_argument_errors(af):
     e0 = af.Array.from_numpy(np.zeros((0,), np.float32))
     assert af.where(e0).elements == 0 and af.sum_all(e0) == 0.0 and af.product_all(e0) == 1.0
     assert af.sum(e0, 0).elements == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the software-pipelined TMA kernels (pipe_scan_kernel / pipe_where_kernel): 4-byte values, long aligned columns
+# ---------------------------------------------------------------------------------------------------------
+PIPE_TILE, PIPE_TILE_KEYED = 12 * 32 * 20, 12 * 32 * 12
+
+
+def _keys(rng, n, kind, dtype):
+    if kind == "same":
+        k = np.zeros(n, dtype)
+    elif kind == "distinct":
+        k = np.arange(n).astype(dtype)
+    elif kind == "long":      # runs longer than several tiles
+        k = np.repeat(rng.integers(0, 3, n // 20000 + 2), rng.integers(15000, 40000, n // 20000 + 2))[:n].astype(dtype)
+    elif kind == "short":
+        k = np.repeat(rng.integers(0, 5, n), rng.integers(1, 9, n))[:n].astype(dtype)
+    else:                     # BASELINE C4: run lengths uniform[1,1024]
+        k = np.repeat(np.arange(n // 256 + 2), rng.integers(1, 1025, n // 256 + 2))[:n].astype(dtype)
+    return k
+
+
+@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32])
+def test_pipe_scan(af, orc, code):
+    rng = np.random.default_rng(9000 + code)
+    shapes = [(4 * PIPE_TILE,), (4 * PIPE_TILE + 1,), (4 * PIPE_TILE + 4,), (5 * PIPE_TILE - 4,), ((1 << 21) + 3,),
+              (40000, 3), (29000, 2, 2), (1 << 22,)]
+    for shape in shapes:
+        base = rand_data(rng, code, shape, nan_frac=0.02, exact=True)
+        g = to_gpu(af, base, None, dtype=code)
+        for op in range(4):
+            if op == po.AF_BINARY_MUL and code in IS_FLOAT:
+                continue
+            for incl in (True, False):
+                t, want = orc.scan(base, 0, op, incl, dtype=code)
+                got = af.scan(g, 0, op, incl)
+                same_bits(got.to_numpy(), d4(want), "pipe scan op%d incl%d %s" % (op, incl, shape))
+    # an aligned column view of a larger parent (strided columns, 16-byte aligned offsets)
+    base = rand_data(rng, code, (60000, 4), exact=True)
+    sl = (slice(8, 8 + 4 * PIPE_TILE + 8), slice(1, 4))
+    g = to_gpu(af, base, sl, dtype=code)
+    for incl in (True, False):
+        t, want = orc.scan(base[sl], 0, 0, incl, dtype=code)
+        same_bits(af.scan(g, 0, 0, incl).to_numpy(), d4(want), "pipe scan view incl%d" % incl)
+
+
+@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32])
+def test_pipe_scan_by_key(af, orc, code):
+    rng = np.random.default_rng(9100 + code)
+    shapes = [(4 * PIPE_TILE_KEYED,), (4 * PIPE_TILE_KEYED + 3,), (6 * PIPE_TILE_KEYED - 4,), ((1 << 21) + 1,), (24000, 3),
+              (1 << 22,)]
+    for shape in shapes:
+        n = int(np.prod(shape))
+        base = rand_data(rng, code, shape, nan_frac=0.02, exact=True)
+        g = to_gpu(af, base, None, dtype=code)
+        for kind in ("same", "distinct", "long", "short", "c4"):
+            for kcode in (po.S32, po.U32):
+                keys = np.asfortranarray(_keys(rng, n, kind, po.NP_OF[kcode]).reshape(shape, order="F"))
+                gk = to_gpu(af, keys, None, dtype=kcode)
+                for op in ((0, 2, 3) if kcode == po.S32 else (0,)):
+                    for incl in (True, False):
+                        t, want = orc.scan_by_key(keys, base, 0, op, incl, dtype=code, key_dtype=kcode)
+                        got = af.scan_by_key(gk, g, 0, op, incl)
+                        same_bits(got.to_numpy(), d4(want), "pipe sbk %s op%d incl%d %s" % (kind, op, incl, shape))
+
+
+@pytest.mark.parametrize("code", [po.U8, po.B8, po.F32, po.S16, po.F64, po.C64])
+def test_pipe_where(af, orc, code):
+    rng = np.random.default_rng(9200 + code)
+    esz = np.dtype(po.NP_OF[code]).itemsize
+    tile = 16 * 4 * 32 * (16 // esz)
+    for n in (4 * tile, 4 * tile + 1, 7 * tile - 5, (1 << 22) + 17):
+        for density in (0.5, 0.01, 0.0, 1.0, 0.9):
+            base = rand_data(rng, code, (n,), small=True)
+            mask = rng.random(n) < density
+            one = np.ones((), base.dtype)
+            base = np.where(mask, np.where(base == 0, one, base), 0 * one).astype(base.dtype)
+            g = to_gpu(af, base, None, dtype=code)
+            want = orc.where(base, dtype=code)
+            got = af.where(g)
+            assert got.dims == (want.size, 1, 1, 1), (n, density, got.dims, want.size)
+            same_bits(got.to_numpy().reshape(-1), want, "pipe where n=%d p=%g" % (n, density))
+
+
+def test_pipe_back_to_back(af, orc):
+    """many launches in a row share the descriptor array (generation tags) and the ticket counter"""
+    rng = np.random.default_rng(9300)
+    n = (1 << 20) + 8
+    x = rng.integers(-4, 5, n).astype(np.int32)
+    k = _keys(rng, n, "c4", np.int32)
+    m = (rng.random(n) < 0.3).astype(np.uint8) * 7
+    gx, gk, gm = af.Array.from_numpy(x), af.Array.from_numpy(k), af.Array.from_numpy(m)
+    w_scan = orc.scan(x, 0, 0, True)[1]
+    w_sbk = orc.scan_by_key(k, x, 0, 0, False)[1]
+    w_where = orc.where(m)
+    for _ in range(25):
+        a, b, c = af.scan(gx, 0, 0, True), af.scan_by_key(gk, gx, 0, 0, False), af.where(gm)
+        same_bits(a.to_numpy(), d4(w_scan), "b2b scan")
+        same_bits(b.to_numpy(), d4(w_sbk), "b2b sbk")
+        same_bits(c.to_numpy().reshape(-1), w_where, "b2b where")
