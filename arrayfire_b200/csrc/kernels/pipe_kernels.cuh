@@ -112,6 +112,64 @@ AFB_DI typename S::State lookback_resolve(const unsigned long long *pd, long lon
 }
 
 // ------------------------------------------------------------------------------------------------
+// walker: R <- R (+) fold of the published aggregates of tiles [pos, end), executed by one full warp.
+// Every CTA keeps its own running fold over ALL tiles of the launch (in ticket order) instead of chasing a
+// chain of published prefixes: a descriptor only ever carries a tile AGGREGATE, every warp-wide load is one
+// coalesced 256-byte request, up to 8 requests are in flight per poll, and the fold order is fixed (bitwise
+// reproducible results for floating-point scans).  With a saturated memory system a synchronous L2 round trip
+// costs 2000-4000 cycles (measured); the prefix chain of the classic decoupled look-back made the distance to
+// the nearest resolved prefix grow with that latency (2-3 x 148 tiles), the walker never waits for anybody's
+// prefix, only for aggregates that were published a tile period earlier.
+// ------------------------------------------------------------------------------------------------
+template<typename S, typename Codec>
+AFB_DI typename S::State walk_fold(const unsigned long long *pd, long long pos, long long end, uint tag, int lane,
+                                   typename S::State R, unsigned long long *npolls = nullptr, int nwin = kPipeWindow) {
+    typedef typename S::State State;
+    while (pos < end) {
+        unsigned long long d[kPipeWindow];
+        uint need = (1u << nwin) - 1u;   // chunks that still have unpublished entries (warp-uniform)
+        const long long wend = (pos + 32LL * nwin < end) ? pos + 32LL * nwin : end;
+        uint spins = 0;
+#pragma unroll
+        for (int q = 0; q < kPipeWindow; q++) d[q] = 0ULL;
+        while (true) {
+#pragma unroll
+            for (int q = 0; q < kPipeWindow; q++) {
+                const long long t = pos + 32 * q + lane;
+                if (((need >> q) & 1u) && t < wend) d[q] = ld_relaxed64(pd + t);
+            }
+            uint still = 0u;
+#pragma unroll
+            for (int q = 0; q < kPipeWindow; q++) {
+                const long long t = pos + 32 * q + lane;
+                const uint lo = (uint)d[q];
+                const bool ok = (t >= wend) || (((lo & ~7u) == tag) && ((lo & 3u) != TILE_INVALID));
+                if (!__all_sync(0xffffffffu, ok)) still |= 1u << q;
+            }
+            if (npolls) (*npolls)++;
+            need = still;
+            if (!need) break;
+            if (++spins > kSpinLimit) __trap();
+        }
+#pragma unroll
+        for (int q = 0; q < kPipeWindow; q++) {
+            if (pos + 32 * q < wend) {                        // warp-uniform
+                const long long t = pos + 32 * q + lane;
+                State v = (t < wend) ? Codec::unpack(d[q]) : S::identity();
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {         // lane + dd holds a LATER tile than lane
+                    State o = shfl_down(v, dd);
+                    if (lane + dd < 32) v = S::join(v, o);
+                }
+                R = S::join(R, shfl_idx(v, 0));
+            }
+        }
+        pos = wend;
+    }
+    return R;
+}
+
+// ------------------------------------------------------------------------------------------------
 // pipe_scan_kernel
 // ------------------------------------------------------------------------------------------------
 // Warp roles of the (single) CTA of an SM:
@@ -125,9 +183,10 @@ AFB_DI typename S::State lookback_resolve(const unsigned long long *pd, long lon
 // Every synchronous L2 round trip (ticket atomic, descriptor poll) costs ~2000 cycles under full HBM load
 // (measured); the roles are split so that none of them sits on the compute warps' path.
 constexpr int kPipeWarps = 12;                      // compute warps
-constexpr int kPipeThreads = 32 * (kPipeWarps + 2); // + look-back warp + DMA warp
-constexpr int kPipeLag = 2;                         // D: pass 2 runs D tiles behind pass 1
-constexpr int kPipeRing = 4;                        // per-tile barrier / scratch ring (> D + 1)
+constexpr int kPipeLB = 2;                          // publisher warp + walker warp
+constexpr int kPipeThreads = 32 * (kPipeWarps + kPipeLB + 1); // + publisher + walker + DMA warp
+constexpr int kPipeLag = 3;                         // D: pass 2 runs D tiles behind pass 1
+constexpr int kPipeRing = 8;                        // per-tile barrier / scratch ring (> D + 1)
 
 template<typename Ti, typename To, typename Tk>
 struct PipeScanArgs {
@@ -147,6 +206,8 @@ struct PipeScanArgs {
     const Tk *carry_key;
     void *summary;
     unsigned long long *debug;   // optional per-CTA cycle counters (AFB200_PIPE_DEBUG=1), 16 words per CTA
+    int ahead;                   // bulk loads in flight ahead of pass 1 (<= STAGES - D - 1)
+    int window;                  // 32-descriptor chunks per walker poll (1..kPipeWindow)
 };
 
 template<bool KEYED, int EPT, int STAGES> struct PipeLayout {
@@ -204,7 +265,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
     kg.s1 = a.ks1; kg.s2 = a.ks2; kg.s3 = a.ks3;
     const uint tag = a.gen << 3;
 
-    if (warp == NW + 1) {
+    if (warp == NW + kPipeLB) {
         // =========================================================================== DMA warp (one thread)
         if (lane != 0) return;
         auto draw = [&]() -> long long { return (long long)(atomicAdd(a.ticket, 1ULL) - a.ticket_base); };
@@ -269,88 +330,91 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                 bulk_wait_read<1>();                  // stores of tiles <= n-1 have finished reading shared memory
             }
             // tile m may be published once the store of tile m - STAGES has drained: m - STAGES <= j - D - 1
-            for (int burst = 0; drawing && burst < 2 && pub <= j + STAGES - D - 1; burst++) publish_next();
+            for (int burst = 0; drawing && burst < 2 && pub <= j + a.ahead; burst++) publish_next();
         }
         bulk_wait_all();
         return;
     }
 
     if (warp == NW) {
-        // =========================================================================== look-back warp
+        // =========================================================================== publisher warp
+        // publishes the aggregate of every tile the moment its warp totals exist (the walkers of all other CTAs
+        // are waiting for it); never blocks on anything but this CTA's own pass 1
+        for (long long j = 0;; j++) {
+            const int s = (int)(j % STAGES), slot = (int)(j % RING);
+            mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
+            const long long tile = sm_tile_id[s];
+            if (tile >= a.ntiles) break;
+            mbar_wait(&p1_bar[slot], (uint32_t)((j / RING) & 1));
+            State st = (lane < NW) ? sm_wtot[slot][lane] : S::identity();
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {     // ordered reduction: lane + dd holds a LATER warp
+                State o = shfl_down(st, dd);
+                if (lane + dd < 32) st = S::join(st, o);
+            }
+            if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(st, tag, TILE_AGGREGATE));
+        }
+        return;
+    }
+
+    if (warp == NW + 1) {
+        // =========================================================================== walker warp
         unsigned long long dbg[4] = {0, 0, 0, 0};
         const long long t_start = clock64();
-        bool pending = false;         // tile j-1 published an aggregate and still needs its prefix
-        long long p_tile = 0;
-        int p_slot = 0;
-        State p_wexc = S::identity(), p_total = S::identity();
-        // prefix known: hand the per-warp carries to pass 2 (and fill the shard summary)
-        auto finalize = [&](long long tile, int slot, State excl, State wexc, State total) {
+        long long pos = 0;                      // R = fold of the tiles [first tile of pos's column, pos)
+        State R = S::identity();
+        if (a.carry) R = S::lift(*a.carry, false);   // sharded scans: one column, the carry sits in front of tile 0
+        for (long long j = 0;; j++) {
+            const int s = (int)(j % STAGES), slot = (int)(j % RING);
+            mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
+            const long long tile = sm_tile_id[s];
+            if (tile >= a.ntiles) break;
+            // ---- advance the running fold to this CTA's tile (foreign aggregates only)
+            const long long c0 = clock64();
+            while (pos < tile) {
+                const long long col_end = (pos / a.tiles_per_col + 1) * a.tiles_per_col;
+                const long long end = tile < col_end ? tile : col_end;
+                R = walk_fold<S, Codec>(a.descs, pos, end, tag, lane, R, a.debug ? &dbg[2] : nullptr, a.window);
+                pos = end;
+                if (pos == col_end) R = S::identity();   // a new column starts
+            }
+            dbg[1] += clock64() - c0;
+            // ---- own tile: per-warp carries for pass 2
+            mbar_wait(&p1_bar[slot], (uint32_t)((j / RING) & 1));
+            State st = (lane < NW) ? sm_wtot[slot][lane] : S::identity();
+#pragma unroll
+            for (int dd = 1; dd < NW; dd <<= 1) {
+                State o = shfl_up(st, dd);
+                if (lane >= dd) st = S::join(o, st);
+            }
+            const State tile_total = shfl_idx(st, NW - 1);
+            State wexc = shfl_up(st, 1);
+            if (lane == 0) wexc = S::identity();
             const dim_t tcol = tile % a.tiles_per_col;
             if (a.summary) {
                 if (KEYED) {
                     uint fh = (lane < NW) ? sm_wfh[slot][lane] : (uint)WCHUNK;
-                    uint pos = fh < (uint)WCHUNK ? (uint)(lane * WCHUNK) + fh : 0xffffffffu;
-                    pos = __reduce_min_sync(0xffffffffu, pos);
-                    if (lane == 0 && pos != 0xffffffffu)
+                    uint hp = fh < (uint)WCHUNK ? (uint)(lane * WCHUNK) + fh : 0xffffffffu;
+                    hp = __reduce_min_sync(0xffffffffu, hp);
+                    if (lane == 0 && hp != 0xffffffffu)
                         atomicMin(reinterpret_cast<unsigned long long *>((char *)a.summary + 24),
-                                  (unsigned long long)(tcol * TILE + pos));
+                                  (unsigned long long)(tcol * TILE + hp));
                 }
                 if (lane == 0 && tcol == a.tiles_per_col - 1) {
-                    const State fin = S::join(excl, total);
+                    const State fin = S::join(R, tile_total);
                     *reinterpret_cast<Slot<To> *>(a.summary) = Slot<To>{S::value(fin)};
                     uint flag = 0;
                     if constexpr (KEYED) flag = fin.flag ? 1u : 0u;
                     *reinterpret_cast<uint *>((char *)a.summary + 16) = flag;
                 }
             }
-            if (lane < NW) sm_wp[slot][lane] = S::value(S::join(excl, wexc));
+            if (lane < NW) sm_wp[slot][lane] = S::value(S::join(R, wexc));
             __syncwarp();
             if (lane == 0) mbar_arrive(&lb_bar[slot]);
-        };
-        for (long long j = 0;; j++) {
-            const int s = (int)(j % STAGES), slot = (int)(j % RING);
-            mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
-            const long long tile = sm_tile_id[s];
-            const bool live = tile < a.ntiles;
-            bool pending_cur = false;
-            State wexc = S::identity(), tile_total = S::identity();
-            if (live) {
-                const dim_t tcol = tile % a.tiles_per_col;
-                mbar_wait(&p1_bar[slot], (uint32_t)((j / RING) & 1));
-                State st = (lane < NW) ? sm_wtot[slot][lane] : S::identity();
-#pragma unroll
-                for (int dd = 1; dd < NW; dd <<= 1) {
-                    State o = shfl_up(st, dd);
-                    if (lane >= dd) st = S::join(o, st);
-                }
-                tile_total = shfl_idx(st, NW - 1);
-                wexc = shfl_up(st, 1);
-                if (lane == 0) wexc = S::identity();
-                if (tcol == 0) {
-                    State excl = S::identity();
-                    if (a.carry) excl = S::lift(*a.carry, false);
-                    if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(S::join(excl, tile_total), tag, TILE_PREFIX));
-                    finalize(tile, slot, excl, wexc, tile_total);
-                } else {
-                    if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(tile_total, tag, TILE_AGGREGATE));
-                    pending_cur = true;
-                }
-                dbg[3]++;
-            }
-            if (pending) {
-                const long long c0 = clock64();
-                const dim_t tcol = p_tile % a.tiles_per_col;
-                const State excl = lookback_resolve<S, Codec, KEYED>(a.descs, p_tile, p_tile - tcol, tag, lane, a.debug ? &dbg[2] : nullptr);
-                if (lane == 0) st_relaxed64(&a.descs[p_tile], Codec::pack(S::join(excl, p_total), tag, TILE_PREFIX));
-                finalize(p_tile, p_slot, excl, p_wexc, p_total);
-                dbg[1] += clock64() - c0;
-            }
-            if (!live) break;
-            pending = pending_cur;
-            p_tile = tile;
-            p_slot = slot;
-            p_wexc = wexc;
-            p_total = tile_total;
+            R = S::join(R, tile_total);
+            pos = tile + 1;
+            if (pos % a.tiles_per_col == 0) R = S::identity();
+            dbg[3]++;
         }
         if (a.debug && lane == 0) {
             dbg[0] = clock64() - t_start;
@@ -362,7 +426,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
     // =============================================================================== compute warps
     const int t = warp * 32 + lane;          // 0 .. NW*32-1
     const int base = t * EPT;                // first element of this thread inside the tile
-    uint fh0 = WCHUNK, fh1 = WCHUNK, fh2 = WCHUNK;   // first head of the warp's chunk in tiles i, i-1, i-2
+    uint fh0 = WCHUNK, fh1 = WCHUNK, fh2 = WCHUNK, fh3 = WCHUNK;   // first head of the warp's chunk in tiles i .. i-3
+    static_assert(kPipeLag == 3, "the fh register ring below is written for D = 3");
     unsigned long long cw_full = 0, cw_lb = 0, cw_p1 = 0, cw_p2 = 0;
     bool ended = false;
     long long n_live = 0;                    // valid once `ended`
@@ -502,7 +567,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
             // elements of this thread that are still "open" towards the warp's left edge
             int nadd = EPT;
             if (KEYED) {
-                const int d = (int)fh2 - lane * EPT;
+                const int d = (int)fh3 - lane * EPT;
                 nadd = d < 0 ? 0 : (d > EPT ? EPT : d);
             }
             if (valid == TILE) {
@@ -538,6 +603,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
         } else if (ended && n_live == 0) {
             break;
         }
+        fh3 = fh2;
         fh2 = fh1;
         fh1 = fh0;
     }

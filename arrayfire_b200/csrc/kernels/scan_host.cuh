@@ -89,6 +89,11 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
                     a.gen = c.scratch->next_wepoch(c.stream);
                     a.carry = (const To *)carry;
                     a.carry_key = (const Tk *)carry_key;
+                    a.ahead = env_int("AFB200_PIPE_AHEAD", ST - kPipeLag - 1);
+                    if (a.ahead > ST - kPipeLag - 1) a.ahead = ST - kPipeLag - 1;
+                    if (a.ahead < 1) a.ahead = 1;
+                    a.window = env_int("AFB200_PIPE_WINDOW", kPipeWindow);
+                    if (a.window < 1 || a.window > kPipeWindow) a.window = kPipeWindow;
                     dim_t grid = (dim_t)c.sms;
                     if (grid > a.ntiles) grid = a.ntiles;
                     a.ticket = c.scratch->chain_ticket;
