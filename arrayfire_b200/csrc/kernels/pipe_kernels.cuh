@@ -308,6 +308,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
         auto publish_next = [&]() {
             const long long t = tk0;
             tk0 = tk1;
+            // keys: stage pub % KST is free once pass 1 of tile pub - KST has read it (pass 1 arrives on p1_bar after
+            // its key loads; tiles are processed in order, so this wait can never block the tile it waits for)
+            if (KEYED && pub >= KST) mbar_wait(&p1_bar[(pub - KST) % RING], (uint32_t)(((pub - KST) / RING) & 1));
             publish(pub, t);
             pub++;
             if (t >= a.ntiles) { drawing = false; n_live = pub - 1; }
@@ -330,7 +333,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                 bulk_wait_read<1>();                  // stores of tiles <= n-1 have finished reading shared memory
             }
             // tile m may be published once the store of tile m - STAGES has drained: m - STAGES <= j - D - 1
-            for (int burst = 0; drawing && burst < 2 && pub <= j + a.ahead; burst++) publish_next();
+            const long long lim = j + a.ahead;
+            for (int burst = 0; drawing && burst < 2 && pub <= lim; burst++) publish_next();
         }
         bulk_wait_all();
         return;

@@ -384,25 +384,31 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_where_kernel(const Cha
 }
 
 // ------------------------------------------------------------------------------------------------
-// pipe_where_kernel: the software-pipelined compaction (same skeleton as pipe_scan_kernel, pipe_kernels.cuh)
+// pipe_where_kernel: the software-pipelined compaction (same machinery as pipe_scan_kernel, pipe_kernels.cuh)
 // ------------------------------------------------------------------------------------------------
-// One CTA per SM: kPW_Warps compute warps + 1 control warp.  Pass 1 of tile i turns every 16-byte vector into
-// a bit mask (kept in shared memory) and counts; the control warp publishes the tile count, resolves the tile's
-// output offset with the 256-wide packed look-back and refills the ring; pass 2 of tile i-1 (executed after pass
-// 1 of tile i, so the look-back latency is hidden) compacts 512 bytes of input at a time through a per-warp
-// strip and flushes it with coalesced stores.  No CTA-wide barrier on the fast path.
+// One CTA per SM: 16 compute warps + publisher + walker + DMA warp.  A tile is kPW_Sub sub-tiles of 32 KB, each
+// staged by one bulk-async copy.  Pass 1 of tile i turns every 16-byte vector into a bit mask (kept in shared
+// memory: the stage itself is released for refill immediately) and counts per (sub-tile, warp); the publisher
+// makes the tile count visible to the other CTAs; the walker keeps the running count of ALL earlier tiles
+// (walk_fold: coalesced reads of published counts, no prefix chain); pass 2 of tile i-1 -- executed after pass 1
+// of tile i, so the walker's L2 round trip (2000-4000 cycles under load) is hidden -- compacts 512 bytes of input
+// at a time through a per-warp strip and flushes it with coalesced stores.  Tiles are large (128 KB of input)
+// because one walker step per tile must fit into the tile period even for a sparse mask.
 constexpr int kPW_Warps = 16;
-constexpr int kPW_U = 4;        // 512-byte slots per warp per tile
+constexpr int kPW_U = 4;        // 512-byte slots per warp per sub-tile
+constexpr int kPW_Sub = 4;      // sub-tiles (bulk copies) per tile
 constexpr int kPW_Stages = 4;
-constexpr int kPW_Threads = 32 * (kPW_Warps + 1);
+constexpr int kPW_Ring = 4;     // per-tile barrier / scratch ring
+constexpr int kPW_Threads = 32 * (kPW_Warps + 3);
 
 template<typename T> struct PipeWhereLayout {
     static constexpr int E = VecN<T>::value;
-    static constexpr int NVEC = kPW_Warps * kPW_U * 32;          // 16-byte vectors per tile
-    static constexpr int TILE = NVEC * E;                        // elements per tile
+    static constexpr int NVEC = kPW_Warps * kPW_U * 32;          // 16-byte vectors per sub-tile
+    static constexpr int SUBTILE = NVEC * E;                     // elements per sub-tile
+    static constexpr int TILE = SUBTILE * kPW_Sub;               // elements per tile
     static constexpr size_t stage_bytes = (size_t)NVEC * 16;     // 32 KB
     static constexpr size_t strip_bytes = (size_t)kPW_Warps * 32 * E * sizeof(uint);
-    static constexpr size_t mask_bytes = (size_t)2 * NVEC * sizeof(unsigned short);
+    static constexpr size_t mask_bytes = (size_t)2 * kPW_Sub * NVEC * sizeof(unsigned short);
     static constexpr size_t total = stage_bytes * kPW_Stages + strip_bytes + mask_bytes + 128;
 };
 
@@ -413,26 +419,36 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     typedef SOps<R, uint, false> S;
     typedef DescCodec<S, uint, false> Codec;
     constexpr int E = Lay::E;
-    constexpr int TILE = Lay::TILE;
-    constexpr int U = kPW_U, NW = kPW_Warps, ST = kPW_Stages;
+    constexpr int TILE = Lay::TILE, SUBTILE = Lay::SUBTILE;
+    constexpr int U = kPW_U, NW = kPW_Warps, ST = kPW_Stages, SUB = kPW_Sub, RING = kPW_Ring;
+    constexpr int NE = SUB * NW;     // (sub-tile, warp) count entries per tile: 64 = two per lane
+    static_assert(NE == 64, "publisher / walker handle two entries per lane");
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char *stage_base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint *strips = reinterpret_cast<uint *>(stage_base + Lay::stage_bytes * ST);
     unsigned short *masks = reinterpret_cast<unsigned short *>(stage_base + Lay::stage_bytes * ST + Lay::strip_bytes);
-    __shared__ uint64_t full_bar[ST];
-    __shared__ uint64_t p1_bar[2], lb_bar[2];
-    __shared__ long long sm_tile_id[ST];
-    __shared__ uint sm_wtot[2][NW];
-    __shared__ uint sm_wp[2][NW];
+    __shared__ uint64_t full_bar[ST], empty_bar[ST];
+    __shared__ uint64_t p1_bar[RING], pub_bar[RING], lb_bar[RING];
+    __shared__ long long sm_stage_tile[ST];     // tile of the sub-tile staged here (or an end marker)
+    __shared__ int sm_stage_valid[ST];          // valid elements of that sub-tile; SUBTILE: staged by a bulk copy
+    __shared__ long long sm_tile_of[RING];      // tile handled in this ring slot (written by pass 1)
+    __shared__ uint sm_wtot[RING][NE];          // hits per (sub-tile, warp)
+    __shared__ uint sm_wexc[RING][NE];          // exclusive offsets inside the tile
+    __shared__ uint sm_total[RING];
+    __shared__ uint sm_wp[RING][NE];            // absolute output offsets
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < ST; s++) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < ST; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], NW);
+        }
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < RING; b++) {
             mbar_init(&p1_bar[b], NW);
+            mbar_init(&pub_bar[b], 1);
             mbar_init(&lb_bar[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -440,148 +456,182 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     __syncthreads();
     const uint tag = a.gen << 3;
 
-    if (warp == NW) {
-        // =========================================================================== control warp
-        long long next_ticket = 0;
-        bool drawing = true;
+    if (warp == NW + 2) {
+        // =========================================================================== DMA warp (one thread)
+        if (lane != 0) return;
         auto draw = [&]() -> long long { return (long long)(atomicAdd(a.ticket, 1ULL) - a.ticket_base); };
-        auto publish = [&](int s, long long tile) {
-            sm_tile_id[s] = tile;
-            if (tile >= a.ntiles) {
-                mbar_arrive(&full_bar[s]);
-                return;
+        long long m = 0;                       // sub-tiles published so far; sub-tile m lives in stage m % ST
+        long long tk0 = draw(), tk1 = draw();  // tickets are drawn two tiles ahead of their use
+        while (true) {
+            const long long tile = tk0;
+            tk0 = tk1;
+            const bool live = tile < a.ntiles;
+            if (live) tk1 = draw();
+            for (int sub = 0; sub < (live ? SUB : 1); sub++, m++) {
+                const int s = (int)(m % ST);
+                if (m >= ST) mbar_wait(&empty_bar[s], (uint32_t)(((m / ST) - 1) & 1));   // pass 1 is done with the stage
+                sm_stage_tile[s] = tile;
+                if (!live) {
+                    sm_stage_valid[s] = 0;
+                    mbar_arrive(&full_bar[s]);
+                    break;
+                }
+                const dim_t lo = tile * TILE + (dim_t)sub * SUBTILE;
+                const dim_t left = a.n - lo;
+                const int valid = left >= SUBTILE ? SUBTILE : (left > 0 ? (int)left : 0);
+                sm_stage_valid[s] = valid;
+                if (valid == SUBTILE) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)Lay::stage_bytes);
+                    bulk_g2s(stage_base + (size_t)s * Lay::stage_bytes, a.in + lo, (uint32_t)Lay::stage_bytes, &full_bar[s]);
+                } else {
+                    mbar_arrive(&full_bar[s]);   // ragged / empty sub-tile: filled (zero-padded) by the compute warps
+                }
             }
-            const dim_t tile_lo = tile * TILE;
-            if (tile_lo + TILE <= a.n) {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)Lay::stage_bytes);
-                bulk_g2s(stage_base + (size_t)s * Lay::stage_bytes, a.in + tile_lo, (uint32_t)Lay::stage_bytes, &full_bar[s]);
-            } else {
-                mbar_arrive(&full_bar[s]);   // ragged last tile: copied (zero-padded) by the compute warps
-            }
-        };
-        // tickets are drawn one tile period apart, never a whole ring at once (see pipe_scan_kernel)
-        long long pub = 0;
-        auto publish_next = [&]() {
-            const long long t = next_ticket;
-            publish((int)(pub % ST), t);
-            pub++;
-            if (t >= a.ntiles) drawing = false;
-            else next_ticket = draw();
-        };
-        if (lane == 0) {
-            next_ticket = draw();
-            publish_next();
-            if (drawing) publish_next();
-        }
-        __syncwarp();
-        for (uint j = 0;; j++) {
-            const int s = j % ST, b = j & 1;
-            long long tile = 0;
-            if (lane == 0) tile = sm_tile_id[s];                 // lane 0 wrote it (and will overwrite it below)
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-            if (tile >= a.ntiles) break;
-            mbar_wait(&p1_bar[b], (j >> 1) & 1);
-            // pass 1 has turned the stage of tile j into masks: tiles up to j + ST may be in the ring
-            if (lane == 0) {
-                for (int burst = 0; drawing && burst < 2 && pub <= (long long)j + ST; burst++) publish_next();
-            }
-            uint st = (lane < NW) ? sm_wtot[b][lane] : 0u;
-#pragma unroll
-            for (int dd = 1; dd < NW; dd <<= 1) {
-                const uint o = __shfl_up_sync(0xffffffffu, st, dd);
-                if (lane >= dd) st += o;
-            }
-            const uint tile_total = __shfl_sync(0xffffffffu, st, NW - 1);
-            uint wexc = __shfl_up_sync(0xffffffffu, st, 1);
-            if (lane == 0) wexc = 0u;
-            uint excl = 0u;
-            if (tile == 0) {
-                if (lane == 0) st_relaxed64(&a.descs[0], Codec::pack(tile_total, tag, TILE_PREFIX));
-            } else {
-                if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(tile_total, tag, TILE_AGGREGATE));
-                excl = lookback_resolve<S, Codec, false>(a.descs, tile, 0, tag, lane);
-                if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(excl + tile_total, tag, TILE_PREFIX));
-            }
-            if (lane < NW) sm_wp[b][lane] = excl + wexc;
-            if (lane == 0 && tile == a.ntiles - 1) *a.total = (unsigned long long)excl + tile_total;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&lb_bar[b]);
-            __syncwarp();
+            if (!live) break;
         }
         return;
     }
 
-    // =============================================================================== compute warps
-    uint *strip = strips + warp * (32 * E);
-    long long tile_prev = 0;
-    for (uint i = 0;; i++) {
-        const int s = i % ST, b = i & 1;
-        mbar_wait(&full_bar[s], (i / ST) & 1);
-        const long long tile = sm_tile_id[s];
-        const bool live = tile < a.ntiles;
-        if (live) {
-            // ---------------------------------------------------------------- pass 1 of tile i: masks + counts
-            const dim_t tile_lo = tile * TILE;
-            unsigned char *stg = stage_base + (size_t)s * Lay::stage_bytes;
-            if (tile_lo + TILE > a.n) {
-                T *dst = reinterpret_cast<T *>(stg);
-                const int valid = (int)(a.n - tile_lo);
-                for (int e = warp * 32 + lane; e < TILE; e += NW * 32) {
-                    if (e < valid) dst[e] = ldg_stream<T>(a.in + tile_lo + e);
-                    else memset(&dst[e], 0, sizeof(T));
-                }
-                named_bar_sync(1, NW * 32);
-            }
-            unsigned short *mk = masks + (size_t)b * Lay::NVEC;
-            uint cnt = 0;
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int q = (warp * U + u) * 32 + lane;
-                const Vec16 v = *reinterpret_cast<const Vec16 *>(stg + (size_t)q * 16);
-                const uint m = nonzero_mask<T>(v);
-                mk[q] = (unsigned short)m;
-                cnt += __popc(m);
-            }
-            cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) sm_wtot[b][warp] = cnt;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p1_bar[b]);
-        }
-        if (i >= 1) {
-            // ---------------------------------------------------------------- pass 2 of tile i-1: compaction
-            const int bp = (i - 1) & 1;
-            mbar_wait(&lb_bar[bp], ((i - 1) >> 1) & 1);
-            const dim_t tile_lo = tile_prev * TILE;
-            const unsigned short *mk = masks + (size_t)bp * Lay::NVEC;
-            uint gpos = sm_wp[bp][warp];
-#pragma unroll 1
-            for (int u = 0; u < U; u++) {
-                const int q = (warp * U + u) * 32 + lane;
-                uint m = mk[q];
-                const uint c = __popc(m);
-                uint inc = c;
+    if (warp == NW) {
+        // =========================================================================== publisher warp
+        for (long long j = 0;; j++) {
+            const int slot = (int)(j % RING);
+            mbar_wait(&p1_bar[slot], (uint32_t)((j / RING) & 1));
+            const long long tile = sm_tile_of[slot];
+            if (tile < a.ntiles) {
+                const uint v0 = sm_wtot[slot][2 * lane], v1 = sm_wtot[slot][2 * lane + 1];
+                uint inc = v0 + v1;
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
                     const uint o = __shfl_up_sync(0xffffffffu, inc, dd);
                     if (lane >= dd) inc += o;
                 }
                 const uint total = __shfl_sync(0xffffffffu, inc, 31);
-                if (total == 0u) continue;        // warp-uniform
-                uint o = inc - c;
-                const uint first = a.base + (uint)(tile_lo + (dim_t)q * E);
-                while (m) {
-                    const int k = __ffs(m) - 1;
-                    m &= m - 1;
-                    strip[o++] = first + k;
+                if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(total, tag, TILE_AGGREGATE));
+                sm_wexc[slot][2 * lane] = inc - v0 - v1;
+                sm_wexc[slot][2 * lane + 1] = inc - v1;
+                if (lane == 0) sm_total[slot] = total;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pub_bar[slot]);
+            if (tile >= a.ntiles) break;
+        }
+        return;
+    }
+
+    if (warp == NW + 1) {
+        // =========================================================================== walker warp
+        long long pos = 0;      // R = hits in the tiles [0, pos)
+        uint R = 0u;
+        for (long long j = 0;; j++) {
+            const int slot = (int)(j % RING);
+            mbar_wait(&pub_bar[slot], (uint32_t)((j / RING) & 1));
+            const long long tile = sm_tile_of[slot];
+            if (tile >= a.ntiles) break;
+            R = walk_fold<S, Codec>(a.descs, pos, tile, tag, lane, R);
+            sm_wp[slot][2 * lane] = R + sm_wexc[slot][2 * lane];
+            sm_wp[slot][2 * lane + 1] = R + sm_wexc[slot][2 * lane + 1];
+            const uint total = sm_total[slot];
+            if (lane == 0 && tile == a.ntiles - 1) *a.total = (unsigned long long)R + total;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lb_bar[slot]);
+            R += total;
+            pos = tile + 1;
+        }
+        return;
+    }
+
+    // =============================================================================== compute warps
+    uint *strip = strips + warp * (32 * E);
+    long long m = 0;            // sub-tile counter (matches the DMA warp's)
+    long long tile_prev = 0;
+    bool ended = false;
+    for (long long i = 0;; i++) {
+        const int b = (int)(i % RING);
+        // ---------------------------------------------------------------- pass 1 of tile i: masks + counts
+        long long tile = 0;
+        unsigned short *mk = masks + (size_t)(i & 1) * (SUB * Lay::NVEC);
+        uint cnts[SUB];
+#pragma unroll 1
+        for (int sub = 0; sub < SUB; sub++) {
+            const int s = (int)(m % ST);
+            mbar_wait(&full_bar[s], (uint32_t)((m / ST) & 1));
+            if (sub == 0) {
+                tile = sm_stage_tile[s];
+                if (tile >= a.ntiles) {
+                    ended = true;
+                    break;
                 }
-                __syncwarp();
-                for (uint r = lane; r < total; r += 32) a.out[gpos + r] = strip[r];
-                __syncwarp();
-                gpos += total;
+            }
+            unsigned char *stg = stage_base + (size_t)s * Lay::stage_bytes;
+            const int valid = sm_stage_valid[s];
+            if (valid != SUBTILE) {
+                T *dst = reinterpret_cast<T *>(stg);
+                const dim_t lo = tile * TILE + (dim_t)sub * SUBTILE;
+                for (int e = warp * 32 + lane; e < SUBTILE; e += NW * 32) {
+                    if (e < valid) dst[e] = ldg_stream<T>(a.in + lo + e);
+                    else memset(&dst[e], 0, sizeof(T));
+                }
+                named_bar_sync(1, NW * 32);
+            }
+            uint cnt = 0;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int q = (warp * U + u) * 32 + lane;
+                const Vec16 v = *reinterpret_cast<const Vec16 *>(stg + (size_t)q * 16);
+                const uint mm = nonzero_mask<T>(v);
+                mk[sub * Lay::NVEC + q] = (unsigned short)mm;
+                cnt += __popc(mm);
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            cnts[sub] = cnt;
+            if (lane == 0) {
+                sm_wtot[b][sub * NW + warp] = cnt;
+                mbar_arrive(&empty_bar[s]);   // the stage may be refilled (the reduce above ordered every lane's reads)
+            }
+            m++;
+        }
+        if (lane == 0 && warp == 0) sm_tile_of[b] = ended ? a.ntiles : tile;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p1_bar[b]);
+        if (i >= 1) {
+            // ---------------------------------------------------------------- pass 2 of tile i-1: compaction
+            const int bp = (int)((i - 1) % RING);
+            mbar_wait(&lb_bar[bp], (uint32_t)(((i - 1) / RING) & 1));
+            const unsigned short *mkp = masks + (size_t)((i - 1) & 1) * (SUB * Lay::NVEC);
+#pragma unroll 1
+            for (int sub = 0; sub < SUB; sub++) {
+                uint gpos = sm_wp[bp][sub * NW + warp];
+                const dim_t sub_lo = tile_prev * TILE + (dim_t)sub * SUBTILE;
+#pragma unroll 1
+                for (int u = 0; u < U; u++) {
+                    const int q = (warp * U + u) * 32 + lane;
+                    uint mm = mkp[sub * Lay::NVEC + q];
+                    const uint c = __popc(mm);
+                    uint inc = c;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const uint o = __shfl_up_sync(0xffffffffu, inc, dd);
+                        if (lane >= dd) inc += o;
+                    }
+                    const uint total = __shfl_sync(0xffffffffu, inc, 31);
+                    if (total == 0u) continue;        // warp-uniform
+                    uint o = inc - c;
+                    const uint first = a.base + (uint)(sub_lo + (dim_t)q * E);
+                    while (mm) {
+                        const int k = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        strip[o++] = first + k;
+                    }
+                    __syncwarp();
+                    for (uint r = lane; r < total; r += 32) a.out[gpos + r] = strip[r];
+                    __syncwarp();
+                    gpos += total;
+                }
             }
         }
-        if (!live) break;
+        if (ended) break;
         tile_prev = tile;
     }
 }
@@ -590,7 +640,7 @@ template<typename T>
 static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base) {
     const dim_t n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
     constexpr dim_t CT = (dim_t)kChainThreads * kCW_U * VecN<T>::value;
-    if (aligned_to(in.ptr, 16) && n >= 4 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
+    if (aligned_to(in.ptr, 16) && n >= 2 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
         typedef PipeWhereLayout<T> PL;
         auto kern = pipe_where_kernel<T>;
         static bool configured[64] = {false};
@@ -612,7 +662,7 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         if (grid > a.ntiles) grid = a.ntiles;
         a.ticket = c.scratch->chain_ticket;
         a.ticket_base = c.scratch->chain_base;
-        c.scratch->chain_base += (unsigned long long)a.ntiles + (unsigned long long)grid;
+        c.scratch->chain_base += (unsigned long long)a.ntiles + 2ULL * (unsigned long long)grid;  // two tickets in flight per CTA
         kern<<<(unsigned)grid, kPW_Threads, PL::total, c.stream>>>(a);
         note_launches(1);
         post_launch_check("pipe_where_kernel");

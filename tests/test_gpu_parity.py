@@ -357,8 +357,9 @@ def test_pipe_scan_by_key(af, orc, code):
 def test_pipe_where(af, orc, code):
     rng = np.random.default_rng(9200 + code)
     esz = np.dtype(po.NP_OF[code]).itemsize
-    tile = 16 * 4 * 32 * (16 // esz)
-    for n in (4 * tile, 4 * tile + 1, 7 * tile - 5, (1 << 22) + 17):
+    tile = 4 * 16 * 4 * 32 * (16 // esz)
+    sub = tile // 4
+    for n in (2 * tile, 2 * tile + 1, 3 * tile - 5, 2 * tile + sub + 3, 2 * tile + 2 * sub, (1 << 22) + 17):
         for density in (0.5, 0.01, 0.0, 1.0, 0.9):
             base = rand_data(rng, code, (n,), small=True)
             mask = rng.random(n) < density
