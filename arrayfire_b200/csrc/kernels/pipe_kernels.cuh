@@ -150,6 +150,7 @@ AFB_DI typename S::State walk_fold(const unsigned long long *pd, long long pos, 
             need = still;
             if (!need) break;
             if (++spins > kSpinLimit) __trap();
+            __nanosleep(100);   // the missing aggregates are at least a publish + L2 round trip away
         }
 #pragma unroll
         for (int q = 0; q < kPipeWindow; q++) {
@@ -183,8 +184,9 @@ AFB_DI typename S::State walk_fold(const unsigned long long *pd, long long pos, 
 // Every synchronous L2 round trip (ticket atomic, descriptor poll) costs ~2000 cycles under full HBM load
 // (measured); the roles are split so that none of them sits on the compute warps' path.
 constexpr int kPipeWarps = 12;                      // compute warps
-constexpr int kPipeLB = 2;                          // publisher warp + walker warp
-constexpr int kPipeThreads = 32 * (kPipeWarps + kPipeLB + 1); // + publisher + walker + DMA warp
+constexpr int kPipeWalkers = 2;                     // walker warps; walker k resolves the tiles j = k (mod kPipeWalkers)
+constexpr int kPipeLB = 1 + kPipeWalkers;           // publisher warp + walker warps
+constexpr int kPipeThreads = 32 * (kPipeWarps + kPipeLB + 1); // + publisher + walkers + DMA warp
 constexpr int kPipeLag = 3;                         // D: pass 2 runs D tiles behind pass 1
 constexpr int kPipeRing = 8;                        // per-tile barrier / scratch ring (> D + 1)
 
@@ -246,6 +248,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
     __shared__ State sm_wtot[RING][NW];
     __shared__ uint sm_wfh[RING][NW];            // first segment head inside the warp's chunk (WCHUNK: none)
     __shared__ To sm_wp[RING][NW];               // value carried into each warp's chunk
+    __shared__ State sm_R[RING];                 // running fold handed from walker to walker
+    __shared__ uint64_t r_bar[RING];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -256,7 +260,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
             mbar_init(&p1_bar[b], NW);
             mbar_init(&lb_bar[b], 1);
             mbar_init(&p2_bar[b], NW);
+            mbar_init(&r_bar[b], 1);
         }
+        mbar_arrive(&r_bar[0]);   // tile 0 has no predecessor: its hand-over phase is completed here
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -361,28 +367,41 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
         return;
     }
 
-    if (warp == NW + 1) {
-        // =========================================================================== walker warp
+    if (warp > NW) {
+        // =========================================================================== walker warps
+        // Walker k resolves this CTA's tiles j = k (mod kPipeWalkers).  The expensive part -- F_j, the fold of the
+        // foreign aggregates published between this CTA's tiles j-1 and j (one loaded L2 round trip, 3000+ cycles,
+        // more than a tile period) -- does not depend on anything this CTA computes, so the walkers overlap it;
+        // only the cheap chain R_j = R_{j-1} (+) total_{j-1} (+) F_j is handed from walker to walker through
+        // shared memory (sm_R / r_bar).
+        const int wk = warp - NW - 1;
         unsigned long long dbg[4] = {0, 0, 0, 0};
         const long long t_start = clock64();
-        long long pos = 0;                      // R = fold of the tiles [first tile of pos's column, pos)
-        State R = S::identity();
-        if (a.carry) R = S::lift(*a.carry, false);   // sharded scans: one column, the carry sits in front of tile 0
+        long long prev = -1;                    // this CTA's previous tile
         for (long long j = 0;; j++) {
             const int s = (int)(j % STAGES), slot = (int)(j % RING);
-            mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));
+            mbar_wait(&full_bar[s], (uint32_t)((j / STAGES) & 1));   // every walker follows the tile stream
             const long long tile = sm_tile_id[s];
             if (tile >= a.ntiles) break;
-            // ---- advance the running fold to this CTA's tile (foreign aggregates only)
-            const long long c0 = clock64();
-            while (pos < tile) {
-                const long long col_end = (pos / a.tiles_per_col + 1) * a.tiles_per_col;
-                const long long end = tile < col_end ? tile : col_end;
-                R = walk_fold<S, Codec>(a.descs, pos, end, tag, lane, R, a.debug ? &dbg[2] : nullptr, a.window);
-                pos = end;
-                if (pos == col_end) R = S::identity();   // a new column starts
+            if ((int)(j % kPipeWalkers) != wk) {
+                prev = tile;
+                continue;
             }
+            // ---- F: foreign tiles between the previous own tile and this one, not reaching back over a column start
+            const long long c0 = clock64();
+            const long long cstart = tile - tile % a.tiles_per_col;
+            const bool chained = prev >= cstart;                    // the previous own tile sits in the same column
+            const long long from = chained ? prev + 1 : cstart;
+            State F = walk_fold<S, Codec>(a.descs, from, tile, tag, lane, S::identity(), a.debug ? &dbg[2] : nullptr, a.window);
             dbg[1] += clock64() - c0;
+            // ---- R: everything in this column up to and including the previous own tile
+            State excl = F;
+            if (chained) {
+                mbar_wait(&r_bar[slot], (uint32_t)((j / RING) & 1));
+                excl = S::join(sm_R[slot], F);
+            } else if (cstart == 0 && a.carry) {
+                excl = S::join(S::lift(*a.carry, false), F);   // sharded scans: the carry sits in front of tile 0
+            }
             // ---- own tile: per-warp carries for pass 2
             mbar_wait(&p1_bar[slot], (uint32_t)((j / RING) & 1));
             State st = (lane < NW) ? sm_wtot[slot][lane] : S::identity();
@@ -405,22 +424,25 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                                   (unsigned long long)(tcol * TILE + hp));
                 }
                 if (lane == 0 && tcol == a.tiles_per_col - 1) {
-                    const State fin = S::join(R, tile_total);
+                    const State fin = S::join(excl, tile_total);
                     *reinterpret_cast<Slot<To> *>(a.summary) = Slot<To>{S::value(fin)};
                     uint flag = 0;
                     if constexpr (KEYED) flag = fin.flag ? 1u : 0u;
                     *reinterpret_cast<uint *>((char *)a.summary + 16) = flag;
                 }
             }
-            if (lane < NW) sm_wp[slot][lane] = S::value(S::join(R, wexc));
+            if (lane < NW) sm_wp[slot][lane] = S::value(S::join(excl, wexc));
+            // hand the running fold to the walker of this CTA's next tile
+            if (lane == 0) sm_R[(slot + 1) % RING] = S::join(excl, tile_total);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&lb_bar[slot]);
-            R = S::join(R, tile_total);
-            pos = tile + 1;
-            if (pos % a.tiles_per_col == 0) R = S::identity();
+            if (lane == 0) {
+                mbar_arrive(&lb_bar[slot]);
+                mbar_arrive(&r_bar[(slot + 1) % RING]);
+            }
+            prev = tile;
             dbg[3]++;
         }
-        if (a.debug && lane == 0) {
+        if (a.debug && lane == 0 && wk == 0) {
             dbg[0] = clock64() - t_start;
             for (int q = 0; q < 4; q++) a.debug[blockIdx.x * 16 + q] = dbg[q];
         }
