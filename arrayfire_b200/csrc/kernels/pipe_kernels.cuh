@@ -215,7 +215,7 @@ struct PipeScanArgs {
 template<bool KEYED, int EPT, int STAGES> struct PipeLayout {
     static constexpr int TILE = kPipeWarps * 32 * EPT;
     static constexpr int KPAD = 4;                                  // key elements kept in front of the tile
-    static constexpr int KSTAGES = KEYED ? STAGES - kPipeLag - 1 : 0;   // keys are dead after pass 1
+    static constexpr int KSTAGES = KEYED ? STAGES - kPipeLag : 0;       // keys are dead after pass 1
     static constexpr size_t val_bytes = (size_t)TILE * 4;
     static constexpr size_t key_stage_bytes = ((size_t)TILE * 4 + KPAD * 4 + 127) / 128 * 128;
     static constexpr size_t total = val_bytes * STAGES + key_stage_bytes * KSTAGES + 128;

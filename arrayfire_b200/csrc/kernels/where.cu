@@ -407,7 +407,8 @@ template<typename T> struct PipeWhereLayout {
     static constexpr int SUBTILE = NVEC * E;                     // elements per sub-tile
     static constexpr int TILE = SUBTILE * kPW_Sub;               // elements per tile
     static constexpr size_t stage_bytes = (size_t)NVEC * 16;     // 32 KB
-    static constexpr size_t strip_bytes = (size_t)kPW_Warps * 32 * E * sizeof(uint);
+    static constexpr int STRIP = 32 * E + 4;                     // + room for the output alignment shift
+    static constexpr size_t strip_bytes = (size_t)kPW_Warps * STRIP * sizeof(uint);
     static constexpr size_t mask_bytes = (size_t)2 * kPW_Sub * NVEC * sizeof(unsigned short);
     static constexpr size_t total = stage_bytes * kPW_Stages + strip_bytes + mask_bytes + 128;
 };
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     }
 
     // =============================================================================== compute warps
-    uint *strip = strips + warp * (32 * E);
+    uint *strip = strips + warp * Lay::STRIP;
     long long m = 0;            // sub-tile counter (matches the DMA warp's)
     long long tile_prev = 0;
     bool ended = false;
@@ -617,15 +618,42 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
                     }
                     const uint total = __shfl_sync(0xffffffffu, inc, 31);
                     if (total == 0u) continue;        // warp-uniform
-                    uint o = inc - c;
+                    // the strip is filled from index (gpos & 3) on, so that its 16-byte quads line up with `out`
+                    const uint shift = gpos & 3u;
+                    uint o = shift + inc - c;
                     const uint first = a.base + (uint)(sub_lo + (dim_t)q * E);
-                    while (mm) {
-                        const int k = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        strip[o++] = first + k;
+                    if (total * 4u >= 32u * E) {
+                        // dense slot: branch-free, one predicated store per element (no per-lane trip counts)
+#pragma unroll
+                        for (int k = 0; k < E; k++) {
+                            if ((mm >> k) & 1u) strip[o] = first + k;
+                            o += (mm >> k) & 1u;
+                        }
+                    } else {
+                        while (mm) {
+                            const int k = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            strip[o++] = first + k;
+                        }
                     }
                     __syncwarp();
-                    for (uint r = lane; r < total; r += 32) a.out[gpos + r] = strip[r];
+                    // flush: whole quads with 16-byte stores, the ragged ends element by element
+                    uint *out_al = a.out + (gpos - shift);
+                    const uint lim = shift + total;
+                    if (total <= 32u) {                // sparse slot: one coalesced scalar store
+                        if (lane < total) a.out[gpos + lane] = strip[shift + lane];
+                    } else
+                    for (uint qd = lane; 4u * qd < lim; qd += 32) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(strip + 4u * qd);
+                        if (4u * qd >= shift && 4u * qd + 4u <= lim) {
+                            *reinterpret_cast<uint4 *>(out_al + 4u * qd) = v;
+                        } else {
+                            if (4u * qd + 0u >= shift && 4u * qd + 0u < lim) out_al[4u * qd + 0u] = v.x;
+                            if (4u * qd + 1u >= shift && 4u * qd + 1u < lim) out_al[4u * qd + 1u] = v.y;
+                            if (4u * qd + 2u >= shift && 4u * qd + 2u < lim) out_al[4u * qd + 2u] = v.z;
+                            if (4u * qd + 3u >= shift && 4u * qd + 3u < lim) out_al[4u * qd + 3u] = v.w;
+                        }
+                    }
                     __syncwarp();
                     gpos += total;
                 }
@@ -640,7 +668,7 @@ template<typename T>
 static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base) {
     const dim_t n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
     constexpr dim_t CT = (dim_t)kChainThreads * kCW_U * VecN<T>::value;
-    if (aligned_to(in.ptr, 16) && n >= 2 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
+    if (aligned_to(in.ptr, 16) && aligned_to(out, 16) && n >= 2 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
         typedef PipeWhereLayout<T> PL;
         auto kern = pipe_where_kernel<T>;
         static bool configured[64] = {false};

@@ -213,6 +213,11 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: libraries that print to fd 1 (NCCL's version banner at
+    # communicator creation) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             log("bench.py: --gpus %d needs torchrun (one rank per GPU); running 1 GPU" % args.gpus)
@@ -229,6 +234,9 @@ def gpu_arm(args):
     af.set_device(local)
     group = None
     if world > 1:
+        # NCCL's own banner / debug lines go to stdout by default; rank 0's stdout must carry the ONE JSON line only
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
         group = dist
     lib_stream = torch.cuda.ExternalStream(af.get_stream(local), device=dev)
@@ -373,7 +381,8 @@ def gpu_arm(args):
             "bytes_per_step": int(total_bytes), "ops": ops, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "where_counts": counts,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
