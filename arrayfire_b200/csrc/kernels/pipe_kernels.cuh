@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
     __shared__ uint64_t p1_bar[RING], lb_bar[RING], p2_bar[RING];
     __shared__ long long sm_tile_id[STAGES];
     __shared__ int sm_valid[STAGES];             // valid elements of the tile; TILE: staged / stored by bulk copies
+    __shared__ int sm_first[STAGES];             // 1: the tile is the first of its column
     __shared__ State sm_wtot[RING][NW];
     __shared__ uint sm_wfh[RING][NW];            // first segment head inside the warp's chunk (WCHUNK: none)
     __shared__ To sm_wp[RING][NW];               // value carried into each warp's chunk
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
             const dim_t left = a.g.len - tile_lo;
             const int valid = left >= TILE ? TILE : (int)left;
             sm_valid[s] = valid;
+            sm_first[s] = tcol == 0 ? 1 : 0;
             if (valid == TILE) {
                 fence_proxy_async();
                 const uint32_t kb = KEYED ? (uint32_t)(TILE * 4 + (tile_lo > 0 ? KPAD * 4 : 0)) : 0u;
@@ -450,18 +452,23 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
     }
 
     // =============================================================================== compute warps
+    // (ring positions are kept incrementally in 32-bit registers: 64-bit `%` and `/` by run-time values cost ~100
+    //  instructions each and used to dominate the per-tile instruction count of these warps)
     const int t = warp * 32 + lane;          // 0 .. NW*32-1
     const int base = t * EPT;                // first element of this thread inside the tile
     uint fh0 = WCHUNK, fh1 = WCHUNK, fh2 = WCHUNK, fh3 = WCHUNK;   // first head of the warp's chunk in tiles i .. i-3
     static_assert(kPipeLag == 3, "the fh register ring below is written for D = 3");
     unsigned long long cw_full = 0, cw_lb = 0, cw_p1 = 0, cw_p2 = 0;
     bool ended = false;
-    long long n_live = 0;                    // valid once `ended`
-    for (long long i = 0;; i++) {
+    uint n_live = 0;                         // valid once `ended`
+    int s1 = 0, ks1 = 0;                     // value / key stage of pass 1's tile
+    uint ph1 = 0;                            // phase parity of full_bar[s1]
+    int s2 = 0;                              // value stage of pass 2's tile
+    for (uint i = 0;; i++) {
         long long k0 = clock64();
         if (!ended) {
-            const int s = (int)(i % STAGES), b = (int)(i % RING);
-            mbar_wait(&full_bar[s], (uint32_t)((i / STAGES) & 1));
+            const int s = s1, b = (int)(i & (RING - 1));
+            mbar_wait(&full_bar[s], ph1);
             cw_full += clock64() - k0;
             k0 = clock64();
             const long long tile = sm_tile_id[s];
@@ -471,13 +478,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
             } else {
                 // ---------------------------------------------------------------- pass 1 of tile i
                 const int valid = sm_valid[s];
-                const dim_t col = tile / a.tiles_per_col, tcol = tile % a.tiles_per_col;
-                const dim_t tile_lo = tcol * TILE;
+                const bool col_start = sm_first[s] != 0;     // first tile of its column
                 To *sv = reinterpret_cast<To *>(val_base + (size_t)s * Lay::val_bytes);
-                Tk *sk = reinterpret_cast<Tk *>(key_base + (size_t)(i % KST) * Lay::key_stage_bytes) + KPAD;
+                Tk *sk = reinterpret_cast<Tk *>(key_base + (size_t)ks1 * Lay::key_stage_bytes) + KPAD;
                 if (valid != TILE) {
                     // ragged tile: plain cooperative copy (elements past the end cannot influence stored outputs,
                     // and are masked to the identity below so that the tile total stays exact)
+                    const dim_t col = tile / a.tiles_per_col, tcol = tile % a.tiles_per_col;
+                    const dim_t tile_lo = tcol * TILE;
                     const Ti *gin = a.in + col_offset(a.g, col) + tile_lo;
                     for (int e = t; e < valid; e += NW * 32) reinterpret_cast<Ti *>(sv)[e] = ldg_stream<Ti>(gin + e);
                     if (KEYED) {
@@ -505,7 +513,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                         for (int k = 0; k < 4; k++) kk[4 * j + k] = reinterpret_cast<const Tk *>(&q)[k];
                     }
                     Tk kprev;
-                    if (base > 0 || tile_lo > 0) kprev = sk[base - 1];
+                    if (base > 0 || !col_start) kprev = sk[base - 1];
                     else kprev = a.carry_key ? *a.carry_key : kk[0];   // position 0 of a column: a head only against the carry key
 #pragma unroll
                     for (int k = 0; k < EPT; k++) {
@@ -548,7 +556,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                     fh0 = pos;
                     if (lane == 0) sm_wfh[b][warp] = pos;
                 }
-                // the warp total is all the look-back warp needs: let it publish while the outputs are formed
+                // the warp total is all the publisher / walker need: let them work while the outputs are formed
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p1_bar[b]);
                 // ---- local results (everything except the value carried into the warp's chunk), in place
@@ -576,15 +584,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                     *reinterpret_cast<Vec16 *>(sv + base + 4 * j) = q;
                 }
                 cw_p1 += clock64() - k0;
+                if (++s1 == STAGES) { s1 = 0; ph1 ^= 1u; }
+                if (++ks1 == KST) ks1 = 0;
             }
         }
-        if (i >= D) {
+        if (i >= (uint)D) {
             // ---------------------------------------------------------------- pass 2 of tile n = i - D
-            const long long n = i - D;
+            const uint n = i - D;
             if (ended && n >= n_live) break;
-            const int sp = (int)(n % STAGES), bp = (int)(n % RING);
+            const int sp = s2, bp = (int)(n & (RING - 1));
             k0 = clock64();
-            mbar_wait(&lb_bar[bp], (uint32_t)((n / RING) & 1));
+            mbar_wait(&lb_bar[bp], (n / RING) & 1u);
             cw_lb += clock64() - k0;
             k0 = clock64();
             const To wp = sm_wp[bp][warp];
@@ -626,6 +636,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
             __syncwarp();
             if (lane == 0) mbar_arrive(&p2_bar[bp]);
             cw_p2 += clock64() - k0;
+            if (++s2 == STAGES) s2 = 0;
         } else if (ended && n_live == 0) {
             break;
         }

@@ -9,7 +9,7 @@ timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smok
 timeout 900 python bench.py > gpurun_out/bench_n1_$TAG.json 2> gpurun_out/bench_n1_$TAG.err; echo "bench rc=$?" >> gpurun_out/bench_n1_$TAG.err
 AFB200_CHAIN_CTAS_PER_SM=1 timeout 600 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_n1_${TAG}_cta1.json 2>/dev/null
 if [ -z "$2" ]; then
-K='regex:span_kernel|dim_kernel|warp_cols_kernel|lookback_kernel|chain_scan_kernel|chain_where_kernel|warp_scan_cols_kernel|strip_scan_kernel|where_kernel|scan_fixup_kernel|copy_strided_kernel|fill_kernel|cast_kernel'
+K='regex:span_kernel|dim_kernel|warp_cols_kernel|lookback_kernel|chain_scan_kernel|chain_where_kernel|pipe_scan_kernel|pipe_where_kernel|warp_scan_cols_kernel|strip_scan_kernel|where_kernel|scan_fixup_kernel|copy_strided_kernel|fill_kernel|cast_kernel'
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/b_ncu_$TAG.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k "$K" -s 39 -c 13 -o gpurun_out/prof_$TAG -f \
