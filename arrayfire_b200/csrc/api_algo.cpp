@@ -333,6 +333,51 @@ Array *scan_by_key_impl(const Array &key, const Array &in, int dim, int binop, b
 }
 
 // ---- where -------------------------------------------------------------------------------------------
+// enqueue the compaction into a worst-case sized output; the u64 hit count lands at *d_count_out (device)
+Array *where_launch(const Array &in, unsigned base, unsigned long long **d_count_out) {
+    const af_dtype t = in.info.type;
+    if (t == f16) AFB_TYPE_ERROR(1, t);
+    const dim_t n = in.elements();
+    if (n >= 0xffffffffLL) fail(AF_ERR_SIZE, "af_where: indices are 32-bit, the input has too many elements");
+    const Array *src = &in;
+    Holder tmp;
+    if (!in.is_linear()) {
+        tmp.a = make_dense_copy(in);
+        src = tmp.a;
+    }
+    Holder big;
+    dim_t cap[4] = {n, 1, 1, 1};
+    big.a = new_array(u32, cap);
+    OpLock lk(in.device());
+    LaunchCtx c = ctx_for_active_device();
+    unsigned long long *d_count = (unsigned long long *)c.scratch->dev_scalar;
+    if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), d_count, base)) AFB_TYPE_ERROR(1, t);
+    *d_count_out = d_count;
+    return big.release();
+}
+
+// trim a worst-case sized where() output to its `h_count` hits (exact-size copy when the result is sparse)
+Array *where_finish(Array *big_raw, dim_t h_count) {
+    Holder big;
+    big.a = big_raw;
+    const dim_t n = big.a->info.dims[0];
+    const char *e = getenv("AFB200_WHERE_SHRINK_DIV");
+    const dim_t div = e ? atoll(e) : 8;
+    if (h_count == 0 || (div > 0 && h_count < n / div)) {
+        dim_t d[4] = {h_count, 1, 1, 1};
+        Holder exact;
+        exact.a = new_array(u32, d);
+        if (h_count) {
+            cudaStream_t s = stream_of(big.a->device());
+            AFB_CUDA(cudaMemcpyAsync(exact.a->data(), big.a->data(), (size_t)h_count * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        return exact.release();
+    }
+    big.a->info.dims[0] = h_count;
+    dense_strides(big.a->info.dims, big.a->info.strides);
+    return big.release();
+}
+
 Array *where_impl(const Array &in, unsigned base, dim_t *count_out) {
     const af_dtype t = in.info.type;
     if (t == f16) AFB_TYPE_ERROR(1, t);
@@ -549,6 +594,29 @@ af_err afx_where_shard(af_array *idx, dim_t *count, const af_array in_h, unsigne
     AFB_ARG(2, in->elements() > 0);
     check_same_device(*in);
     *idx = where_impl(*in, base, count);
+    AFB_API_END
+}
+
+af_err afx_where_shard_launch(af_array *idx, void **count_dev, const af_array in_h, unsigned base) {
+    AFB_API_BEGIN
+    AFB_ARG(0, idx != nullptr);
+    AFB_ARG(1, count_dev != nullptr);
+    Array *in = from_handle(in_h);
+    AFB_ARG(2, in->elements() > 0);
+    check_same_device(*in);
+    unsigned long long *d = nullptr;
+    *idx = where_launch(*in, base, &d);
+    *count_dev = d;
+    AFB_API_END
+}
+
+af_err afx_where_shard_finish(af_array *idx, dim_t count) {
+    AFB_API_BEGIN
+    AFB_ARG(0, idx != nullptr && *idx != nullptr);
+    Array *big = from_handle(*idx);
+    AFB_ARG(1, count >= 0 && count <= big->info.dims[0]);
+    check_same_device(*big);
+    *idx = where_finish(big, count);
     AFB_API_END
 }
 

@@ -167,7 +167,22 @@ class LocalGpu:
         self.stream = torch.cuda.ExternalStream(af.get_stream(), device=self.dev)
 
     def payload(self):
-        return self.torch.zeros(PAYLOAD_BYTES, dtype=self.torch.uint8, device=self.dev)
+        """the per-op 64-byte partial record.  ONE persistent device buffer: every op overwrites the fields it
+        reads back, and ops on the library's stream are ordered, so no per-op allocation / memset is needed."""
+        if getattr(self, "_payload", None) is None:
+            self._payload = self.torch.zeros(PAYLOAD_BYTES, dtype=self.torch.uint8, device=self.dev)
+        return self._payload
+
+    def to_host(self, gathered):
+        """[world, PAYLOAD_BYTES] device tensor -> numpy, through a persistent pinned landing zone (one async copy +
+        one stream synchronisation; `.cpu()` would stage through pageable memory)"""
+        n = gathered.numel()
+        if getattr(self, "_pinned", None) is None or self._pinned.numel() < n:
+            self._pinned = self.torch.empty(max(n, 8 * PAYLOAD_BYTES), dtype=self.torch.uint8, pin_memory=True)
+        dst = self._pinned[:n]
+        dst.copy_(gathered.reshape(-1), non_blocking=True)
+        self.stream.synchronize()
+        return dst.numpy().reshape(gathered.shape[0], -1).copy()
 
     def on_stream(self):
         return self.torch.cuda.stream(self.stream)
@@ -259,6 +274,27 @@ class LocalGpu:
         af._check(af.lib.afx_where_shard(ct.byref(h), ct.byref(n), a.handle, ct.c_uint(base)))
         return af.Array(h), n.value
 
+    def where_launch(self, a, base):
+        """enqueue the shard's compaction; returns (opaque handle, 64-byte uint8 device view whose first 8 bytes
+        will hold the hit count) -- nothing is synchronised"""
+        af, ct = self.af, self.ct
+        h, p = ct.c_void_p(), ct.c_void_p()
+        af._check(af.lib.afx_where_shard_launch(ct.byref(h), ct.byref(p), a.handle, ct.c_uint(base)))
+        if getattr(self, "_slot_ptr", None) != p.value:
+            ptr = p.value
+
+            class _Holder:
+                __cuda_array_interface__ = {"shape": (PAYLOAD_BYTES,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                            "strides": None}
+            self._slot = self.torch.as_tensor(_Holder(), device=self.dev)
+            self._slot_ptr = ptr
+        return h, self._slot
+
+    def where_finish(self, h, count):
+        af, ct = self.af, self.ct
+        af._check(af.lib.afx_where_shard_finish(ct.byref(h), ct.c_longlong(count)))
+        return af.Array(h)
+
     def bytes_view(self, a):
         """uint8 torch view of a linear array's device memory (no copy)"""
         ptr = a.device_ptr()
@@ -291,7 +327,22 @@ class ShardedOps:
         """[world, PAYLOAD_BYTES] uint8 numpy array of every rank's payload (one collective, one D2H)"""
         with self.local.on_stream():
             g = self.group.all_gather_bytes(buf)
+            if hasattr(self.local, "to_host"):
+                return self.local.to_host(g)
             return g.cpu().numpy()
+
+    def _shard_bases(self, base):
+        """global offsets of every rank's shard.  A sharding is fixed for the life of the arrays, so the offsets are
+        exchanged once per distinct `base` and cached (every rank calls with its own base, collectively)."""
+        cache = self.__dict__.setdefault("_bases", {})
+        if base not in cache:
+            import torch
+            t = torch.zeros(PAYLOAD_BYTES, dtype=torch.uint8)
+            t[:8] = torch.frombuffer(bytearray(np.uint64(base).tobytes()), dtype=torch.uint8)
+            dev = getattr(self.local, "dev", None)
+            g = self._gather(t.to(dev) if dev is not None else t)
+            cache[base] = [int(g[r, :8].view(np.uint64)[0]) for r in range(self.world)]
+        return cache[base]
 
     # -- reductions ----------------------------------------------------------------------------------
     def reduce_all(self, op, a):
@@ -307,13 +358,12 @@ class ShardedOps:
         """(value, GLOBAL u32 index) of af_imin_all / af_imax_all; `base` is this shard's global offset"""
         buf = self.local.payload()
         self.local.ireduce_partial(buf, a, _AFX_OP[op])
-        import torch
-        buf[24:32] = torch.frombuffer(bytearray(np.uint64(base).tobytes()), dtype=torch.uint8).to(buf.device)
         g = self._gather(buf)
+        bases = self._shard_bases(int(base))
         code = self.local.dtype(a)
         dt = np.dtype(_NP_OF[code])
         vals = [g[r, :dt.itemsize].view(dt)[0] for r in range(self.world)]
-        gidx = [int(g[r, 16:20].view(np.uint32)[0]) + int(g[r, 24:32].view(np.uint64)[0]) for r in range(self.world)]
+        gidx = [int(g[r, 16:20].view(np.uint32)[0]) + bases[r] for r in range(self.world)]
         v, i = fold_arg(op, vals, gidx, is_b8=(code == _B8))
         return v, i & 0xffffffff
 
@@ -360,9 +410,16 @@ class ShardedOps:
     def where(self, a, base):
         """af_where: returns (this shard's indices [global numbering], offset of the slice in the global
         output, global hit count).  The output stays sharded."""
-        idx, n = self.local.where_shard(a, base)
-        g = self._gather(self.local.host_scalar_payload(np.int64(n).tobytes()))
-        counts = [int(g[r, :8].view(np.int64)[0]) for r in range(self.world)]
+        if hasattr(self.local, "where_launch"):
+            # kernel, all-gather of the device-resident counts and ONE read-back / synchronisation
+            h, slot = self.local.where_launch(a, base)
+            g = self._gather(slot)
+            counts = [int(g[r, :8].view(np.int64)[0]) for r in range(self.world)]
+            idx = self.local.where_finish(h, counts[self.rank])
+        else:
+            idx, n = self.local.where_shard(a, base)
+            g = self._gather(self.local.host_scalar_payload(np.int64(n).tobytes()))
+            counts = [int(g[r, :8].view(np.int64)[0]) for r in range(self.world)]
         off, total = where_offsets(counts)
         return idx, int(off[self.rank]), total
 

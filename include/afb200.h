@@ -215,6 +215,12 @@ AFAPI af_err afx_scan_shard_local(af_array *out, void *summary, const af_array k
 AFAPI af_err afx_scan_shard_fixup(af_array out, const void *carry, dim_t count, af_binary_op op);
 /* af_where over a shard with every index offset by `base` (= rank*N/G); returns the hit count too */
 AFAPI af_err afx_where_shard(af_array *idx, dim_t *count, const af_array in, unsigned base);
+/* The same in two asynchronous halves, so that a multi-GPU caller pays ONE host synchronisation for the kernel
+ * and the exchange of the counts together: _launch enqueues the compaction into a worst-case sized u32 array and
+ * leaves the hit count (u64) in device memory at *count_dev (valid until the next libafb200 call on this device);
+ * _finish trims the array to `count` hits once the caller has read the count back. */
+AFAPI af_err afx_where_shard_launch(af_array *idx, void **count_dev, const af_array in, unsigned base);
+AFAPI af_err afx_where_shard_finish(af_array *idx, dim_t count);
 /* number of CUDA kernels this library launched on the calling thread's device since the last reset */
 AFAPI af_err afx_launch_count(unsigned long long *count, bool reset);
 

@@ -23,11 +23,13 @@ class StackGroup:
 
     def all_gather_bytes(self, payload):
         import torch
+        key = self.key
+        self.key += 1      # an op may gather more than once: every collective of a call gets its own slot
         if not self.replay:
-            self.payloads.setdefault(self.key, {})[self.rank] = payload.clone()
+            self.payloads.setdefault(key, {})[self.rank] = payload.clone()
             # first pass: the other ranks are unknown yet -> answer with copies of our own payload
             return torch.stack([payload] * self.world)
-        rows = self.payloads[self.key]
+        rows = self.payloads[key]
         return torch.stack([rows[r] for r in range(self.world)])
 
 
@@ -51,6 +53,7 @@ def run_sharded(af, sh, world, call):
         for r in range(world):
             grp.rank = ops.rank = r
             grp.key = 0
+            ops.__dict__.pop("_bases", None)   # the simulated ranks share one ShardedOps: no cross-rank caching
             out[r] = call(ops, r)
     return out
 
