@@ -22,6 +22,8 @@
 // Semantics: /root/reference/src/backend/cpu/kernel/scan.hpp:37-72, scan_by_key.hpp:43-86.
 #pragma once
 
+#include <type_traits>
+
 #include "chain_kernels.cuh"
 
 namespace afb {
@@ -238,8 +240,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
     constexpr int NW = kPipeWarps, D = kPipeLag, RING = kPipeRing;
     constexpr int KST = Lay::KSTAGES > 0 ? Lay::KSTAGES : 1;
 
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *val_base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // (a pointer that provably derives from the __shared__ array keeps its address space: the round trip through
+    //  uintptr_t used for manual alignment made every stage access a generic LD.E/ST.E with 64-bit address math)
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    unsigned char *val_base = pipe_smem;
     unsigned char *key_base = val_base + Lay::val_bytes * STAGES;
     __shared__ uint64_t full_bar[STAGES];
     __shared__ uint64_t p1_bar[RING], lb_bar[RING], p2_bar[RING];
@@ -478,10 +482,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
             } else {
                 // ---------------------------------------------------------------- pass 1 of tile i
                 const int valid = sm_valid[s];
+                // the ragged last tile of a column gets its own instantiation: the fast path carries no bounds checks
+                auto pass1 = [&](auto rag_c) {
+                constexpr bool RAG = decltype(rag_c)::value;
                 const bool col_start = sm_first[s] != 0;     // first tile of its column
                 To *sv = reinterpret_cast<To *>(val_base + (size_t)s * Lay::val_bytes);
                 Tk *sk = reinterpret_cast<Tk *>(key_base + (size_t)ks1 * Lay::key_stage_bytes) + KPAD;
-                if (valid != TILE) {
+                if (RAG) {
                     // ragged tile: plain cooperative copy (elements past the end cannot influence stored outputs,
                     // and are masked to the identity below so that the tile total stays exact)
                     const dim_t col = tile / a.tiles_per_col, tcol = tile % a.tiles_per_col;
@@ -520,7 +527,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                         const bool head = kk[k] != (k == 0 ? kprev : kk[k - 1]);
                         hb |= (head ? 1u : 0u) << k;
                     }
-                    if (valid != TILE) {
+                    if (RAG) {
                         const int nv = valid - base;   // heads past the end do not exist
                         hb = nv <= 0 ? 0u : (nv >= 32 ? hb : (hb & ((1u << nv) - 1u)));
                     }
@@ -531,7 +538,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
 #pragma unroll
                 for (int k = 0; k < EPT; k++) {
                     To e = R::pre(v[k]);
-                    if (valid != TILE && base + k >= valid) e = R::init();
+                    if (RAG && base + k >= valid) e = R::init();
                     if (k == 0) run = e;
                     else if (KEYED) run = ((hb >> k) & 1u) ? e : R::join(run, e);
                     else run = R::join(run, e);
@@ -583,6 +590,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                     for (int k = 0; k < 4; k++) reinterpret_cast<To *>(&q)[k] = o[4 * j + k];
                     *reinterpret_cast<Vec16 *>(sv + base + 4 * j) = q;
                 }
+                };
+                if (valid == TILE) pass1(std::false_type{});
+                else pass1(std::true_type{});
                 cw_p1 += clock64() - k0;
                 if (++s1 == STAGES) { s1 = 0; ph1 ^= 1u; }
                 if (++ks1 == KST) ks1 = 0;

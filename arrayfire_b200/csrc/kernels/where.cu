@@ -425,8 +425,8 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     constexpr int NE = SUB * NW;     // (sub-tile, warp) count entries per tile: 64 = two per lane
     static_assert(NE == 64, "publisher / walker handle two entries per lane");
 
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *stage_base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(128) unsigned char pipe_smem[];   // see pipe_scan_kernel: keeps the accesses LDS/STS
+    unsigned char *stage_base = pipe_smem;
     uint *strips = reinterpret_cast<uint *>(stage_base + Lay::stage_bytes * ST);
     unsigned short *masks = reinterpret_cast<unsigned short *>(stage_base + Lay::stage_bytes * ST + Lay::strip_bytes);
     __shared__ uint64_t full_bar[ST], empty_bar[ST];
