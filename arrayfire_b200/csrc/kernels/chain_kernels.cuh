@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_scan_kernel(const Chai
     typedef DescCodec<S, To, KEYED> Codec;
     typedef TileDesc<State> Desc;
 
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *stage_base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(128) unsigned char chain_smem[];   // derived pointers stay in the shared address space
+    unsigned char *stage_base = chain_smem;
     __shared__ uint64_t full_bar[kChainStages];
     __shared__ long long sm_tile_id[kChainStages];
     __shared__ int sm_staged[kChainStages];     // 1: the tile's operands are in shared memory

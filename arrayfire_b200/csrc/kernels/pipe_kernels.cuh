@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
     if (warp == NW + kPipeLB) {
         // =========================================================================== DMA warp (one thread)
         if (lane != 0) return;
-        auto draw = [&]() -> long long { return (long long)(atomicAdd(a.ticket, 1ULL) - a.ticket_base); };
+        // returns the RAW counter value: subtracting ticket_base right here would make the thread wait for the atomic's
+        // round trip (~2500 cycles under load, measured) on every draw instead of two tiles later, when the ticket is used
+        auto draw = [&]() -> unsigned long long { return atomicAdd(a.ticket, 1ULL); };
         long long pub = 0;        // tiles published so far; tile n uses value stage n % STAGES, key stage n % KST
         long long n_live = -1;    // number of real tiles of this CTA, known once the end ticket has been drawn
         auto publish = [&](long long n, long long tile) {
@@ -315,14 +317,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
         // two per tile period, never a whole ring at once: a CTA that drew STAGES consecutive tickets would own
         // STAGES consecutive tiles, and since every tile waits for its predecessor's aggregate the CTAs would start
         // one after the other.
-        long long tk0 = draw(), tk1 = draw();
+        unsigned long long tk0 = draw(), tk1 = draw();
         bool drawing = true;
+        unsigned long long dma_dbg[4] = {0, 0, 0, 0};
+        const long long dma_start = clock64();
         auto publish_next = [&]() {
-            const long long t = tk0;
+            const long long t = (long long)(tk0 - a.ticket_base);
             tk0 = tk1;
             // keys: stage pub % KST is free once pass 1 of tile pub - KST has read it (pass 1 arrives on p1_bar after
             // its key loads; tiles are processed in order, so this wait can never block the tile it waits for)
+            const long long w0 = clock64();
             if (KEYED && pub >= KST) mbar_wait(&p1_bar[(pub - KST) % RING], (uint32_t)(((pub - KST) / RING) & 1));
+            dma_dbg[2] += clock64() - w0;
             publish(pub, t);
             pub++;
             if (t >= a.ntiles) { drawing = false; n_live = pub - 1; }
@@ -334,7 +340,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
             if (j >= D) {
                 const long long n = j - D;            // pass 2 of tile n is the next to finish
                 if (!drawing && n >= n_live) break;
+                long long w1 = clock64();
                 mbar_wait(&p2_bar[n % RING], (uint32_t)((n / RING) & 1));
+                dma_dbg[0] += clock64() - w1;
                 const int sp = (int)(n % STAGES);
                 if (sm_valid[sp] == TILE) {
                     const long long tp = sm_tile_id[sp];
@@ -342,13 +350,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
                     bulk_s2g(a.out + col * a.g.len + tcol * TILE, val_base + (size_t)sp * Lay::val_bytes, (uint32_t)Lay::val_bytes);
                 }
                 bulk_commit();
+                w1 = clock64();
                 bulk_wait_read<1>();                  // stores of tiles <= n-1 have finished reading shared memory
+                dma_dbg[1] += clock64() - w1;
             }
             // tile m may be published once the store of tile m - STAGES has drained: m - STAGES <= j - D - 1
             const long long lim = j + a.ahead;
             for (int burst = 0; drawing && burst < 2 && pub <= lim; burst++) publish_next();
         }
         bulk_wait_all();
+        if (a.debug) {
+            dma_dbg[3] = clock64() - dma_start;
+            for (int q = 0; q < 4; q++) a.debug[blockIdx.x * 16 + 4 + q] = dma_dbg[q];
+        }
         return;
     }
 

@@ -111,8 +111,8 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
                         static unsigned long long h[1024 * 16];
                         AFB_CUDA(cudaStreamSynchronize(c.stream));
                         AFB_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
-                        const char *names[12] = {"lb_total", "lb_resolve", "polls", "tiles", "-", "-",
-                                                 "-", "-", "cmp_wait_full", "cmp_wait_lb", "cmp_p1", "cmp_p2"};
+                        const char *names[12] = {"lb_total", "lb_resolve", "polls", "tiles", "dma_wait_p2", "dma_wait_read",
+                                                 "dma_wait_p1key", "dma_total", "cmp_wait_full", "cmp_wait_lb", "cmp_p1", "cmp_p2"};
                         fprintf(stderr, "[pipe_scan debug] grid=%d ntiles=%lld keyed=%d\n", (int)grid, (long long)a.ntiles, (int)KEYED);
                         for (int q = 0; q < 12; q++) {
                             double sum = 0, mx = 0;

@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_where_kernel(const Cha
     constexpr size_t STAGE = (size_t)TILE * sizeof(T);
     constexpr int STRIP = 32 * E;                        // indices one warp can produce from one slot
 
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *stage_base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(128) unsigned char chain_smem[];   // derived pointers stay in the shared address space
+    unsigned char *stage_base = chain_smem;
     uint *strips = reinterpret_cast<uint *>(stage_base + STAGE * kChainStages);   // [8][STRIP]
     __shared__ uint64_t full_bar[kChainStages];
     __shared__ long long sm_tile_id[kChainStages];
@@ -460,11 +460,12 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     if (warp == NW + 2) {
         // =========================================================================== DMA warp (one thread)
         if (lane != 0) return;
-        auto draw = [&]() -> long long { return (long long)(atomicAdd(a.ticket, 1ULL) - a.ticket_base); };
+        // raw counter values; ticket_base is subtracted at the point of use so that nothing waits on the atomic itself
+        auto draw = [&]() -> unsigned long long { return atomicAdd(a.ticket, 1ULL); };
         long long m = 0;                       // sub-tiles published so far; sub-tile m lives in stage m % ST
-        long long tk0 = draw(), tk1 = draw();  // tickets are drawn two tiles ahead of their use
+        unsigned long long tk0 = draw(), tk1 = draw();  // tickets are drawn two tiles ahead of their use
         while (true) {
-            const long long tile = tk0;
+            const long long tile = (long long)(tk0 - a.ticket_base);
             tk0 = tk1;
             const bool live = tile < a.ntiles;
             if (live) tk1 = draw();

@@ -305,11 +305,12 @@ def gpu_arm(args):
     ab = algorithmic_bytes(w, counts)   # global sizes; counts are global totals in the sharded path
     total_bytes = sum(ab.values())
     value = total_bytes * args.steps / (ms_total * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
     ops = {}
     for n in OP_ORDER:
         ms = per_op_ms[n] / args.steps
-        ops[n] = {"ms": round(ms, 4), "GBps": round(ab[n] / (ms * 1e-3) / 1e9, 1)}
-    peak, peak_src = measured_peak()
+        gbs = ab[n] / (ms * 1e-3) / 1e9
+        ops[n] = {"ms": round(ms, 4), "GBps": round(gbs, 1), "frac_of_peak_per_gpu": round(gbs / world / peak, 4)}
     span_bytes = sum(ab[n] for n in SPAN_OPS)
     span_ms = sum(per_op_ms[n] for n in SPAN_OPS) / args.steps
     achieved = span_bytes / world / (span_ms * 1e-3) / 1e9   # per GPU
@@ -317,12 +318,16 @@ def gpu_arm(args):
                 "frac": round(achieved / peak, 4), "traffic": None,
                 "kernel": "span_kernel (whole-array / long-column streaming reduction): " + ", ".join(SPAN_OPS),
                 "peak_source": peak_src, "frac_of_nominal_8000": round(achieved / 8000.0, 4),
-                "how": "algorithmic bytes of the span ops / CUDA-event time of those API calls (includes the scalar D2H)"}
+                "algorithmic_bytes_per_launch": round(span_bytes / world / len(SPAN_OPS)),
+                "how": "mean over the 5 whole-array span_kernel launches of a step: algorithmic bytes / CUDA-event time of "
+                       "those API calls on the library's stream (includes the scalar D2H); traffic = mean ncu dram read+write "
+                       "bytes of the same 5 launches (profiles/r01_span_kernel_traffic.json)"}
     prof = os.path.join(ROOT, "profiles", "r01_span_kernel_traffic.json")
     if os.path.exists(prof):
         try:
             with open(prof) as f:
-                roofline["traffic"] = json.load(f).get("traffic_bytes_per_launch")
+                t = json.load(f).get("traffic_bytes_per_launch")
+                roofline["traffic"] = None if t is None else round(t / world)   # captured at N = 1; shards scale 1/N
         except Exception:
             pass
 

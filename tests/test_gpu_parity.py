@@ -388,3 +388,47 @@ def test_pipe_back_to_back(af, orc):
         same_bits(a.to_numpy(), d4(w_scan), "b2b scan")
         same_bits(b.to_numpy(), d4(w_sbk), "b2b sbk")
         same_bits(c.to_numpy().reshape(-1), w_where, "b2b where")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json's configurations at FULL size (C1..C5), checked against numpy / the oracle
+# ---------------------------------------------------------------------------------------------------------
+def test_full_size_configs(af, orc):
+    rng = np.random.default_rng(0xAF00)
+    # C1: inclusive scan of 2^26 integer-valued f32 (every prefix exactly representable -> bit-exact in any order)
+    n1 = 1 << 26
+    x1 = rng.integers(-4, 5, n1).astype(np.float32)
+    want = np.cumsum(x1.astype(np.float64))
+    assert np.abs(want).max() < 2 ** 24
+    g1 = af.Array.from_numpy(x1)
+    got = af.accum(g1, 0).to_numpy().reshape(-1)
+    assert np.array_equal(got, want.astype(np.float32))
+    assert af.sum_all(g1) == float(want[-1])
+    del got, want, g1
+    # C4: exclusive add scan_by_key of 2^28 s32, run lengths uniform[1,1024] -> the oracle's serial loop
+    n4 = 1 << 28
+    v4 = rng.integers(-15, 15, n4).astype(np.int32)
+    k4 = np.repeat(np.arange(n4 // 256 + 2, dtype=np.int32), rng.integers(1, 1025, n4 // 256 + 2))[:n4]
+    got = af.scan_by_key(af.Array.from_numpy(k4), af.Array.from_numpy(v4), 0, af.AF_BINARY_ADD, False).to_numpy().reshape(-1)
+    want = orc.scan_by_key(k4, v4, 0, 0, False)[1].reshape(-1)
+    assert got.tobytes() == want.tobytes()
+    del got, want, v4, k4
+    # C3: sum_all / imax_all (first occurrence among exact ties) of 2^30 f32; C5: count / where of a 2^30 u8 mask
+    n3 = 1 << 30
+    u3 = (rng.integers(0, 1 << 24, n3, dtype=np.int32).astype(np.float32) / np.float32(1 << 24))
+    g3 = af.Array.from_numpy(u3)
+    v, i = af.imax_all(g3)
+    assert (v, i) == (float(u3.max()), int(np.argmax(u3)))
+    v, i = af.imin_all(g3)
+    last_min = n3 - 1 - int(np.argmin(u3[::-1]))
+    assert (v, i) == (float(u3.min()), last_min)
+    del g3, u3
+    for p in (0.5, 0.01):
+        m = np.where(rng.random(n3, dtype=np.float32) < p, rng.integers(1, 256, n3, dtype=np.uint8), 0).astype(np.uint8)
+        gm = af.Array.from_numpy(m)
+        want = np.flatnonzero(m).astype(np.uint32)
+        assert af.count_all(gm) == want.size
+        got = af.where(gm)
+        assert got.dims == (want.size, 1, 1, 1)
+        assert got.to_numpy().reshape(-1).tobytes() == want.tobytes()
+        del got, want, gm, m
