@@ -185,10 +185,10 @@ AFB_DI typename S::State walk_fold(const unsigned long long *pd, long long pos, 
 //                  of pass 1 and writes finished tiles back with bulk stores
 // Every synchronous L2 round trip (ticket atomic, descriptor poll) costs ~2000 cycles under full HBM load
 // (measured); the roles are split so that none of them sits on the compute warps' path.
-constexpr int kPipeWarps = 12;                      // compute warps
+constexpr int kPipeWarps = 12;                      // compute warps (default; a template parameter of the kernel)
 constexpr int kPipeWalkers = 2;                     // walker warps; walker k resolves the tiles j = k (mod kPipeWalkers)
 constexpr int kPipeLB = 1 + kPipeWalkers;           // publisher warp + walker warps
-constexpr int kPipeThreads = 32 * (kPipeWarps + kPipeLB + 1); // + publisher + walkers + DMA warp
+constexpr int pipe_threads(int nw) { return 32 * (nw + kPipeLB + 1); }   // + publisher + walkers + DMA warp
 constexpr int kPipeLag = 3;                         // D: pass 2 runs D tiles behind pass 1
 constexpr int kPipeRing = 8;                        // per-tile barrier / scratch ring (> D + 1)
 
@@ -214,8 +214,8 @@ struct PipeScanArgs {
     int window;                  // 32-descriptor chunks per walker poll (1..kPipeWindow)
 };
 
-template<bool KEYED, int EPT, int STAGES> struct PipeLayout {
-    static constexpr int TILE = kPipeWarps * 32 * EPT;
+template<bool KEYED, int EPT, int STAGES, int NWARPS = kPipeWarps> struct PipeLayout {
+    static constexpr int TILE = NWARPS * 32 * EPT;
     static constexpr int KPAD = 4;                                  // key elements kept in front of the tile
     static constexpr int KSTAGES = KEYED ? STAGES - kPipeLag : 0;       // keys are dead after pass 1
     static constexpr size_t val_bytes = (size_t)TILE * 4;
@@ -224,20 +224,20 @@ template<bool KEYED, int EPT, int STAGES> struct PipeLayout {
     static_assert(val_bytes % 128 == 0, "value stages must stay 128-byte aligned");
 };
 
-template<int OP, typename Ti, typename To, bool KEYED, typename Tk, int EPT, int STAGES>
-__global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeScanArgs<Ti, To, Tk> a) {
+template<int OP, typename Ti, typename To, bool KEYED, typename Tk, int EPT, int STAGES, int NWARPS>
+__global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(const PipeScanArgs<Ti, To, Tk> a) {
     static_assert(sizeof(Ti) == 4 && sizeof(To) == 4 && sizeof(Tk) == 4, "pipe scan: 4-byte values and keys");
     static_assert(EPT % 4 == 0 && ((EPT / 4) & 1) == 1 && EPT <= 32, "EPT*4 bytes must be an odd number of 16-byte vectors");
     typedef Rule<OP, Ti, To> R;
     typedef SOps<R, To, KEYED> S;
     typedef typename S::State State;
     typedef DescCodec<S, To, KEYED> Codec;
-    typedef PipeLayout<KEYED, EPT, STAGES> Lay;
+    typedef PipeLayout<KEYED, EPT, STAGES, NWARPS> Lay;
     constexpr int TILE = Lay::TILE;
     constexpr int NV = EPT / 4;
     constexpr int WCHUNK = 32 * EPT;
     constexpr int KPAD = Lay::KPAD;
-    constexpr int NW = kPipeWarps, D = kPipeLag, RING = kPipeRing;
+    constexpr int NW = NWARPS, D = kPipeLag, RING = kPipeRing;
     constexpr int KST = Lay::KSTAGES > 0 ? Lay::KSTAGES : 1;
 
     // (a pointer that provably derives from the __shared__ array keeps its address space: the round trip through
@@ -250,9 +250,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) pipe_scan_kernel(const PipeSc
     __shared__ long long sm_tile_id[STAGES];
     __shared__ int sm_valid[STAGES];             // valid elements of the tile; TILE: staged / stored by bulk copies
     __shared__ int sm_first[STAGES];             // 1: the tile is the first of its column
-    __shared__ State sm_wtot[RING][NW];
-    __shared__ uint sm_wfh[RING][NW];            // first segment head inside the warp's chunk (WCHUNK: none)
-    __shared__ To sm_wp[RING][NW];               // value carried into each warp's chunk
+    __shared__ State sm_wtot[RING][NWARPS];
+    __shared__ uint sm_wfh[RING][NWARPS];            // first segment head inside the warp's chunk (WCHUNK: none)
+    __shared__ To sm_wp[RING][NWARPS];               // value carried into each warp's chunk
     __shared__ State sm_R[RING];                 // running fold handed from walker to walker
     __shared__ uint64_t r_bar[RING];
 

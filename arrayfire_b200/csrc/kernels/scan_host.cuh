@@ -57,11 +57,15 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
             }
             // ---- 4-byte values (and keys): software-pipelined TMA-in / TMA-out kernel, one CTA per SM
             if constexpr (sizeof(Ti) == 4 && sizeof(To) == 4 && sizeof(Tk) == 4) {
+                // measured on B200 (profiles/r01*): plain scans like few, fat warps (12 x 20 elements, 7 stages: 4.8 TB/s vs
+                // 4.1 TB/s with 16 x 12); by-key scans are latency-bound in pass 1 and like more warps (16 x 12 elements,
+                // 6 value + 3 key stages: 4.7 TB/s vs 4.1 TB/s with 12 warps)
                 constexpr int EPT = KEYED ? 12 : 20;
-                constexpr int ST = 7;
-                typedef PipeLayout<KEYED, EPT, ST> PL;
+                constexpr int NWP = KEYED ? 16 : 12;
+                constexpr int ST = KEYED ? 6 : 7;
+                typedef PipeLayout<KEYED, EPT, ST, NWP> PL;
                 if (ok && g.len >= 4 * (dim_t)PL::TILE && !env_int("AFB200_NO_PIPE", 0)) {
-                    auto kern = pipe_scan_kernel<OP, Ti, To, KEYED, Tk, EPT, ST>;
+                    auto kern = pipe_scan_kernel<OP, Ti, To, KEYED, Tk, EPT, ST, NWP>;
                     static bool configured[64] = {false};
                     const int dv = c.device & 63;
                     if (!configured[dv]) {
@@ -104,7 +108,7 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
                     if (dbg && !dbg_buf) AFB_CUDA(cudaMalloc(&dbg_buf, 1024 * 16 * 8));
                     a.debug = dbg ? dbg_buf : nullptr;
                     if (dbg) AFB_CUDA(cudaMemsetAsync(dbg_buf, 0, 1024 * 16 * 8, c.stream));
-                    kern<<<(unsigned)grid, kPipeThreads, PL::total, c.stream>>>(a);
+                    kern<<<(unsigned)grid, pipe_threads(NWP), PL::total, c.stream>>>(a);
                     note_launches(1);
                     post_launch_check("pipe_scan_kernel");
                     if (dbg) {

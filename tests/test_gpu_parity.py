@@ -292,7 +292,7 @@ def test_argument_errors(af):
 # ---------------------------------------------------------------------------------------------------------
 # the software-pipelined TMA kernels (pipe_scan_kernel / pipe_where_kernel): 4-byte values, long aligned columns
 # ---------------------------------------------------------------------------------------------------------
-PIPE_TILE, PIPE_TILE_KEYED = 12 * 32 * 20, 12 * 32 * 12
+PIPE_TILE, PIPE_TILE_KEYED = 12 * 32 * 20, 16 * 32 * 12
 
 
 def _keys(rng, n, kind, dtype):
