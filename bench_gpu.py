@@ -287,6 +287,14 @@ def gpu_arm(args):
     end.record(lib_stream)
     barrier()
     launches = af.launch_count()
+    if rank == 0 and world == 1 and len(sampler.rows) < 8:
+        # the timed region (~150 ms) can be too short for the sampling thread: keep the same load running, untimed,
+        # until the clock / throttle-reason record has a few samples taken UNDER LOAD
+        t_end = time.time() + 0.5
+        while time.time() < t_end and len(sampler.rows) < 16:
+            step()
+            time.sleep(0)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = start.elapsed_time(end)
     per_op_ms = {}
