@@ -8,6 +8,8 @@
 // with no usable device every entry point fails with AF_ERR_DRIVER.
 #include <cstdlib>
 
+#include <atomic>
+
 #include "common.hpp"
 
 using namespace afb;
@@ -617,6 +619,35 @@ af_err afx_where_shard_finish(af_array *idx, dim_t count) {
     AFB_ARG(1, count >= 0 && count <= big->info.dims[0]);
     check_same_device(*big);
     *idx = where_finish(big, count);
+    AFB_API_END
+}
+
+af_err afx_peer_exchange(void *out, const void *payload, const unsigned long long *peer_bufs, int rank, int world,
+                         unsigned epoch) {
+    AFB_API_BEGIN
+    AFB_ARG(0, out != nullptr);
+    AFB_ARG(1, payload != nullptr);
+    AFB_ARG(2, peer_bufs != nullptr);
+    AFB_ARG(4, world >= 1 && world <= 8 && rank >= 0 && rank < world);
+    AFB_ARG(5, epoch != 0);
+    const int dev = active_device();
+    OpLock lk(dev);
+    LaunchCtx c = ctx_for_active_device();
+    // pinned landing zone: [0, 512) gathered records, [2048, 2052) arrival flag
+    unsigned char *hp = (unsigned char *)c.scratch->host_pinned;
+    volatile unsigned *flag = (volatile unsigned *)(hp + 2048);
+    launch_peer_exchange(c, payload, peer_bufs, rank, world, epoch, hp, (unsigned *)(hp + 2048));
+    // spin on the host flag instead of a stream synchronisation: the kernel raises it after its last store
+    unsigned long long spins = 0;
+    while (*flag != epoch) {
+        if ((++spins & 0xfffff) == 0) {
+            cudaError_t e = cudaStreamQuery(c.stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) AFB_CUDA(e);
+            if (e == cudaSuccess && *flag != epoch) fail(AF_ERR_INTERNAL, "afx_peer_exchange: the exchange kernel ended without raising its flag");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(out, hp, (size_t)world * 64);
     AFB_API_END
 }
 

@@ -182,6 +182,10 @@ bool launch_scan_fixup(const LaunchCtx &c, Op op, af_dtype t, void *out, dim_t c
 // writes hit indices (+base) to `out` (capacity = elements) and the count to *d_count (device, 8 bytes)
 bool launch_where(const LaunchCtx &c, af_dtype t, const View &in, unsigned *out, unsigned long long *d_count,
                   unsigned base);
+// all-gather of one 64-byte record per rank over peer-mapped symmetric buffers; the world x 64 bytes land in pinned
+// host memory at host_out and *host_flag becomes `epoch` (kernels/peer.cu)
+void launch_peer_exchange(const LaunchCtx &c, const void *payload, const unsigned long long *bufs, int rank, int world,
+                          unsigned epoch, void *host_out, unsigned *host_flag);
 // dense copy of a strided view (same dtype), value fill, dtype cast (dense -> dense)
 void launch_copy_strided(const LaunchCtx &c, af_dtype t, const View &in, void *out);
 void launch_fill(const LaunchCtx &c, af_dtype t, void *out, dim_t n, double re, double im);

@@ -166,6 +166,40 @@ class LocalGpu:
         self.dev = torch.device("cuda", af.get_device())
         self.stream = torch.cuda.ExternalStream(af.get_stream(), device=self.dev)
 
+    def enable_peer_exchange(self, dist):
+        """set up the NVLink peer path of the O(1) combine (kernels/peer.cu): a symmetric, peer-mapped 2 KB buffer per
+        rank (torch.distributed._symmetric_memory).  Returns False -- and the NCCL all-gather stays in use -- when the
+        platform cannot map peer memory."""
+        self._peer = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            world, rank = dist.get_world_size(), dist.get_rank()
+            if world < 2 or world > 8:
+                return False
+            t = symm.empty(2048, dtype=self.torch.uint8, device=self.dev)
+            t.zero_()
+            hdl = symm.rendezvous(t, dist.group.WORLD)
+            self.torch.cuda.synchronize()
+            dist.barrier()
+            ptrs = (self.ct.c_ulonglong * 8)(*([int(p) for p in hdl.buffer_ptrs] + [0] * (8 - world)))
+            self._peer = {"tensor": t, "handle": hdl, "ptrs": ptrs, "rank": rank, "world": world, "epoch": 0,
+                          "out": (self.ct.c_ubyte * (8 * PAYLOAD_BYTES))()}
+            return True
+        except Exception as ex:  # noqa: BLE001 -- any failure here only means "keep using NCCL"
+            import sys
+            print("[afb200] peer exchange unavailable, using NCCL all-gather: %r" % (ex,), file=sys.stderr)
+            self._peer = None
+            return False
+
+    def peer_gather(self, buf):
+        """[world, PAYLOAD_BYTES] numpy array of every rank's 64-byte record, exchanged by ONE kernel over peer memory"""
+        p = self._peer
+        p["epoch"] += 1
+        af, ct = self.af, self.ct
+        af._check(af.lib.afx_peer_exchange(p["out"], ct.c_void_p(buf.data_ptr()), p["ptrs"], ct.c_int(p["rank"]),
+                                           ct.c_int(p["world"]), ct.c_uint(p["epoch"])))
+        return np.frombuffer(p["out"], dtype=np.uint8, count=p["world"] * PAYLOAD_BYTES).reshape(p["world"], PAYLOAD_BYTES).copy()
+
     def payload(self):
         """the per-op 64-byte partial record.  ONE persistent device buffer: every op overwrites the fields it
         reads back, and ops on the library's stream are ordered, so no per-op allocation / memset is needed."""
@@ -213,9 +247,13 @@ class LocalGpu:
         h = ct.c_void_p()
         carry_ptr = None
         if carry_bytes is not None:
-            c = self.torch.frombuffer(bytearray(carry_bytes), dtype=self.torch.uint8).to(self.dev, non_blocking=False)
-            self._keep = c
-            carry_ptr = ct.c_void_p(c.data_ptr())
+            # zero-copy: the kernel's walkers read the carry once, straight from pinned host memory.  The slot may be
+            # rewritten by the next sharded scan only after that scan's own gather, which waits (stream order) for this
+            # kernel -- so a single slot suffices.
+            if getattr(self, "_carry_pinned", None) is None:
+                self._carry_pinned = self.torch.zeros(64, dtype=self.torch.uint8, pin_memory=True)
+            self._carry_pinned[:len(carry_bytes)] = self.torch.frombuffer(bytearray(carry_bytes), dtype=self.torch.uint8)
+            carry_ptr = ct.c_void_p(self._carry_pinned.data_ptr())
         af._check(af.lib.afx_scan_shard(ct.byref(h), None, a.handle, ct.c_int(binop), ct.c_bool(inclusive), carry_ptr, None))
         return af.Array(h)
 
@@ -321,10 +359,22 @@ class ShardedOps:
         self.local = local if local is not None else LocalGpu()
         self.group = Group(dist)
         self.rank, self.world = self.group.rank, self.group.world
+        import os
+        if (dist is not None and self.world > 1 and hasattr(self.local, "enable_peer_exchange")
+                and os.environ.get("AFB200_NO_PEER", "0") != "1"):
+            ok = self.local.enable_peer_exchange(dist)
+            # every rank must take the same path: fall back together
+            import torch
+            flag = torch.tensor([1 if ok else 0], device=self.local.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.local._peer = None
 
     # -- helpers -----------------------------------------------------------------------------------
     def _gather(self, buf):
         """[world, PAYLOAD_BYTES] uint8 numpy array of every rank's payload (one collective, one D2H)"""
+        if getattr(self.local, "_peer", None) is not None:
+            return self.local.peer_gather(buf)
         with self.local.on_stream():
             g = self.group.all_gather_bytes(buf)
             if hasattr(self.local, "to_host"):
@@ -374,7 +424,7 @@ class ShardedOps:
         buf = self.local.payload()
         red = _BINOP_TO_RED[binop]
         code = self.local.reduce_partial(buf, a, _AFX_OP[red])
-        if hasattr(self.local, "scan_with_device_carry"):
+        if hasattr(self.local, "scan_with_device_carry") and getattr(self.local, "_peer", None) is None:
             with self.local.on_stream():
                 gd = self.group.all_gather_bytes(buf)
                 out = self.local.scan_with_device_carry(a, binop, inclusive, gd, code, scan_out_type(self.local.dtype(a)), self.rank)

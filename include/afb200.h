@@ -221,6 +221,13 @@ AFAPI af_err afx_where_shard(af_array *idx, dim_t *count, const af_array in, uns
  * _finish trims the array to `count` hits once the caller has read the count back. */
 AFAPI af_err afx_where_shard_launch(af_array *idx, void **count_dev, const af_array in, unsigned base);
 AFAPI af_err afx_where_shard_finish(af_array *idx, dim_t count);
+/* All-gather of one 64-byte record per rank WITHOUT a collective library: `peer_bufs[r]` is rank r's symmetric buffer
+ * (>= 1088 bytes, zero-initialised, peer-mapped into this process -- e.g. torch.distributed._symmetric_memory), `payload`
+ * this rank's record in device memory.  One CTA stores the record into every peer's buffer, flags it, waits for all
+ * peers' flags and copies the world x 64 gathered bytes to `out` (host); the call returns when they have arrived.
+ * `epoch` must be 1, 2, 3, ... on successive calls, identically on every rank (world <= 8). */
+AFAPI af_err afx_peer_exchange(void *out, const void *payload, const unsigned long long *peer_bufs, int rank, int world,
+                               unsigned epoch);
 /* number of CUDA kernels this library launched on the calling thread's device since the last reset */
 AFAPI af_err afx_launch_count(unsigned long long *count, bool reset);
 
