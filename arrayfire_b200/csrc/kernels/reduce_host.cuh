@@ -208,10 +208,18 @@ void run_dim(const LaunchCtx &c, const View &in, int dim, const typename P::Para
     bool vec_ok = V > 1 && (g.d0 % V == 0) && (reinterpret_cast<uintptr_t>(in.ptr) % (sizeof(In) * V) == 0) &&
                   (g.sd % V == 0) && (g.na == 1 || g.sa % V == 0) && (g.nb == 1 || g.sb % V == 0);
     if (env_int("AFB200_DIM_NOVEC", 0)) vec_ok = false;
-    const int vec = vec_ok ? V : 1;
-    const dim_t gx = (g.d0 + 32 * vec - 1) / (32 * vec);
     dim_t gz = g.na * g.nb;
     if (gz > 65535) gz = 65535;
+    // narrow matrices (few rows along dim 0, e.g. the row blocks of a matrix partitioned over 8 GPUs): 16-byte vectors
+    // would leave most SMs without a CTA even with 8 cluster splits -> trade vector width for CTAs
+    int vec = vec_ok ? V : 1;
+    constexpr int VH = (V >= 4 && sizeof(In) * (V / 2) >= 4) ? V / 2 : 1;
+    // (tools/dim_sweep.py on B200, 8192 columns: 8192 rows 4349 GB/s with 16-byte vs 3526 with 8-byte vectors;
+    //  4096 rows 2473 vs 2901; 1024 rows 641 vs 1024; scalar lanes never win)
+    const dim_t want_ctas = (dim_t)c.sms * 3;
+    if (vec_ok && VH > 1 && ((g.d0 + 32 * V - 1) / (32 * V)) * gz * 8 < want_ctas) vec = VH;
+    { const int f = env_int("AFB200_DIM_VEC", 0); if (f == 1 || (f == VH && vec_ok) || (f == V && vec_ok)) vec = f; }
+    const dim_t gx = (g.d0 + 32 * vec - 1) / (32 * vec);
     // split the reduced axis across a cluster when the grid would not fill the machine
     int splits = 1;
     const dim_t want = (dim_t)c.sms * 4;
@@ -220,9 +228,12 @@ void run_dim(const LaunchCtx &c, const View &in, int dim, const typename P::Para
     a.splits = splits;
     dim3 grid((unsigned)gx, (unsigned)splits, (unsigned)gz), block(32, kDimRows, 1);
     if (gx > 0x7fffffffLL) fail(AF_ERR_SIZE, "reduce: dim 0 too large");
-    if (vec_ok) {
+    if (vec == V && V > 1) {
         if (splits > 1) launch_with_cluster(dim_kernel<P, V>, grid, block, dim3(1, splits, 1), c.stream, a);
         else dim_kernel<P, V><<<grid, block, 0, c.stream>>>(a);
+    } else if (vec == VH && VH > 1) {
+        if (splits > 1) launch_with_cluster(dim_kernel<P, VH>, grid, block, dim3(1, splits, 1), c.stream, a);
+        else dim_kernel<P, VH><<<grid, block, 0, c.stream>>>(a);
     } else {
         if (splits > 1) launch_with_cluster(dim_kernel<P, 1>, grid, block, dim3(1, splits, 1), c.stream, a);
         else dim_kernel<P, 1><<<grid, block, 0, c.stream>>>(a);
