@@ -189,7 +189,7 @@ constexpr int kPipeWarps = 12;                      // compute warps (default; a
 constexpr int kPipeWalkers = 2;                     // walker warps; walker k resolves the tiles j = k (mod kPipeWalkers)
 constexpr int kPipeLB = 1 + kPipeWalkers;           // publisher warp + walker warps
 constexpr int pipe_threads(int nw) { return 32 * (nw + kPipeLB + 1); }   // + publisher + walkers + DMA warp
-constexpr int kPipeLag = 3;                         // D: pass 2 runs D tiles behind pass 1
+constexpr int kPipeLag = 3;                         // default D: pass 2 runs D tiles behind pass 1 (template parameter)
 constexpr int kPipeRing = 8;                        // per-tile barrier / scratch ring (> D + 1)
 
 template<typename Ti, typename To, typename Tk>
@@ -214,17 +214,17 @@ struct PipeScanArgs {
     int window;                  // 32-descriptor chunks per walker poll (1..kPipeWindow)
 };
 
-template<bool KEYED, int EPT, int STAGES, int NWARPS = kPipeWarps> struct PipeLayout {
+template<bool KEYED, int EPT, int STAGES, int NWARPS = kPipeWarps, int DLAG = kPipeLag> struct PipeLayout {
     static constexpr int TILE = NWARPS * 32 * EPT;
     static constexpr int KPAD = 4;                                  // key elements kept in front of the tile
-    static constexpr int KSTAGES = KEYED ? STAGES - kPipeLag : 0;       // keys are dead after pass 1
+    static constexpr int KSTAGES = KEYED ? STAGES - DLAG : 0;           // keys are dead after pass 1
     static constexpr size_t val_bytes = (size_t)TILE * 4;
     static constexpr size_t key_stage_bytes = ((size_t)TILE * 4 + KPAD * 4 + 127) / 128 * 128;
     static constexpr size_t total = val_bytes * STAGES + key_stage_bytes * KSTAGES + 128;
     static_assert(val_bytes % 128 == 0, "value stages must stay 128-byte aligned");
 };
 
-template<int OP, typename Ti, typename To, bool KEYED, typename Tk, int EPT, int STAGES, int NWARPS>
+template<int OP, typename Ti, typename To, bool KEYED, typename Tk, int EPT, int STAGES, int NWARPS, int DLAG>
 __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(const PipeScanArgs<Ti, To, Tk> a) {
     static_assert(sizeof(Ti) == 4 && sizeof(To) == 4 && sizeof(Tk) == 4, "pipe scan: 4-byte values and keys");
     static_assert(EPT % 4 == 0 && ((EPT / 4) & 1) == 1 && EPT <= 32, "EPT*4 bytes must be an odd number of 16-byte vectors");
@@ -232,12 +232,13 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
     typedef SOps<R, To, KEYED> S;
     typedef typename S::State State;
     typedef DescCodec<S, To, KEYED> Codec;
-    typedef PipeLayout<KEYED, EPT, STAGES, NWARPS> Lay;
+    typedef PipeLayout<KEYED, EPT, STAGES, NWARPS, DLAG> Lay;
     constexpr int TILE = Lay::TILE;
     constexpr int NV = EPT / 4;
     constexpr int WCHUNK = 32 * EPT;
     constexpr int KPAD = Lay::KPAD;
-    constexpr int NW = NWARPS, D = kPipeLag, RING = kPipeRing;
+    constexpr int NW = NWARPS, D = DLAG, RING = kPipeRing;
+    static_assert(D >= 1 && D + 2 <= kPipeRing && D < STAGES - 1, "lag out of range");
     constexpr int KST = Lay::KSTAGES > 0 ? Lay::KSTAGES : 1;
 
     // (a pointer that provably derives from the __shared__ array keeps its address space: the round trip through
@@ -474,8 +475,9 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
     //  instructions each and used to dominate the per-tile instruction count of these warps)
     const int t = warp * 32 + lane;          // 0 .. NW*32-1
     const int base = t * EPT;                // first element of this thread inside the tile
-    uint fh0 = WCHUNK, fh1 = WCHUNK, fh2 = WCHUNK, fh3 = WCHUNK;   // first head of the warp's chunk in tiles i .. i-3
-    static_assert(kPipeLag == 3, "the fh register ring below is written for D = 3");
+    uint fh[D + 1];                          // first head of the warp's chunk in tiles i .. i-D (registers: constant indices)
+#pragma unroll
+    for (int q = 0; q <= D; q++) fh[q] = WCHUNK;
     unsigned long long cw_full = 0, cw_lb = 0, cw_p1 = 0, cw_p2 = 0;
     bool ended = false;
     uint n_live = 0;                         // valid once `ended`
@@ -574,7 +576,7 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                 if (KEYED) {
                     uint pos = hb ? (uint)(lane * EPT + (__ffs(hb) - 1)) : (uint)WCHUNK;
                     pos = __reduce_min_sync(0xffffffffu, pos);
-                    fh0 = pos;
+                    fh[0] = pos;
                     if (lane == 0) sm_wfh[b][warp] = pos;
                 }
                 // the warp total is all the publisher / walker need: let them work while the outputs are formed
@@ -627,7 +629,7 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
             // elements of this thread that are still "open" towards the warp's left edge
             int nadd = EPT;
             if (KEYED) {
-                const int d = (int)fh3 - lane * EPT;
+                const int d = (int)fh[D] - lane * EPT;
                 nadd = d < 0 ? 0 : (d > EPT ? EPT : d);
             }
             if (valid == TILE) {
@@ -664,9 +666,8 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
         } else if (ended && n_live == 0) {
             break;
         }
-        fh3 = fh2;
-        fh2 = fh1;
-        fh1 = fh0;
+#pragma unroll
+        for (int q = D; q >= 1; q--) fh[q] = fh[q - 1];
     }
     if (a.debug && t == 0) {
         a.debug[blockIdx.x * 16 + 8] = cw_full;
