@@ -52,10 +52,18 @@ AFB_DI bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x100000u) : "memory");
     return ok != 0;
 }
+AFB_DI unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 AFB_DI void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    // a phase that does not complete within 20 s of wall time is a protocol bug (a bulk copy that never lands, a
+    // role that died): fail loudly instead of hanging the device.  (Every failed try parks the warp for up to ~1 ms.)
+    const unsigned long long t0 = global_ns();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();  // a bulk copy that never lands is a bug: fail loudly, do not hang
+        if (global_ns() - t0 > 20000000000ULL) __trap();
     }
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completes on `bar`
