@@ -192,17 +192,23 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_scan_kernel(const Chai
             mbar_arrive(&full_bar[s]);  // ragged last tile of a column: consumers load it straight from global
         }
     };
-    auto draw = [&]() -> long long { return (long long)(atomicAdd(a.ticket, 1ULL) - a.ticket_base); };
+    // raw counter values: ticket_base is subtracted where the ticket is used, so nothing waits on the atomic's round trip
+    auto draw = [&]() -> unsigned long long { return atomicAdd(a.ticket, 1ULL); };
+    // Tickets are drawn one tile period apart (two per iteration while the ring fills), never a whole ring at once: a CTA
+    // owning kChainStages consecutive tiles makes the CTAs start one after the other (see pipe_kernels.cuh).
+    unsigned long long raw_next = 0;
+    long long pub = 0;    // tiles published by this CTA; tile n lives in stage n % kChainStages
+    auto publish_next = [&]() {
+        const long long t = (long long)(raw_next - a.ticket_base);
+        publish((int)(pub % kChainStages), t);
+        pub++;
+        if (t >= a.ntiles) drawing = false;
+        else raw_next = draw();
+    };
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kChainStages; s++) {
-            if (drawing) {
-                const long long t = draw();
-                publish(s, t);
-                if (t >= a.ntiles) drawing = false;
-            }
-        }
-        if (drawing) next_ticket = draw();
+        raw_next = draw();
+        publish_next();
+        if (drawing) publish_next();
     }
 
     // ================================================================== tile loop
@@ -315,10 +321,9 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_scan_kernel(const Chai
         }
         __syncthreads();
         // every warp has its operands in registers: refill this stage with the tile drawn one iteration ago
-        if (tid == 0 && drawing) {
-            publish(s, next_ticket);
-            if (next_ticket >= a.ntiles) drawing = false;
-            else next_ticket = draw();
+        if (tid == 0) {
+            // the stages of the tiles <= it are free: tile `pub` may go out while pub - kChainStages <= it
+            for (int burst = 0; drawing && burst < 2 && pub <= (long long)it + kChainStages; burst++) publish_next();
         }
         State warp_excl = S::identity(), tile_total = S::identity();
 #pragma unroll
