@@ -40,78 +40,54 @@ template<int N> AFB_DI void bulk_wait_read() { asm volatile("cp.async.bulk.wait_
 AFB_DI void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 AFB_DI void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-constexpr int kPipeWindow = 8;   // 32-descriptor chunks per look-back window (window = 256 tiles)
+constexpr int kPipeWindow = 8;   // 32-descriptor chunks per walker poll (window = 256 tiles)
 
 // ------------------------------------------------------------------------------------------------
-// look-back over packed 64-bit descriptors, executed by one full warp.
-// Returns (in every lane) the fold of all tiles in [first, tile) -- or, for segmented states, of the tiles
-// after the nearest segment head.  `first` is the first tile of the column: it always publishes TILE_PREFIX.
-//
-// Chunk q of a window holds the 32 tiles at distance 32q+1 .. 32q+32 behind `look`, lane l the one at distance
-// 32q+l+1: every warp-wide load is ONE coalesced 256-byte request.  (The first version gave each lane 8
-// consecutive descriptors: 256 sector requests per poll and CTA, all 148 CTAs on the same ~25 L2 lines --
-// measured 2800 cycles per poll, 11 polls per tile.)
+// tile descriptors of the pipelined kernels: W = sizeof(value) / 4 packed 64-bit words per tile, each word
+//   [63:32] 32 bits of the value   [31:3] generation   [2] segment-head flag   [1:0] status
+// Every word carries the generation tag, so a reader that sees the tag of THIS launch in all W words has a
+// consistent value (a descriptor is written exactly once per launch): relaxed accesses, no fences.
 // ------------------------------------------------------------------------------------------------
-template<typename S, typename Codec, bool KEYED>
-AFB_DI typename S::State lookback_resolve(const unsigned long long *pd, long long tile, long long first, uint tag, int lane,
-                                          unsigned long long *npolls = nullptr) {
+template<typename S, typename To, bool KEYED> struct PipeCodec {
     typedef typename S::State State;
-    State excl = S::identity();
-    long long look = tile - 1;   // newest tile not folded yet
-    while (true) {
-        unsigned long long d[kPipeWindow];
-        int qstop = kPipeWindow, P = 32;   // chunk / lane of the descriptor that ends the look-back (if any)
-        uint spins = 0;
-        while (true) {
+    static constexpr int W = (int)sizeof(To) / 4;
+    static_assert(sizeof(To) % 4 == 0 && W >= 1 && W <= 2, "packed descriptors hold 4- or 8-byte values");
+    AFB_DI static void pack(State s, uint32_t tag, uint32_t status, unsigned long long (&w)[W]) {
+        uint32_t flag = 0;
+        if constexpr (KEYED) flag = s.flag ? 4u : 0u;
+        union { To t; uint32_t u[W]; } x;
+        x.t = S::value(s);
 #pragma unroll
-            for (int q = 0; q < kPipeWindow; q++) {
-                const long long t = look - 32 * q - lane;
-                d[q] = 0ULL;
-                if (t >= first) d[q] = ld_relaxed64(pd + t);
-            }
-            bool resolved = true;
-            qstop = kPipeWindow;
-            P = 32;
-#pragma unroll
-            for (int q = 0; q < kPipeWindow; q++) {
-                const uint lo = (uint)d[q];
-                const bool ok = ((lo & ~7u) == tag) && ((lo & 3u) != TILE_INVALID);
-                bool ends = ok && ((lo & 3u) == TILE_PREFIX);
-                if (KEYED) ends = ends || (ok && (lo & 4u));
-                const uint smask = __ballot_sync(0xffffffffu, ends);
-                const uint bmask = __ballot_sync(0xffffffffu, !ok);
-                if (resolved && qstop == kPipeWindow) {      // still walking back (warp-uniform)
-                    const int p = smask ? (__ffs(smask) - 1) : 32;
-                    const uint newer = (p >= 32) ? 0xffffffffu : ((1u << p) - 1u);
-                    if (bmask & newer) resolved = false;      // a descriptor in front of the stop is not published yet
-                    else if (p < 32) { qstop = q; P = p; }
-                }
-            }
-            if (npolls) (*npolls)++;
-            if (resolved) break;
-            if (++spins > kSpinLimit) __trap();
-        }
-        // ordered fold, oldest first: chunks from the stopping one (or the last) down to chunk 0
-        State acc = S::identity();
-#pragma unroll
-        for (int q = kPipeWindow - 1; q >= 0; q--) {
-            if (q <= qstop) {                                 // warp-uniform
-                State v = S::identity();
-                if (q < qstop || lane <= P) v = Codec::unpack(d[q]);
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {         // lane + dd holds an EARLIER tile than lane
-                    State o = shfl_down(v, dd);
-                    if (lane + dd < 32) v = S::join(o, v);
-                }
-                acc = S::join(acc, shfl_idx(v, 0));
-            }
-        }
-        excl = S::join(acc, excl);
-        if (qstop < kPipeWindow) break;
-        look -= 32 * kPipeWindow;
+        for (int j = 0; j < W; j++) w[j] = ((unsigned long long)x.u[j] << 32) | tag | flag | status;
     }
-    return excl;
-}
+    AFB_DI static State unpack(const unsigned long long (&w)[W]) {
+        union { To t; uint32_t u[W]; } x;
+#pragma unroll
+        for (int j = 0; j < W; j++) x.u[j] = (uint32_t)(w[j] >> 32);
+        if constexpr (KEYED) return State{x.t, (int)((w[0] >> 2) & 1u)};
+        else return x.t;
+    }
+    AFB_DI static bool valid(const unsigned long long (&w)[W], uint32_t tag) {
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < W; j++) ok = ok && ((((uint32_t)w[j]) & ~7u) == tag) && ((((uint32_t)w[j]) & 3u) != TILE_INVALID);
+        return ok;
+    }
+    AFB_DI static void load(const unsigned long long *pd, long long tile, unsigned long long (&w)[W]) {
+        if constexpr (W == 1) {
+            w[0] = ld_relaxed64(pd + tile);
+        } else {
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(pd + 2 * tile) : "memory");
+        }
+    }
+    AFB_DI static void store(unsigned long long *pd, long long tile, const unsigned long long (&w)[W]) {
+        if constexpr (W == 1) {
+            st_relaxed64(pd + tile, w[0]);
+        } else {
+            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(pd + 2 * tile), "l"(w[0]), "l"(w[1]) : "memory");
+        }
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // walker: R <- R (+) fold of the published aggregates of tiles [pos, end), executed by one full warp.
@@ -127,25 +103,27 @@ template<typename S, typename Codec>
 AFB_DI typename S::State walk_fold(const unsigned long long *pd, long long pos, long long end, uint tag, int lane,
                                    typename S::State R, unsigned long long *npolls = nullptr, int nwin = kPipeWindow) {
     typedef typename S::State State;
+    constexpr int W = Codec::W;
     while (pos < end) {
-        unsigned long long d[kPipeWindow];
+        unsigned long long d[kPipeWindow][W];
         uint need = (1u << nwin) - 1u;   // chunks that still have unpublished entries (warp-uniform)
         const long long wend = (pos + 32LL * nwin < end) ? pos + 32LL * nwin : end;
         uint spins = 0;
 #pragma unroll
-        for (int q = 0; q < kPipeWindow; q++) d[q] = 0ULL;
+        for (int q = 0; q < kPipeWindow; q++)
+#pragma unroll
+            for (int j = 0; j < W; j++) d[q][j] = 0ULL;
         while (true) {
 #pragma unroll
             for (int q = 0; q < kPipeWindow; q++) {
                 const long long t = pos + 32 * q + lane;
-                if (((need >> q) & 1u) && t < wend) d[q] = ld_relaxed64(pd + t);
+                if (((need >> q) & 1u) && t < wend) Codec::load(pd, t, d[q]);
             }
             uint still = 0u;
 #pragma unroll
             for (int q = 0; q < kPipeWindow; q++) {
                 const long long t = pos + 32 * q + lane;
-                const uint lo = (uint)d[q];
-                const bool ok = (t >= wend) || (((lo & ~7u) == tag) && ((lo & 3u) != TILE_INVALID));
+                const bool ok = (t >= wend) || Codec::valid(d[q], tag);
                 if (!__all_sync(0xffffffffu, ok)) still |= 1u << q;
             }
             if (npolls) (*npolls)++;
@@ -214,27 +192,31 @@ struct PipeScanArgs {
     int window;                  // 32-descriptor chunks per walker poll (1..kPipeWindow)
 };
 
-template<bool KEYED, int EPT, int STAGES, int NWARPS = kPipeWarps, int DLAG = kPipeLag> struct PipeLayout {
+template<bool KEYED, int EPT, int STAGES, int NWARPS = kPipeWarps, int DLAG = kPipeLag, int ES = 4, int KS = 4> struct PipeLayout {
     static constexpr int TILE = NWARPS * 32 * EPT;
-    static constexpr int KPAD = 4;                                  // key elements kept in front of the tile
+    static constexpr int KPAD = 16 / KS;                            // key elements kept in front of the tile (16 bytes)
     static constexpr int KSTAGES = KEYED ? STAGES - DLAG : 0;           // keys are dead after pass 1
-    static constexpr size_t val_bytes = (size_t)TILE * 4;
-    static constexpr size_t key_stage_bytes = ((size_t)TILE * 4 + KPAD * 4 + 127) / 128 * 128;
+    static constexpr size_t val_bytes = (size_t)TILE * ES;
+    static constexpr size_t key_stage_bytes = ((size_t)TILE * KS + 16 + 127) / 128 * 128;
     static constexpr size_t total = val_bytes * STAGES + key_stage_bytes * KSTAGES + 128;
     static_assert(val_bytes % 128 == 0, "value stages must stay 128-byte aligned");
 };
 
 template<int OP, typename Ti, typename To, bool KEYED, typename Tk, int EPT, int STAGES, int NWARPS, int DLAG>
 __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(const PipeScanArgs<Ti, To, Tk> a) {
-    static_assert(sizeof(Ti) == 4 && sizeof(To) == 4 && sizeof(Tk) == 4, "pipe scan: 4-byte values and keys");
-    static_assert(EPT % 4 == 0 && ((EPT / 4) & 1) == 1 && EPT <= 32, "EPT*4 bytes must be an odd number of 16-byte vectors");
+    constexpr int ES = (int)sizeof(To), KS = (int)sizeof(Tk);
+    constexpr int EV = 16 / ES;                 // elements per 16-byte vector
+    static_assert(sizeof(Ti) == sizeof(To) && (ES == 4 || ES == 8) && (KS == 4 || KS == 8), "pipe scan: in-place, 4- or 8-byte values and keys");
+    static_assert(EPT % EV == 0 && ((EPT / EV) & 1) == 1 && EPT <= 32, "EPT*ES bytes must be an odd number of 16-byte vectors");
+    constexpr bool KVEC = (EPT * KS) % 16 == 0; // the thread's keys can be read as 16-byte vectors
+    constexpr int KEV = 16 / KS;
     typedef Rule<OP, Ti, To> R;
     typedef SOps<R, To, KEYED> S;
     typedef typename S::State State;
-    typedef DescCodec<S, To, KEYED> Codec;
-    typedef PipeLayout<KEYED, EPT, STAGES, NWARPS, DLAG> Lay;
+    typedef PipeCodec<S, To, KEYED> Codec;
+    typedef PipeLayout<KEYED, EPT, STAGES, NWARPS, DLAG, (int)sizeof(To), (int)sizeof(Tk)> Lay;
     constexpr int TILE = Lay::TILE;
-    constexpr int NV = EPT / 4;
+    constexpr int NV = EPT / EV;
     constexpr int WCHUNK = 32 * EPT;
     constexpr int KPAD = Lay::KPAD;
     constexpr int NW = NWARPS, D = DLAG, RING = kPipeRing;
@@ -301,14 +283,14 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
             sm_first[s] = tcol == 0 ? 1 : 0;
             if (valid == TILE) {
                 fence_proxy_async();
-                const uint32_t kb = KEYED ? (uint32_t)(TILE * 4 + (tile_lo > 0 ? KPAD * 4 : 0)) : 0u;
+                const uint32_t kb = KEYED ? (uint32_t)(TILE * KS + (tile_lo > 0 ? 16 : 0)) : 0u;
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)Lay::val_bytes + kb);
                 bulk_g2s(val_base + (size_t)s * Lay::val_bytes, a.in + col_offset(a.g, col) + tile_lo, (uint32_t)Lay::val_bytes, &full_bar[s]);
                 if (KEYED) {
                     const Tk *ksrc = a.key + col_offset(kg, col) + tile_lo;
                     unsigned char *kdst = key_base + (size_t)(n % KST) * Lay::key_stage_bytes;
                     if (tile_lo > 0) bulk_g2s(kdst, ksrc - KPAD, kb, &full_bar[s]);   // key[tile_lo-1] lands in the pad
-                    else bulk_g2s(kdst + KPAD * 4, ksrc, kb, &full_bar[s]);
+                    else bulk_g2s(kdst + 16, ksrc, kb, &full_bar[s]);
                 }
             } else {
                 mbar_arrive(&full_bar[s]);   // ragged last tile of a column: the compute warps copy it themselves
@@ -383,7 +365,11 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                 State o = shfl_down(st, dd);
                 if (lane + dd < 32) st = S::join(st, o);
             }
-            if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(st, tag, TILE_AGGREGATE));
+            if (lane == 0) {
+                unsigned long long w[Codec::W];
+                Codec::pack(st, tag, TILE_AGGREGATE, w);
+                Codec::store(a.descs, tile, w);
+            }
         }
         return;
     }
@@ -521,19 +507,24 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                 Ti v[EPT];
 #pragma unroll
                 for (int j = 0; j < NV; j++) {
-                    const Vec16 q = *reinterpret_cast<const Vec16 *>(reinterpret_cast<const Ti *>(sv) + base + 4 * j);
+                    const Vec16 q = *reinterpret_cast<const Vec16 *>(reinterpret_cast<const Ti *>(sv) + base + EV * j);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) v[4 * j + k] = reinterpret_cast<const Ti *>(&q)[k];
+                    for (int k = 0; k < EV; k++) v[EV * j + k] = reinterpret_cast<const Ti *>(&q)[k];
                 }
                 uint hb = 0u;   // bit k: element k of this thread starts a segment
                 if (KEYED) {
                     Tk kk[EPT];
+                    if constexpr (KVEC) {
 #pragma unroll
-                    for (int j = 0; j < NV; j++) {
-                        // keys sit KPAD elements into their buffer: still 16-byte aligned
-                        const Vec16 q = *reinterpret_cast<const Vec16 *>(sk + base + 4 * j);
+                        for (int j = 0; j < EPT / KEV; j++) {
+                            // keys sit 16 bytes into their buffer: still 16-byte aligned
+                            const Vec16 q = *reinterpret_cast<const Vec16 *>(sk + base + KEV * j);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) kk[4 * j + k] = reinterpret_cast<const Tk *>(&q)[k];
+                            for (int k = 0; k < KEV; k++) kk[KEV * j + k] = reinterpret_cast<const Tk *>(&q)[k];
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < EPT; k++) kk[k] = sk[base + k];
                     }
                     Tk kprev;
                     if (base > 0 || !col_start) kprev = sk[base - 1];
@@ -603,8 +594,8 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                 for (int j = 0; j < NV; j++) {
                     Vec16 q;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) reinterpret_cast<To *>(&q)[k] = o[4 * j + k];
-                    *reinterpret_cast<Vec16 *>(sv + base + 4 * j) = q;
+                    for (int k = 0; k < EV; k++) reinterpret_cast<To *>(&q)[k] = o[EV * j + k];
+                    *reinterpret_cast<Vec16 *>(sv + base + EV * j) = q;
                 }
                 };
                 if (valid == TILE) pass1(std::false_type{});
@@ -636,13 +627,13 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                 if (nadd > 0) {
 #pragma unroll
                     for (int j = 0; j < NV; j++) {
-                        Vec16 q = *reinterpret_cast<const Vec16 *>(sv + base + 4 * j);
+                        Vec16 q = *reinterpret_cast<const Vec16 *>(sv + base + EV * j);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
+                        for (int k = 0; k < EV; k++) {
                             To &e = reinterpret_cast<To *>(&q)[k];
-                            if (!KEYED || 4 * j + k < nadd) e = R::join(wp, e);
+                            if (!KEYED || EV * j + k < nadd) e = R::join(wp, e);
                         }
-                        *reinterpret_cast<Vec16 *>(sv + base + 4 * j) = q;
+                        *reinterpret_cast<Vec16 *>(sv + base + EV * j) = q;
                     }
                 }
                 fence_proxy_async();   // make the generic-proxy writes (both passes) visible to the bulk store

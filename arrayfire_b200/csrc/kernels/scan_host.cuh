@@ -56,15 +56,18 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
                 }
             }
             // ---- 4-byte values (and keys): software-pipelined TMA-in / TMA-out kernel, one CTA per SM
-            if constexpr (sizeof(Ti) == 4 && sizeof(To) == 4 && sizeof(Tk) == 4) {
+            if constexpr (sizeof(Ti) == sizeof(To) && (sizeof(To) == 4 || sizeof(To) == 8) && (sizeof(Tk) == 4 || sizeof(Tk) == 8)) {
                 // measured on B200 (profiles/r01*): plain scans like few, fat warps (12 x 20 elements, 7 stages: 4.8 TB/s vs
                 // 4.1 TB/s with 16 x 12); by-key scans are latency-bound in pass 1 and like more warps (16 x 12 elements,
                 // 6 value + 3 key stages: 4.7 TB/s vs 4.1 TB/s with 12 warps)
-                constexpr int EPT = KEYED ? 12 : 20;
-                constexpr int NWP = KEYED ? 16 : 12;
+                // 8-byte values (f64, s64, u64, c32) keep the same stage bytes with half the elements per thread
+                constexpr int ES = (int)sizeof(To);
+                constexpr int EPT = (KEYED ? 12 : 20) * 4 / ES;
+                constexpr int NWP = KEYED ? ((sizeof(Tk) > sizeof(To)) ? 12 : 16) : 12;   // 8-byte keys of 4-byte values: smaller tiles
                 constexpr int ST = KEYED ? 6 : 7;
                 constexpr int DL = 3;   // measured: D = 2 (one more tile of prefetch instead) costs the plain scan 25 % (0.140 vs 0.110 ms)
-                typedef PipeLayout<KEYED, EPT, ST, NWP, DL> PL;
+                typedef PipeLayout<KEYED, EPT, ST, NWP, DL, (int)sizeof(To), (int)sizeof(Tk)> PL;
+                static_assert(PL::total <= 225 * 1024, "pipe scan: the stage rings must fit one SM");
                 if (ok && g.len >= 4 * (dim_t)PL::TILE && !env_int("AFB200_NO_PIPE", 0)) {
                     auto kern = pipe_scan_kernel<OP, Ti, To, KEYED, Tk, EPT, ST, NWP, DL>;
                     static bool configured[64] = {false};
@@ -90,7 +93,7 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
                         AFB_CUDA(cudaMemsetAsync(summary, 0, 24, c.stream));
                         AFB_CUDA(cudaMemsetAsync((char *)summary + 24, 0xff, 8, c.stream));
                     }
-                    a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
+                    a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8 * (sizeof(To) / 4), c.stream);
                     a.gen = c.scratch->next_wepoch(c.stream);
                     a.carry = (const To *)carry;
                     a.carry_key = (const Tk *)carry_key;

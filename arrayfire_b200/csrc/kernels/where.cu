@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     typedef PipeWhereLayout<T> Lay;
     typedef Rule<OP_ADD, uint, uint> R;
     typedef SOps<R, uint, false> S;
-    typedef DescCodec<S, uint, false> Codec;
+    typedef PipeCodec<S, uint, false> Codec;
     constexpr int E = Lay::E;
     constexpr int TILE = Lay::TILE, SUBTILE = Lay::SUBTILE;
     constexpr int U = kPW_U, NW = kPW_Warps, ST = kPW_Stages, SUB = kPW_Sub, RING = kPW_Ring;
@@ -510,7 +510,11 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
                     if (lane >= dd) inc += o;
                 }
                 const uint total = __shfl_sync(0xffffffffu, inc, 31);
-                if (lane == 0) st_relaxed64(&a.descs[tile], Codec::pack(total, tag, TILE_AGGREGATE));
+                if (lane == 0) {
+                    unsigned long long w[1];
+                    Codec::pack(total, tag, TILE_AGGREGATE, w);
+                    Codec::store(a.descs, tile, w);
+                }
                 sm_wexc[slot][2 * lane] = inc - v0 - v1;
                 sm_wexc[slot][2 * lane + 1] = inc - v1;
                 if (lane == 0) sm_total[slot] = total;

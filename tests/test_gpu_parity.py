@@ -309,7 +309,7 @@ def _keys(rng, n, kind, dtype):
     return k
 
 
-@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32])
+@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32, po.F64, po.S64, po.U64, po.C32])
 def test_pipe_scan(af, orc, code):
     rng = np.random.default_rng(9000 + code)
     shapes = [(4 * PIPE_TILE,), (4 * PIPE_TILE + 1,), (4 * PIPE_TILE + 4,), (5 * PIPE_TILE - 4,), ((1 << 21) + 3,),
@@ -333,20 +333,24 @@ def test_pipe_scan(af, orc, code):
         same_bits(af.scan(g, 0, 0, incl).to_numpy(), d4(want), "pipe scan view incl%d" % incl)
 
 
-@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32])
+@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32, po.F64, po.S64, po.C32])
 def test_pipe_scan_by_key(af, orc, code):
     rng = np.random.default_rng(9100 + code)
     shapes = [(4 * PIPE_TILE_KEYED,), (4 * PIPE_TILE_KEYED + 3,), (6 * PIPE_TILE_KEYED - 4,), ((1 << 21) + 1,), (24000, 3),
               (1 << 22,)]
+    if code not in (po.F32, po.S32):
+        shapes = shapes[:3] + shapes[4:5] + [((1 << 20) + 5,)]
     for shape in shapes:
         n = int(np.prod(shape))
         base = rand_data(rng, code, shape, nan_frac=0.02, exact=True)
         g = to_gpu(af, base, None, dtype=code)
         for kind in ("same", "distinct", "long", "short", "c4"):
-            for kcode in (po.S32, po.U32):
+            for kcode in (po.S32, po.U32, po.S64):
                 keys = np.asfortranarray(_keys(rng, n, kind, po.NP_OF[kcode]).reshape(shape, order="F"))
                 gk = to_gpu(af, keys, None, dtype=kcode)
                 for op in ((0, 2, 3) if kcode == po.S32 else (0,)):
+                    if op != 0 and code == po.C32 and kind not in ("c4", "long"):
+                        continue
                     for incl in (True, False):
                         t, want = orc.scan_by_key(keys, base, 0, op, incl, dtype=code, key_dtype=kcode)
                         got = af.scan_by_key(gk, g, 0, op, incl)
