@@ -61,9 +61,9 @@ AFB_DI void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     // a phase that does not complete within 20 s of wall time is a protocol bug (a bulk copy that never lands, a
     // role that died): fail loudly instead of hanging the device.  (Every failed try parks the warp for up to ~1 ms.)
-    const unsigned long long t0 = global_ns();
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (global_ns() - t0 > 20000000000ULL) __trap();
+        if (clock64() - t0 > 40000000000LL) __trap();   // ~20 s at 1.97 GHz
     }
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completes on `bar`
