@@ -484,22 +484,25 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
             } else {
                 // ---------------------------------------------------------------- pass 1 of tile i
                 const int valid = sm_valid[s];
-                // the ragged last tile of a column gets its own instantiation: the fast path carries no bounds checks
                 auto pass1 = [&](auto rag_c) {
                 constexpr bool RAG = decltype(rag_c)::value;
                 const bool col_start = sm_first[s] != 0;     // first tile of its column
                 To *sv = reinterpret_cast<To *>(val_base + (size_t)s * Lay::val_bytes);
                 Tk *sk = reinterpret_cast<Tk *>(key_base + (size_t)ks1 * Lay::key_stage_bytes) + KPAD;
-                if (RAG) {
-                    // ragged tile: plain cooperative copy (elements past the end cannot influence stored outputs,
-                    // and are masked to the identity below so that the tile total stays exact)
+                if (valid != TILE) {
+                    // ragged last tile of a column: plain cooperative copy, padded to a full tile with the op's identity
+                    // (and the last key repeated), so that the one fast path below serves every tile: elements past the
+                    // end cannot influence stored outputs, and identities keep the tile total exact
                     const dim_t col = tile / a.tiles_per_col, tcol = tile % a.tiles_per_col;
                     const dim_t tile_lo = tcol * TILE;
                     const Ti *gin = a.in + col_offset(a.g, col) + tile_lo;
                     for (int e = t; e < valid; e += NW * 32) reinterpret_cast<Ti *>(sv)[e] = ldg_stream<Ti>(gin + e);
+                    for (int e = valid + t; e < TILE; e += NW * 32) sv[e] = R::init();   // Ti and To are the same type here
                     if (KEYED) {
                         const Tk *gk = a.key + col_offset(kg, col) + tile_lo;
                         for (int e = t; e < valid; e += NW * 32) sk[e] = __ldg(gk + e);
+                        const Tk last = __ldg(gk + valid - 1);
+                        for (int e = valid + t; e < TILE; e += NW * 32) sk[e] = last;
                         if (t == 0 && tile_lo > 0) sk[-1] = __ldg(gk - 1);
                     }
                     named_bar_sync(1, NW * 32);
@@ -598,8 +601,7 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                     *reinterpret_cast<Vec16 *>(sv + base + EV * j) = q;
                 }
                 };
-                if (valid == TILE) pass1(std::false_type{});
-                else pass1(std::true_type{});
+                pass1(std::false_type{});
                 cw_p1 += clock64() - k0;
                 if (++s1 == STAGES) { s1 = 0; ph1 ^= 1u; }
                 if (++ks1 == KST) ks1 = 0;
