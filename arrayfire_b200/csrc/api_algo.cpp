@@ -636,6 +636,7 @@ af_err afx_peer_exchange(void *out, const void *payload, const unsigned long lon
     // pinned landing zone: [0, 512) gathered records, [2048, 2052) arrival flag
     unsigned char *hp = (unsigned char *)c.scratch->host_pinned;
     volatile unsigned *flag = (volatile unsigned *)(hp + 2048);
+    *flag = 0;   // the kernel raises it to `epoch`; never trust what an earlier exchange (or cudaMallocHost) left there
     launch_peer_exchange(c, payload, peer_bufs, rank, world, epoch, hp, (unsigned *)(hp + 2048));
     // spin on the host flag instead of a stream synchronisation: the kernel raises it after its last store
     unsigned long long spins = 0;

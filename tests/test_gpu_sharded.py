@@ -117,3 +117,27 @@ def test_sharded_reduce_scan_where_single_gpu(env, world):
     assert np.concatenate([g[0] for g in got]).tobytes() == want.tobytes()
     for idx, off, total in got:
         assert idx.tobytes() == want[off:off + idx.size].tobytes()
+
+
+def test_peer_exchange_single_rank(env):
+    """afx_peer_exchange with world = 1: the rank's own buffer plays every role (store, flag, wait, host landing);
+    the multi-rank protocol itself is exercised by tools/check_sharded.py under torchrun."""
+    import ctypes
+
+    import torch
+    af, sh, _ = env
+    buf = torch.zeros(2048, dtype=torch.uint8, device="cuda")
+    ptrs = (ctypes.c_ulonglong * 8)(buf.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
+    out = (ctypes.c_ubyte * 512)()
+    for epoch in range(1, 6):
+        payload = torch.arange(64, dtype=torch.uint8, device="cuda") + epoch
+        torch.cuda.synchronize()
+        af._check(af.lib.afx_peer_exchange(out, ctypes.c_void_p(payload.data_ptr()), ptrs, ctypes.c_int(0), ctypes.c_int(1),
+                                           ctypes.c_uint(epoch)))
+        got = np.frombuffer(out, dtype=np.uint8, count=64)
+        assert got.tolist() == [(i + epoch) % 256 for i in range(64)], epoch
+    # argument checking
+    with pytest.raises(af.AfError):
+        af._check(af.lib.afx_peer_exchange(out, ctypes.c_void_p(payload.data_ptr()), ptrs, ctypes.c_int(0), ctypes.c_int(9), ctypes.c_uint(1)))
+    with pytest.raises(af.AfError):
+        af._check(af.lib.afx_peer_exchange(out, ctypes.c_void_p(payload.data_ptr()), ptrs, ctypes.c_int(0), ctypes.c_int(1), ctypes.c_uint(0)))
