@@ -19,7 +19,7 @@ IS_FLOAT = {po.F32, po.F64, po.C32, po.C64, po.F16}
 
 # shapes chosen to hit every kernel regime (see arrayfire_b200/csrc/kernels/*_host.cuh)
 SHAPES_SMALL = [(1,), (7,), (1000,), (5, 3), (1, 9), (33, 1, 4), (4, 5, 3, 2), (2, 1, 1, 3), (257, 70), (40, 300)]
-SHAPES_BIG = [(70001,), (5000, 3), (3000, 100), (200003, 3), (130, 1000), (4, 50001), (96, 64, 2, 3), (1 << 20,)]
+SHAPES_BIG = [(70001,), (5000, 3), (3000, 100), (200003, 3), (130, 1000), (4, 50001), (96, 64, 2, 3), (1 << 20,), (2500, 4800)]
 
 
 @pytest.fixture(scope="module")
