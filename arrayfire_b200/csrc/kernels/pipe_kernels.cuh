@@ -206,7 +206,12 @@ template<int OP, typename Ti, typename To, bool KEYED, typename Tk, int EPT, int
 __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(const PipeScanArgs<Ti, To, Tk> a) {
     constexpr int ES = (int)sizeof(To), KS = (int)sizeof(Tk);
     constexpr int EV = 16 / ES;                 // elements per 16-byte vector
-    static_assert(sizeof(Ti) == sizeof(To) && (ES == 4 || ES == 8) && (KS == 4 || KS == 8), "pipe scan: in-place, 4- or 8-byte values and keys");
+    // NARROW: promoting scans (u8/s8/b8/s16/u16 -> 32 bit, never by key).  The input tile is staged in the ring the keys
+    // use otherwise (dead after pass 1); pass 1 converts and writes the 32-bit results into the value stage.
+    constexpr bool NARROW = sizeof(Ti) < sizeof(To);
+    constexpr int IS = (int)sizeof(Ti);
+    static_assert((sizeof(Ti) == sizeof(To) || (NARROW && !KEYED && ES == 4 && (EPT * IS) % 4 == 0)) && (ES == 4 || ES == 8) &&
+                  (KS == 4 || KS == 8), "pipe scan: 4- or 8-byte results, in place or promoted from 1- / 2-byte inputs");
     static_assert(EPT % EV == 0 && ((EPT / EV) & 1) == 1 && EPT <= 32, "EPT*ES bytes must be an odd number of 16-byte vectors");
     constexpr bool KVEC = (EPT * KS) % 16 == 0; // the thread's keys can be read as 16-byte vectors
     constexpr int KEV = 16 / KS;
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
     typedef SOps<R, To, KEYED> S;
     typedef typename S::State State;
     typedef PipeCodec<S, To, KEYED> Codec;
-    typedef PipeLayout<KEYED, EPT, STAGES, NWARPS, DLAG, (int)sizeof(To), (int)sizeof(Tk)> Lay;
+    typedef PipeLayout<KEYED || NARROW, EPT, STAGES, NWARPS, DLAG, (int)sizeof(To), NARROW ? (int)sizeof(Ti) : (int)sizeof(Tk)> Lay;
     constexpr int TILE = Lay::TILE;
     constexpr int NV = EPT / EV;
     constexpr int WCHUNK = 32 * EPT;
@@ -283,6 +288,13 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
             sm_first[s] = tcol == 0 ? 1 : 0;
             if (valid == TILE) {
                 fence_proxy_async();
+                if constexpr (NARROW) {
+                    // the narrow input goes to the side ring; the value stage is written by pass 1
+                    mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(TILE * IS));
+                    bulk_g2s(key_base + (size_t)(n % KST) * Lay::key_stage_bytes, a.in + col_offset(a.g, col) + tile_lo,
+                             (uint32_t)(TILE * IS), &full_bar[s]);
+                    return;
+                }
                 const uint32_t kb = KEYED ? (uint32_t)(TILE * KS + (tile_lo > 0 ? 16 : 0)) : 0u;
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)Lay::val_bytes + kb);
                 bulk_g2s(val_base + (size_t)s * Lay::val_bytes, a.in + col_offset(a.g, col) + tile_lo, (uint32_t)Lay::val_bytes, &full_bar[s]);
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
             // keys: stage pub % KST is free once pass 1 of tile pub - KST has read it (pass 1 arrives on p1_bar after
             // its key loads; tiles are processed in order, so this wait can never block the tile it waits for)
             const long long w0 = clock64();
-            if (KEYED && pub >= KST) mbar_wait(&p1_bar[(pub - KST) % RING], (uint32_t)(((pub - KST) / RING) & 1));
+            if ((KEYED || NARROW) && pub >= KST) mbar_wait(&p1_bar[(pub - KST) % RING], (uint32_t)(((pub - KST) / RING) & 1));
             dma_dbg[2] += clock64() - w0;
             publish(pub, t);
             pub++;
@@ -496,8 +508,12 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                     const dim_t col = tile / a.tiles_per_col, tcol = tile % a.tiles_per_col;
                     const dim_t tile_lo = tcol * TILE;
                     const Ti *gin = a.in + col_offset(a.g, col) + tile_lo;
-                    for (int e = t; e < valid; e += NW * 32) reinterpret_cast<Ti *>(sv)[e] = ldg_stream<Ti>(gin + e);
-                    for (int e = valid + t; e < TILE; e += NW * 32) sv[e] = R::init();   // Ti and To are the same type here
+                    if constexpr (NARROW) {
+                        for (int e = t; e < valid; e += NW * 32) sv[e] = R::pre(ldg_stream<Ti>(gin + e));   // converted here, RAG below
+                    } else {
+                        for (int e = t; e < valid; e += NW * 32) reinterpret_cast<Ti *>(sv)[e] = ldg_stream<Ti>(gin + e);
+                    }
+                    for (int e = valid + t; e < TILE; e += NW * 32) sv[e] = R::init();   // in place: Ti and To are the same type
                     if (KEYED) {
                         const Tk *gk = a.key + col_offset(kg, col) + tile_lo;
                         for (int e = t; e < valid; e += NW * 32) sk[e] = __ldg(gk + e);
@@ -507,12 +523,29 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                     }
                     named_bar_sync(1, NW * 32);
                 }
-                Ti v[EPT];
+                To xin[EPT];   // the thread's elements after the op's pre-transform
+                if constexpr (NARROW && !RAG) {
+                    constexpr int NWORD = EPT * IS / 4;
+                    const uint32_t *si = reinterpret_cast<const uint32_t *>(key_base + (size_t)ks1 * Lay::key_stage_bytes) + (size_t)t * NWORD;
+                    uint32_t wds[NWORD];
 #pragma unroll
-                for (int j = 0; j < NV; j++) {
-                    const Vec16 q = *reinterpret_cast<const Vec16 *>(reinterpret_cast<const Ti *>(sv) + base + EV * j);
+                    for (int j = 0; j < NWORD; j++) wds[j] = si[j];
 #pragma unroll
-                    for (int k = 0; k < EV; k++) v[EV * j + k] = reinterpret_cast<const Ti *>(&q)[k];
+                    for (int k = 0; k < EPT; k++) xin[k] = R::pre(reinterpret_cast<const Ti *>(wds)[k]);
+                } else if constexpr (NARROW && RAG) {
+#pragma unroll
+                    for (int j = 0; j < NV; j++) {
+                        const Vec16 q = *reinterpret_cast<const Vec16 *>(sv + base + EV * j);
+#pragma unroll
+                        for (int k = 0; k < EV; k++) xin[EV * j + k] = reinterpret_cast<const To *>(&q)[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NV; j++) {
+                        const Vec16 q = *reinterpret_cast<const Vec16 *>(reinterpret_cast<const Ti *>(sv) + base + EV * j);
+#pragma unroll
+                        for (int k = 0; k < EV; k++) xin[EV * j + k] = R::pre(reinterpret_cast<const Ti *>(&q)[k]);
+                    }
                 }
                 uint hb = 0u;   // bit k: element k of this thread starts a segment
                 if (KEYED) {
@@ -547,8 +580,7 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                 To run = R::init();
 #pragma unroll
                 for (int k = 0; k < EPT; k++) {
-                    To e = R::pre(v[k]);
-                    if (RAG && base + k >= valid) e = R::init();
+                    const To e = xin[k];
                     if (k == 0) run = e;
                     else if (KEYED) run = ((hb >> k) & 1u) ? e : R::join(run, e);
                     else run = R::join(run, e);
@@ -601,7 +633,8 @@ __global__ void __launch_bounds__(pipe_threads(NWARPS), 1) pipe_scan_kernel(cons
                     *reinterpret_cast<Vec16 *>(sv + base + EV * j) = q;
                 }
                 };
-                pass1(std::false_type{});
+                if (NARROW && valid != TILE) pass1(std::true_type{});   // ragged promoted tile: converted by the copy above
+                else pass1(std::false_type{});
                 cw_p1 += clock64() - k0;
                 if (++s1 == STAGES) { s1 = 0; ph1 ^= 1u; }
                 if (++ks1 == KST) ks1 = 0;

@@ -56,17 +56,19 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
                 }
             }
             // ---- 4-byte values (and keys): software-pipelined TMA-in / TMA-out kernel, one CTA per SM
-            if constexpr (sizeof(Ti) == sizeof(To) && (sizeof(To) == 4 || sizeof(To) == 8) && (sizeof(Tk) == 4 || sizeof(Tk) == 8)) {
+            if constexpr (((sizeof(Ti) == sizeof(To) && (sizeof(To) == 4 || sizeof(To) == 8)) || (!KEYED && sizeof(Ti) < 4 && sizeof(To) == 4)) &&
+                          (sizeof(Tk) == 4 || sizeof(Tk) == 8)) {
                 // measured on B200 (profiles/r01*): plain scans like few, fat warps (12 x 20 elements, 7 stages: 4.8 TB/s vs
                 // 4.1 TB/s with 16 x 12); by-key scans are latency-bound in pass 1 and like more warps (16 x 12 elements,
                 // 6 value + 3 key stages: 4.7 TB/s vs 4.1 TB/s with 12 warps)
                 // 8-byte values (f64, s64, u64, c32) keep the same stage bytes with half the elements per thread
                 constexpr int ES = (int)sizeof(To);
-                constexpr int EPT = (KEYED ? 12 : 20) * 4 / ES;
+                constexpr bool NARROW = sizeof(Ti) < sizeof(To);   // promoting scans: smaller tiles, the input has its own ring
+                constexpr int EPT = NARROW ? 12 : (KEYED ? 12 : 20) * 4 / ES;
                 constexpr int NWP = KEYED ? ((sizeof(Tk) > sizeof(To)) ? 12 : 16) : 12;   // 8-byte keys of 4-byte values: smaller tiles
                 constexpr int ST = KEYED ? 6 : 7;
                 constexpr int DL = 3;   // measured: D = 2 (one more tile of prefetch instead) costs the plain scan 25 % (0.140 vs 0.110 ms)
-                typedef PipeLayout<KEYED, EPT, ST, NWP, DL, (int)sizeof(To), (int)sizeof(Tk)> PL;
+                typedef PipeLayout<KEYED || NARROW, EPT, ST, NWP, DL, (int)sizeof(To), NARROW ? (int)sizeof(Ti) : (int)sizeof(Tk)> PL;
                 static_assert(PL::total <= 225 * 1024, "pipe scan: the stage rings must fit one SM");
                 if (ok && g.len >= 4 * (dim_t)PL::TILE && !env_int("AFB200_NO_PIPE", 0)) {
                     auto kern = pipe_scan_kernel<OP, Ti, To, KEYED, Tk, EPT, ST, NWP, DL>;

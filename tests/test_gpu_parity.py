@@ -309,7 +309,7 @@ def _keys(rng, n, kind, dtype):
     return k
 
 
-@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32, po.F64, po.S64, po.U64, po.C32])
+@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32, po.F64, po.S64, po.U64, po.C32, po.U8, po.S8, po.B8, po.S16, po.U16])
 def test_pipe_scan(af, orc, code):
     rng = np.random.default_rng(9000 + code)
     shapes = [(4 * PIPE_TILE,), (4 * PIPE_TILE + 1,), (4 * PIPE_TILE + 4,), (5 * PIPE_TILE - 4,), ((1 << 21) + 3,),
@@ -324,6 +324,8 @@ def test_pipe_scan(af, orc, code):
                 t, want = orc.scan(base, 0, op, incl, dtype=code)
                 got = af.scan(g, 0, op, incl)
                 same_bits(got.to_numpy(), d4(want), "pipe scan op%d incl%d %s" % (op, incl, shape))
+        t, want = orc.accum(base, 0, dtype=code)      # b8: counts the non-zeros instead of adding the bytes
+        same_bits(af.accum(g, 0).to_numpy(), d4(want), "pipe accum %s" % (shape,))
     # an aligned column view of a larger parent (strided columns, 16-byte aligned offsets)
     base = rand_data(rng, code, (60000, 4), exact=True)
     sl = (slice(8, 8 + 4 * PIPE_TILE + 8), slice(1, 4))
