@@ -177,6 +177,7 @@ struct ChainWhereArgs {
     uint base;
     unsigned long long *ticket;
     unsigned long long ticket_base;
+    unsigned long long *debug;     // optional per-CTA cycle counters of pipe_where_kernel (AFB200_PIPE_DEBUG=1)
 };
 
 // bit k of the result: element k of the 16-byte vector is non-zero
@@ -553,6 +554,8 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     long long m = 0;            // sub-tile counter (matches the DMA warp's)
     long long tile_prev = 0;
     bool ended = false;
+    unsigned long long cw[4] = {0, 0, 0, 0};   // wait full, pass 1, wait walker, pass 2
+    const long long cw_start = clock64();
     for (long long i = 0;; i++) {
         const int b = (int)(i % RING);
         // ---------------------------------------------------------------- pass 1 of tile i: masks + counts
@@ -562,7 +565,10 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
 #pragma unroll 1
         for (int sub = 0; sub < SUB; sub++) {
             const int s = (int)(m % ST);
+            long long k0 = clock64();
             mbar_wait(&full_bar[s], (uint32_t)((m / ST) & 1));
+            cw[0] += clock64() - k0;
+            k0 = clock64();
             if (sub == 0) {
                 tile = sm_stage_tile[s];
                 if (tile >= a.ntiles) {
@@ -596,6 +602,7 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
                 sm_wtot[b][sub * NW + warp] = cnt;
                 mbar_arrive(&empty_bar[s]);   // the stage may be refilled (the reduce above ordered every lane's reads)
             }
+            cw[1] += clock64() - k0;
             m++;
         }
         if (lane == 0 && warp == 0) sm_tile_of[b] = ended ? a.ntiles : tile;
@@ -604,7 +611,10 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
         if (i >= 1) {
             // ---------------------------------------------------------------- pass 2 of tile i-1: compaction
             const int bp = (int)((i - 1) % RING);
+            long long k1 = clock64();
             mbar_wait(&lb_bar[bp], (uint32_t)(((i - 1) / RING) & 1));
+            cw[2] += clock64() - k1;
+            k1 = clock64();
             const unsigned short *mkp = masks + (size_t)((i - 1) & 1) * (SUB * Lay::NVEC);
 #pragma unroll 1
             for (int sub = 0; sub < SUB; sub++) {
@@ -663,9 +673,14 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
                     gpos += total;
                 }
             }
+            cw[3] += clock64() - k1;
         }
         if (ended) break;
         tile_prev = tile;
+    }
+    if (a.debug && warp == 0 && lane == 0) {
+        for (int q = 0; q < 4; q++) a.debug[blockIdx.x * 8 + q] = cw[q];
+        a.debug[blockIdx.x * 8 + 4] = clock64() - cw_start;
     }
 }
 
@@ -683,6 +698,7 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
             configured[dv] = true;
         }
         ChainWhereArgs<T> a;
+        a.debug = nullptr;
         a.in = (const T *)in.ptr;
         a.n = n;
         a.out = out;
@@ -696,9 +712,25 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         a.ticket = c.scratch->chain_ticket;
         a.ticket_base = c.scratch->chain_base;
         c.scratch->chain_base += (unsigned long long)a.ntiles + 2ULL * (unsigned long long)grid;  // two tickets in flight per CTA
+        static unsigned long long *dbg_buf = nullptr;
+        const bool dbg = env_int("AFB200_PIPE_DEBUG", 0) != 0;
+        if (dbg && !dbg_buf) AFB_CUDA(cudaMalloc(&dbg_buf, 1024 * 8 * 8));
+        a.debug = dbg ? dbg_buf : nullptr;
         kern<<<(unsigned)grid, kPW_Threads, PL::total, c.stream>>>(a);
         note_launches(1);
         post_launch_check("pipe_where_kernel");
+        if (dbg) {
+            static unsigned long long h[1024 * 8];
+            AFB_CUDA(cudaStreamSynchronize(c.stream));
+            AFB_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+            const char *names[5] = {"cmp_wait_full", "cmp_p1", "cmp_wait_walker", "cmp_p2", "total"};
+            fprintf(stderr, "[pipe_where debug] grid=%d ntiles=%lld\n", (int)grid, (long long)a.ntiles);
+            for (int q = 0; q < 5; q++) {
+                double sum = 0;
+                for (int b = 0; b < (int)grid; b++) sum += (double)h[b * 8 + q];
+                fprintf(stderr, "   %-16s mean %.0f\n", names[q], sum / (double)grid);
+            }
+        }
         return;
     }
     if (aligned_to(in.ptr, 16) && n >= CT && !env_int("AFB200_NO_CHAIN", 0)) {
@@ -713,6 +745,7 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
             resident[dv] = nb > 0 ? nb : 1;
         }
         ChainWhereArgs<T> a;
+        a.debug = nullptr;
         a.in = (const T *)in.ptr;
         a.n = n;
         a.out = out;
