@@ -371,6 +371,7 @@ void Scratch::ensure_basics() {
 }
 
 void *Scratch::need_wtiles(size_t bytes, cudaStream_t s) {
+    bytes += 64;   // the walkers read descriptors in 16-byte pairs and may touch the word after the last tile
     if (bytes > wtiles_bytes) {
         if (wtiles) { AFB_CUDA(cudaStreamSynchronize(s)); cudaFree(wtiles); }
         size_t nb = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
