@@ -140,6 +140,7 @@ def build_suite(af, torch, d, rank, world, group):
             "C5.where_01": lambda: ops.where(m01, d["c5_base"]),
             "C5.count": lambda: ops.reduce_all(sh.OP_COUNT, m50),
         }
+        keep.append(ops)
     return suite, keep
 
 
@@ -157,8 +158,9 @@ class E2E:
     """The same suite through the public API with pinned HOST inputs: af_create_array (H2D) -> op ->
     af_get_data_ptr / scalar (D2H) every step."""
 
-    def __init__(self, af, torch, d, world):
+    def __init__(self, af, torch, d, world, ops=None):
         self.af, self.torch = af, torch
+        self.ops, self.d = ops, d      # ops: arrayfire_b200.sharded.ShardedOps when world > 1 (cross-GPU combine included)
         self.h = {}
         for k in ("x1", "m2_cols", "m2_rows", "x3", "i3", "u3", "k4", "v4", "m50", "m01"):
             t = torch.empty(d[k].shape, dtype=d[k].dtype, pin_memory=True)
@@ -184,6 +186,8 @@ class E2E:
         arr.host_into(self.out.view(np.uint8)[:max(n, 1)])
 
     def step(self):
+        if self.ops is not None:
+            return self.step_sharded()
         af = self.af
         self.h2d = self.d2h = 0
         counts = {}
@@ -202,6 +206,31 @@ class E2E:
         self._down(af.accum(x1, 0))
         r = af.where(self._up("m01")); counts["C5.where_01"] = r.elements; self._down(r)
         af.count_all(m50); self.d2h += 4
+        return counts
+
+
+    def step_sharded(self):
+        """N > 1: every rank uploads ITS shard from pinned host memory, the whole-array ops go through ShardedOps (kernel +
+        cross-GPU combine), array results (the rank's slice) come back to the host"""
+        from arrayfire_b200 import sharded as sh
+        af, ops, d = self.af, self.ops, self.d
+        self.h2d = self.d2h = 0
+        counts = {}
+        self._down(af.sum(self._up("m2_cols"), 0))
+        ops.reduce_all(sh.OP_SUM, self._up("x3")); self.d2h += 4
+        self._down(af.sum(self._up("m2_rows"), 1))
+        ops.reduce_all(sh.OP_SUM, self._up("i3")); self.d2h += 4
+        self._down(af.max(self._up("m2_cols"), 0))
+        ops.ireduce_all(sh.OP_MAX, self._up("u3"), d["x3_base"]); self.d2h += 8
+        self._down(af.max(self._up("m2_rows"), 1))
+        self._down(ops.scan_by_key(self._up("k4"), self._up("v4"), af.AF_BINARY_ADD, False))
+        x1 = self._up("x1")
+        ops.reduce_all(sh.OP_SUM, x1); self.d2h += 4
+        m50 = self._up("m50")
+        r, _, total = ops.where(m50, d["c5_base"]); counts["C5.where_50"] = total; self._down(r)
+        self._down(ops.scan(x1, af.AF_BINARY_ADD, True))
+        r, _, total = ops.where(self._up("m01"), d["c5_base"]); counts["C5.where_01"] = total; self._down(r)
+        ops.reduce_all(sh.OP_COUNT, m50); self.d2h += 4
         return counts
 
 
@@ -246,6 +275,7 @@ def gpu_arm(args):
     d = make_inputs(torch, w, rank, world, dev)
     log("[rank %d] inputs ready in %.1f s" % (rank, time.time() - t0))
     suite, keep = build_suite(af, torch, d, rank, world, group)
+    e2e_ops = keep[-1] if world > 1 else None   # build_suite appends its ShardedOps instance
 
     def barrier():
         torch.cuda.synchronize()
@@ -343,7 +373,7 @@ def gpu_arm(args):
     e2e = None
     if not args.no_e2e:
         t0 = time.time()
-        runner = E2E(af, torch, d, world)
+        runner = E2E(af, torch, d, world, e2e_ops)
         log("[rank %d] pinned host copies ready in %.1f s" % (rank, time.time() - t0))
         ksteps = max(1, min(args.steps, 5))
         runner.step()   # warm the pool for the host-path allocations
@@ -360,12 +390,13 @@ def gpu_arm(args):
             t = torch.tensor([e_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t[0])
-        # under N > 1 the e2e arm runs each rank's shard independently (no combine); bytes are per-rank sums
-        e_bytes = total_bytes if world == 1 else total_bytes
+        # under N > 1 every rank uploads its shard and the whole-array ops include the cross-GPU combine
+        e_bytes = total_bytes
         e2e = {"value": round(e_bytes * ksteps / (e_ms * 1e-3) / 1e9, 2), "unit": "GB/s",
                "h2d_bytes_per_step": int(runner.h2d) * world, "d2h_bytes_per_step": int(runner.d2h) * world,
                "steps": ksteps, "ms_per_step": round(e_ms / ksteps, 2),
-               "how": "pinned host inputs -> af_create_array (H2D) -> op -> af_get_data_ptr / scalar (D2H), every step"}
+               "how": "pinned host inputs -> af_create_array (H2D) -> op (N > 1: sharded op incl. the cross-GPU combine) -> "
+                      "af_get_data_ptr / scalar (D2H), every step"}
         del runner
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
