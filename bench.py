@@ -33,6 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED = 0xAF00
+WORKLOAD = ("C1..C5 suite of BASELINE.json, every op once per step: sum+inclusive scan 2^26 f32; sum/max dim0+dim1 8192x8192 f32; "
+            "sum_all f32/s32 + imax_all f32 2^30; scan_by_key excl add 2^28 s32; where 50%/1% + count 2^30 u8")
 
 
 def log(*a):
@@ -237,8 +239,7 @@ def reference_arm(args):
         "impl": "reference", "metric": "effective_GBps_reduce_scan_where", "value": base["value"], "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32/s32/u8", "data": "synthetic",
-        "config": {"workload": "C1..C5 suite of BASELINE.json (sum/max dim0+dim1, sum_all, imax_all, scan, "
-                               "scan_by_key, where, count)", "sample": base["sample"]},
+        "config": {"workload": WORKLOAD, "sample": base["sample"]},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-from bench import (OP_ORDER, SEED, ClockSampler, algorithmic_bytes, log, run_cpu, workload)
+from bench import (OP_ORDER, SEED, WORKLOAD, ClockSampler, algorithmic_bytes, log, run_cpu, workload)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 
@@ -414,9 +414,7 @@ def gpu_arm(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/s32/u8",
             "data": "synthetic",
-            "config": {"workload": "C1..C5 suite of BASELINE.json, every op once per step: sum+inclusive scan 2^26 f32; "
-                                   "sum/max dim0+dim1 8192x8192 f32; sum_all f32/s32 + imax_all f32 2^30; scan_by_key excl "
-                                   "add 2^28 s32; where 50%/1% + count 2^30 u8",
+            "config": {"workload": WORKLOAD,
                        "scale": args.scale, "l2": "every input (>=256 MiB) exceeds the 126 MB L2 and ops are interleaved so "
                                                   "no input is re-read while resident",
                        "sharding": "none" if world == 1 else "whole-array ops sharded along the flattened axis (global sizes "
