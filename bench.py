@@ -12,9 +12,10 @@ timed region.  `roofline` describes the dominant kernel (the whole-array span re
 per-op breakdown, `cpu_baseline` times the reference's CPU implementation on a bounded sample.
 
 With N > 1 (launched under torchrun, one rank per GPU) the whole-array ops C3/C4/C5 are sharded along the
-flattened axis (strong scaling: the global sizes stay those of BASELINE.json), per-shard partials are
-combined with NCCL (arrayfire_b200/sharded.py), and the dimension-wise ops C1/C2 are partitioned along a
-non-reduced axis with no communication.
+flattened axis (strong scaling: the global sizes stay those of BASELINE.json), the 64-byte per-shard partials
+are exchanged by one kernel over NVLink peer memory (afx_peer_exchange; NCCL all-gather as the fallback) and
+folded in rank order (arrayfire_b200/sharded.py); the dimension-wise ops of C2 are partitioned along a
+non-reduced axis with no communication.  The e2e arm then uploads every rank's shard from pinned host memory.
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref when it was built from
 /root/reference, else the oracle port) on rank 0, each step a bounded sample of the same workload.
