@@ -1,23 +1,29 @@
-// pipe_kernels.cuh -- the software-pipelined, TMA-in / TMA-out single-pass scan of libafb200 (4-byte types).
+// pipe_kernels.cuh -- the software-pipelined, TMA-in / TMA-out single-pass scan of libafb200
+// (4- and 8-byte values, by key or not, and the promoting scans of 1- / 2-byte inputs).
 //
-// Why it exists (profiles/r01b_*.md): the first persistent chained scan (chain_kernels.cuh) kept every warp of
+// Why it exists (profiles/r01_summary.md): the first persistent chained scan (chain_kernels.cuh) kept every warp of
 // a CTA on the CTA barrier while warp 0 walked the look-back chain -- ncu showed 65-70 % of the stall samples on
 // `barrier`, 10-13 us per tile, 15-28 % of DRAM peak -- and spent 22-60 thread-instructions per element on
-// per-slot shuffle scans.  This kernel removes both costs:
+// per-slot shuffle scans.  On a B200 whose HBM is saturated every synchronous L2 round trip (descriptor poll, ticket
+// atomic) costs 1700-4000 cycles, so the design rule here is: NO compute warp ever waits on one.
 //
-//   * ONE CTA per SM: 8 compute warps + 1 control warp.  Tiles are drawn by monotone ticket (a tile only ever
-//     waits for tiles with smaller tickets, whose CTAs are already running), staged into a ring of shared-memory
-//     stages by bulk-async copies (TMA, mbarrier complete_tx) several tiles ahead, transformed IN PLACE in shared
-//     memory and written back by bulk-async stores: no thread ever issues a global load/store on the fast path.
-//   * blocked register layout: a thread owns EPT consecutive elements (EPT*4 bytes is an ODD number of 16-byte
+//   * ONE CTA per SM, warp-specialised: 12-16 compute warps + a publisher warp + two walker warps + a one-thread DMA
+//     warp, talking through mbarriers only.  Tiles are drawn by monotone ticket (a tile only ever waits for tiles with
+//     smaller tickets, whose CTAs are already running), staged into a ring of shared-memory stages by bulk-async copies
+//     (TMA, mbarrier complete_tx) three tiles ahead, transformed IN PLACE in shared memory and written back by
+//     bulk-async stores: no thread issues a global load/store on the fast path.
+//   * blocked register layout: a thread owns EPT consecutive elements (EPT*size bytes is an ODD number of 16-byte
 //     vectors, so the 128-bit shared-memory accesses of a quarter-warp are conflict-free): one serial scan per
-//     thread + ONE shuffle scan per warp per tile (~3-10 instructions per element instead of 22-60).
-//   * the look-back is taken off the critical path: pass 1 of tile i (local scan, warp totals) is followed by
-//     pass 2 of tile i-1 (add the resolved prefix), so the control warp has a whole tile period to resolve tile
-//     i's prefix; the compute warps never wait on the CTA barrier at all (mbarriers only).
-//   * look-back windows are 256 tiles wide (8 packed 64-bit descriptors per lane, value + generation + flag +
-//     status in one relaxed load): one L2 round trip covers every tile in flight on the 148 SMs.
-//   * by-key scans stop the look-back at the first predecessor that contains a segment head.
+//     thread + ONE shuffle scan per warp per tile (~6-14 instructions per element instead of 22-60).
+//   * two passes, D = 3 tiles apart: pass 1 of tile i (local scan in place, warp totals) is followed by pass 2 of tile
+//     i-3 (add the value carried into the warp's chunk), so the tile's prefix has three tile periods to arrive.
+//   * publisher: the moment the warp totals of a tile exist, its AGGREGATE goes out as packed 64-bit word(s)
+//     (value | generation | head flag | status; relaxed store, no fences, never cleared between launches).
+//   * walkers instead of a chain of prefixes: every CTA keeps its own running fold over ALL published aggregates in
+//     ticket order (walk_fold: coalesced 256-byte descriptor reads, 8 in flight).  The fold of the foreign tiles
+//     between two own tiles depends on nothing this CTA computes, so the two walkers overlap it; only the cheap chain
+//     R_j = R_{j-1} (+) total_{j-1} (+) F_j is handed from walker to walker through shared memory.  Fixed fold order:
+//     bitwise reproducible floating-point scans.
 //
 // Semantics: /root/reference/src/backend/cpu/kernel/scan.hpp:37-72, scan_by_key.hpp:43-86.
 #pragma once
@@ -154,15 +160,16 @@ AFB_DI typename S::State walk_fold(const unsigned long long *pd, long long pos, 
 // pipe_scan_kernel
 // ------------------------------------------------------------------------------------------------
 // Warp roles of the (single) CTA of an SM:
-//   warps 0..NW-1  compute: pass 1 of tile i (local scan in place, warp totals), then pass 2 of tile i-D
-//                  (add the value carried into the warp's chunk); mbarriers only, never a CTA-wide barrier
-//   warp NW        look-back: publishes the aggregate of tile j as soon as its warp totals exist, and
-//                  resolves tile j-1 -- whose predecessors published their aggregates a whole tile period
-//                  earlier, so one poll (one loaded L2 round trip, ~1 us on a saturated B200) normally suffices
-//   warp NW+1      DMA (one thread): draws tile tickets two ahead, keeps the bulk loads STAGES-D-1 tiles ahead
-//                  of pass 1 and writes finished tiles back with bulk stores
-// Every synchronous L2 round trip (ticket atomic, descriptor poll) costs ~2000 cycles under full HBM load
-// (measured); the roles are split so that none of them sits on the compute warps' path.
+//   warps 0..NW-1      compute: pass 1 of tile i (local scan in place, warp totals), then pass 2 of tile i-D
+//                      (add the value carried into the warp's chunk); mbarriers only, never a CTA-wide barrier
+//   warp NW            publisher: folds the warp totals of tile j and publishes the tile aggregate at once
+//   warps NW+1, NW+2   walkers: walker k resolves this CTA's tiles j = k (mod 2): fold of the foreign aggregates since
+//                      the previous own tile (one loaded L2 round trip, 3000+ cycles), chained with the running fold
+//                      handed over by the other walker; writes the per-warp carries pass 2 waits for
+//   warp NW+3          DMA (one thread): draws tile tickets two ahead, keeps the bulk loads STAGES-D-1 tiles ahead of
+//                      pass 1 and writes finished tiles back with bulk stores
+// Measured alternatives (profiles/r01_summary.md): one or three walkers, D = 2, a classic PREFIX chain, 128-bit
+// descriptor loads, delayed polls -- all slower or neutral.
 constexpr int kPipeWarps = 12;                      // compute warps (default; a template parameter of the kernel)
 constexpr int kPipeWalkers = 2;                     // walker warps; walker k resolves the tiles j = k (mod kPipeWalkers)
 constexpr int kPipeLB = 1 + kPipeWalkers;           // publisher warp + walker warps
