@@ -19,7 +19,8 @@ __all__ = [
     "s8", "AF_BINARY_ADD", "AF_BINARY_MUL", "AF_BINARY_MIN", "AF_BINARY_MAX", "sum", "product", "min", "max", "count",
     "all_true", "any_true", "sum_all", "product_all", "min_all", "max_all", "count_all", "all_true_all", "any_true_all",
     "imin", "imax", "imin_all", "imax_all", "accum", "scan", "scan_by_key", "where", "sync", "constant", "info_string",
-    "get_stream", "launch_count", "device_gc", "seq", "span",
+    "get_stream", "launch_count", "device_gc", "seq", "span", "sum_by_key", "product_by_key", "min_by_key", "max_by_key",
+    "count_by_key", "all_true_by_key", "any_true_by_key", "max_ragged", "cast", "moddims", "flat",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -408,6 +409,72 @@ def imin_all(a):
 
 def imax_all(a):
     return _ireduce_all(lib.af_imax_all, a)
+
+
+# ---- reductions by key (af::sumByKey & co., src/api/cpp/reduce.cpp:28-166) ---------------------------
+def _by_key(fn, keys, vals, dim, *extra, fnsd=True):
+    ko, vo = _vp(), _vp()
+    d = _fnsd(vals, dim) if fnsd else dim
+    _check(fn(ctypes.byref(ko), ctypes.byref(vo), keys.handle, vals.handle, ctypes.c_int(d), *extra))
+    return Array(ko), Array(vo)
+
+
+def sum_by_key(keys, vals, dim=-1, nanval=None):
+    if nanval is None:
+        return _by_key(lib.af_sum_by_key, keys, vals, dim)
+    return _by_key(lib.af_sum_by_key_nan, keys, vals, dim, ctypes.c_double(nanval), fnsd=False)
+
+
+def product_by_key(keys, vals, dim=-1, nanval=None):
+    if nanval is None:
+        return _by_key(lib.af_product_by_key, keys, vals, dim)
+    return _by_key(lib.af_product_by_key_nan, keys, vals, dim, ctypes.c_double(nanval), fnsd=False)
+
+
+def min_by_key(keys, vals, dim=-1):
+    return _by_key(lib.af_min_by_key, keys, vals, dim)
+
+
+def max_by_key(keys, vals, dim=-1):
+    return _by_key(lib.af_max_by_key, keys, vals, dim)
+
+
+def count_by_key(keys, vals, dim=-1):
+    return _by_key(lib.af_count_by_key, keys, vals, dim)
+
+
+def all_true_by_key(keys, vals, dim=-1):
+    return _by_key(lib.af_all_true_by_key, keys, vals, dim)
+
+
+def any_true_by_key(keys, vals, dim=-1):
+    return _by_key(lib.af_any_true_by_key, keys, vals, dim)
+
+
+def max_ragged(a, ragged_len, dim):
+    """af::max(val, idx, in, ragged_len, dim), src/api/cpp/reduce.cpp:120-127"""
+    v, i = _vp(), _vp()
+    _check(lib.af_max_ragged(ctypes.byref(v), ctypes.byref(i), a.handle, ragged_len.handle, ctypes.c_int(dim)))
+    return Array(v), Array(i)
+
+
+def cast(a, dtype):
+    """array::as(type) -> af_cast"""
+    h = _vp()
+    _check(lib.af_cast(ctypes.byref(h), a.handle, ctypes.c_int(dtype)))
+    return Array(h)
+
+
+def moddims(a, dims):
+    h = _vp()
+    _check(lib.af_moddims(ctypes.byref(h), a.handle, ctypes.c_uint(len(dims)), _dims_arr(dims)))
+    return Array(h, a._keepalive)
+
+
+def flat(a):
+    h = _vp()
+    _check(lib.af_flat(ctypes.byref(h), a.handle))
+    return Array(h, a._keepalive)
 
 
 # ---- scans (af::accum / scan / scanByKey default dim = 0, src/api/cpp/scan.cpp:15-33) --------------

@@ -90,9 +90,10 @@ af_err reduce_dimwise(af_array *out, const af_array in_h, int dim, Family fam, O
 }
 
 // ---- whole array ---------------------------------------------------------------------------------
-// Runs the reduction into `dst` (device, one element of *to).  Non-linear views with short columns are
-// materialised first so the flattening kernel streams long spans.
-void reduce_all_into(const Array &in, Op eff, af_dtype to, bool change_nan, double nanval, void *dst) {
+// Runs the reduction into `dst` (device, one element of *to; null: the device slot paired with the host record).
+// Non-linear views with short columns are materialised first so the flattening kernel streams long spans.
+// With `ret` the kernel also publishes the value to a pinned host record (no D2H copy / stream synchronisation).
+void reduce_all_into(const Array &in, Op eff, af_dtype to, bool change_nan, double nanval, void *dst, HostRet *ret = nullptr) {
     const Array *src = &in;
     Holder tmp;
     if (!in.is_linear() && in.info.dims[0] < 4096) {
@@ -101,32 +102,34 @@ void reduce_all_into(const Array &in, Op eff, af_dtype to, bool change_nan, doub
     }
     OpLock lk(in.device());
     LaunchCtx c = ctx_for_active_device();
-    if (!launch_reduce_all(c, eff, in.info.type, to, view_of(*src), change_nan, nanval, dst))
+    if (ret) {
+        *ret = c.scratch->next_host_ret();
+        if (!dst) dst = ret->dev;
+    }
+    if (!launch_reduce_all(c, eff, in.info.type, to, view_of(*src), change_nan, nanval, dst, ret))
         AFB_TYPE_ERROR(1, in.info.type);
 }
 
 double identity_of(Op op) { return (op == OP_MUL || op == OP_AND) ? 1.0 : 0.0; }
 
-void read_scalar(af_dtype t, const void *dev, cudaStream_t s, double *real, double *imag) {
-    alignas(16) unsigned char raw[16];
-    AFB_CUDA(cudaMemcpyAsync(raw, dev, dtype_size(t), cudaMemcpyDeviceToHost, s));
-    AFB_CUDA(cudaStreamSynchronize(s));
+// one element of dtype t (host bytes) -> the (real, imag) doubles of the scalar API
+void decode_scalar(af_dtype t, const void *raw, double *real, double *imag) {
     switch (t) {
-        case f32: *real = *(float *)raw; break;
-        case f64: *real = *(double *)raw; break;
-        case c32: *real = ((float *)raw)[0]; if (imag) *imag = ((float *)raw)[1]; break;
-        case c64: *real = ((double *)raw)[0]; if (imag) *imag = ((double *)raw)[1]; break;
-        case s32: *real = *(int *)raw; break;
-        case u32: *real = *(unsigned *)raw; break;
-        case s64: *real = (double)*(long long *)raw; break;
-        case u64: *real = (double)*(unsigned long long *)raw; break;
-        case s16: *real = *(short *)raw; break;
-        case u16: *real = *(unsigned short *)raw; break;
-        case s8: case b8: *real = *(signed char *)raw; break;
-        case u8: *real = *(unsigned char *)raw; break;
+        case f32: *real = *(const float *)raw; break;
+        case f64: *real = *(const double *)raw; break;
+        case c32: *real = ((const float *)raw)[0]; if (imag) *imag = ((const float *)raw)[1]; break;
+        case c64: *real = ((const double *)raw)[0]; if (imag) *imag = ((const double *)raw)[1]; break;
+        case s32: *real = *(const int *)raw; break;
+        case u32: *real = *(const unsigned *)raw; break;
+        case s64: *real = (double)*(const long long *)raw; break;
+        case u64: *real = (double)*(const unsigned long long *)raw; break;
+        case s16: *real = *(const short *)raw; break;
+        case u16: *real = *(const unsigned short *)raw; break;
+        case s8: case b8: *real = *(const signed char *)raw; break;
+        case u8: *real = *(const unsigned char *)raw; break;
         case f16: {
             // IEEE binary16 -> double
-            unsigned short h = *(unsigned short *)raw;
+            unsigned short h = *(const unsigned short *)raw;
             int sign = h >> 15, e = (h >> 10) & 31, m = h & 1023;
             double v;
             if (e == 0) v = std::ldexp((double)m, -24);
@@ -156,11 +159,14 @@ af_err reduce_all_scalar(double *real, double *imag, const af_array in_h, Family
         return AF_SUCCESS;
     }
     check_same_device(*in);
-    Holder res;
-    dim_t one[4] = {1, 1, 1, 1};
-    res.a = new_array(to, one);
-    reduce_all_into(*in, eff, to, change_nan, nanval, res.a->data());
-    read_scalar(to, res.a->data(), stream_of(in->device()), real, imag);
+    // the last CTA of the reduction writes the scalar straight into a pinned host record and raises its flag: the host
+    // spins on the flag instead of paying cudaMemcpyAsync + cudaStreamSynchronize (the reference's getScalar,
+    // src/backend/cuda/copy.cpp:178-184)
+    HostRet ret;
+    reduce_all_into(*in, eff, to, change_nan, nanval, nullptr, &ret);
+    LaunchCtx c = ctx_for_active_device();
+    wait_host_ret(c, ret);
+    decode_scalar(to, ret.host, real, imag);
     AFB_API_END
 }
 
@@ -222,7 +228,7 @@ af_err ireduce_dimwise(af_array *val, af_array *idx, const af_array in_h, int di
     AFB_API_END
 }
 
-void ireduce_all_into(const Array &in, Op op, void *dval, unsigned *dloc) {
+void ireduce_all_into(const Array &in, Op op, void *dval, unsigned *dloc, HostRet *ret = nullptr) {
     const Array *src = &in;
     Holder tmp;
     if (!in.is_linear() && in.info.dims[0] < 4096) {
@@ -231,7 +237,14 @@ void ireduce_all_into(const Array &in, Op op, void *dval, unsigned *dloc) {
     }
     OpLock lk(in.device());
     LaunchCtx c = ctx_for_active_device();
-    if (!launch_ireduce_all(c, op, in.info.type, view_of(*src), dval, dloc)) AFB_TYPE_ERROR(1, in.info.type);
+    if (ret) {
+        *ret = c.scratch->next_host_ret();
+        if (!dval) {   // device copy goes to the slot paired with the record: value at +0, index at +32
+            dval = ret->dev;
+            dloc = (unsigned *)((char *)ret->dev + 32);
+        }
+    }
+    if (!launch_ireduce_all(c, op, in.info.type, view_of(*src), dval, dloc, ret)) AFB_TYPE_ERROR(1, in.info.type);
 }
 
 af_err ireduce_all_scalar(double *real, double *imag, unsigned *loc, const af_array in_h, Op op) {
@@ -246,14 +259,12 @@ af_err ireduce_all_scalar(double *real, double *imag, unsigned *loc, const af_ar
     if (t == f16) AFB_TYPE_ERROR(1, t);  // no f16 case in the reference (reduce.cpp:1095-1131)
     if (t == c32 || t == c64) AFB_ARG(1, imag != nullptr);
     check_same_device(*in);
-    Holder res, l;
-    dim_t one[4] = {1, 1, 1, 1};
-    res.a = new_array(t, one);
-    l.a = new_array(u32, one);
-    ireduce_all_into(*in, op, res.a->data(), (unsigned *)l.a->data());
-    cudaStream_t s = stream_of(in->device());
-    AFB_CUDA(cudaMemcpyAsync(loc, l.a->data(), 4, cudaMemcpyDeviceToHost, s));
-    read_scalar(t, res.a->data(), s, real, imag);  // synchronises
+    HostRet ret;
+    ireduce_all_into(*in, op, nullptr, nullptr, &ret);
+    LaunchCtx c = ctx_for_active_device();
+    wait_host_ret(c, ret);
+    decode_scalar(t, ret.host, real, imag);
+    *loc = *(const unsigned *)((const char *)ret.host + 32);
     AFB_API_END
 }
 
@@ -352,8 +363,11 @@ Array *where_launch(const Array &in, unsigned base, unsigned long long **d_count
     big.a = new_array(u32, cap);
     OpLock lk(in.device());
     LaunchCtx c = ctx_for_active_device();
-    unsigned long long *d_count = (unsigned long long *)c.scratch->dev_scalar;
-    if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), d_count, base)) AFB_TYPE_ERROR(1, t);
+    // every launch owns one slot of the 64-entry ring: a later where() on this device cannot overwrite the count before
+    // the caller's gather has consumed it (at most 63 launches may be outstanding)
+    HostRet ret = c.scratch->next_host_ret();
+    unsigned long long *d_count = (unsigned long long *)ret.dev;
+    if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), d_count, base, nullptr)) AFB_TYPE_ERROR(1, t);
     *d_count_out = d_count;
     return big.release();
 }
@@ -398,12 +412,17 @@ Array *where_impl(const Array &in, unsigned base, dim_t *count_out) {
     big.a = new_array(u32, cap);
     unsigned long long h_count = 0;
     {
-        OpLock lk(in.device());
-        LaunchCtx c = ctx_for_active_device();
-        unsigned long long *d_count = (unsigned long long *)c.scratch->dev_scalar;
-        if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), d_count, base)) AFB_TYPE_ERROR(1, t);
-        AFB_CUDA(cudaMemcpyAsync(&h_count, d_count, 8, cudaMemcpyDeviceToHost, c.stream));
-        AFB_CUDA(cudaStreamSynchronize(c.stream));
+        HostRet ret;
+        LaunchCtx c;
+        {
+            OpLock lk(in.device());
+            c = ctx_for_active_device();
+            ret = c.scratch->next_host_ret();
+            if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), (unsigned long long *)ret.dev, base, &ret))
+                AFB_TYPE_ERROR(1, t);
+        }
+        wait_host_ret(c, ret);   // the kernel's last tile wrote the count into the pinned record
+        h_count = *(const unsigned long long *)ret.host;
     }
     if (count_out) *count_out = (dim_t)h_count;
     const char *e = getenv("AFB200_WHERE_SHRINK_DIV");

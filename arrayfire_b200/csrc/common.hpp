@@ -164,14 +164,32 @@ struct LaunchCtx {
 };
 LaunchCtx ctx_for_active_device();
 
+// A scalar coming back from a kernel WITHOUT cudaMemcpyAsync + cudaStreamSynchronize: the kernel's last thread stores the
+// payload (<= 48 bytes) into a pinned, device-mapped 64-byte record, fences to system scope and raises the record's flag
+// to `seq`; the host spins on the flag (wait_host_ret).  `dev` is a 64-byte device slot paired with the record for
+// kernels that also keep the value on the device (the hit count of af_where).  Records come from a small ring
+// (Scratch::next_host_ret, under the device's op mutex); `seq` is monotone per device and never 0.
+struct HostRet {
+    void *host;        // pinned payload, as seen by host AND device (UVA)
+    unsigned *flag;    // pinned
+    unsigned seq;
+    void *dev;         // device slot
+};
+void wait_host_ret(const LaunchCtx &c, const HostRet &r);   // spins; surfaces kernel failures as af_err instead of hanging
+
 // out: dense array with dims = in.dims but dims[dim] = 1.  Returns false if (op,ti,to) is not instantiated.
 bool launch_reduce(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool change_nan,
                    double nanval, void *out);
 // out: device pointer to ONE element of `to`
+// `ret` (optional): the result is ALSO published to the pinned record (value at host+0, index at host+32)
 bool launch_reduce_all(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, bool change_nan,
-                       double nanval, void *out);
+                       double nanval, void *out, const HostRet *ret = nullptr);
 bool launch_ireduce(const LaunchCtx &c, Op op, af_dtype t, const View &in, int dim, void *out_val, unsigned *out_loc);
-bool launch_ireduce_all(const LaunchCtx &c, Op op, af_dtype t, const View &in, void *out_val, unsigned *out_loc);
+bool launch_ireduce_all(const LaunchCtx &c, Op op, af_dtype t, const View &in, void *out_val, unsigned *out_loc,
+                        const HostRet *ret = nullptr);
+// af_max_ragged: like launch_ireduce(OP_MAX) but line j only looks at its first min(len, rlen[j]) elements
+bool launch_ireduce_ragged(const LaunchCtx &c, Op op, af_dtype t, const View &in, int dim, const unsigned *rlen,
+                           void *out_val, unsigned *out_loc);
 // carry / carry_key: optional device pointers (sharded scans); out is dense with in.dims
 bool launch_scan(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool inclusive,
                  void *out, const void *carry);
@@ -180,8 +198,17 @@ bool launch_scan_by_key(const LaunchCtx &c, Op op, af_dtype t, af_dtype tk, cons
 // out[i] = op(*carry_host, out[i]) for i < count, in place (cross-shard fix-up of a by-key scan)
 bool launch_scan_fixup(const LaunchCtx &c, Op op, af_dtype t, void *out, dim_t count, const void *carry_host);
 // writes hit indices (+base) to `out` (capacity = elements) and the count to *d_count (device, 8 bytes)
+// `ret` (optional): the count is also published to the pinned record (u64 at host+0)
 bool launch_where(const LaunchCtx &c, af_dtype t, const View &in, unsigned *out, unsigned long long *d_count,
-                  unsigned base);
+                  unsigned base, const HostRet *ret = nullptr);
+// ---- reductions by key (kernels/rbk_*.cu): keys = n dense 32-bit keys, runs of equal consecutive keys are segments
+// pass 1: number of runs -> published through `ret` (u64); tile_base[t] (device, ntiles + 1 words) = runs starting before tile t
+dim_t rbk_tile_elems();
+void launch_rbk_count(const LaunchCtx &c, const void *keys, dim_t n, unsigned *tile_base, const HostRet &ret);
+// pass 2: vals reduced per run along `dim` into vals_out (dense, dims[dim] = n_reduced); keys_out (may be null) gets one key per run
+bool launch_rbk_reduce(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const void *keys, dim_t n, const View &vals,
+                       int dim, bool change_nan, double nanval, const unsigned *tile_base, void *keys_out, void *vals_out,
+                       dim_t n_reduced);
 // all-gather of one 64-byte record per rank over peer-mapped symmetric buffers; the world x 64 bytes land in pinned
 // host memory at host_out and *host_flag becomes `epoch` (kernels/peer.cu)
 void launch_peer_exchange(const LaunchCtx &c, const void *payload, const unsigned long long *bufs, int rank, int world,
@@ -204,8 +231,10 @@ struct Scratch {
     unsigned long long *chain_ticket = nullptr;                 // monotone 64-bit ticket of the persistent chained kernels
     unsigned long long chain_base = 0;                          // host mirror: its value once all enqueued launches are done
     unsigned epoch = 0, wepoch = 0;                             // generation tags of the two descriptor arrays
-    void *host_pinned = nullptr;   size_t host_pinned_bytes = 0;  // D2H landing zone for scalars
-    void *dev_scalar = nullptr;                                 // 64-byte device scalar slot(s)
+    void *host_pinned = nullptr;   size_t host_pinned_bytes = 0;  // pinned: [0,4096) peer exchange, [4096,8192) HostRet ring
+    void *dev_scalar = nullptr;                                 // 64 device slots of 64 bytes (paired with the HostRet ring)
+    unsigned ret_seq = 0;                                       // last HostRet sequence number handed out
+    HostRet next_host_ret();                                    // call under the device's op mutex
 
     void *need_partials(size_t bytes);
     unsigned *need_tickets(size_t count);

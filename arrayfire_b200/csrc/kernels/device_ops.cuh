@@ -272,6 +272,18 @@ AFB_DI uint ld_relaxed(const uint *p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// system-scope release / acquire: flags read by the host (pinned memory) or by peer GPUs (NVLink-mapped memory)
+AFB_DI void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+AFB_DI unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// raise the flag of a pinned host record after its payload has been stored by THIS thread (common.hpp: HostRet)
+AFB_DI void host_ret_publish(unsigned *flag, unsigned seq) {
+    __threadfence_system();
+    st_release_sys(flag, seq);
+}
 AFB_DI unsigned long long ld_relaxed64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

@@ -28,13 +28,6 @@ struct PeerArgs {
     unsigned *host_flag;                 // pinned host
 };
 
-AFB_DI void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-AFB_DI unsigned ld_acquire_sys(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __global__ void __launch_bounds__(64) peer_exchange_kernel(const PeerArgs a) {
     const int t = threadIdx.x;
     const int par = (int)(a.epoch & 1u);

@@ -1,0 +1,437 @@
+// rbk_kernels.cuh -- reductions BY KEY (af_sum_by_key, af_min_by_key, ... SURVEY.md section 8(f)-1).
+//
+// Semantics (/root/reference/src/backend/cpu/kernel/reduce.hpp:64-160, src/backend/cpu/reduce.cpp:73-108): `keys` is a
+// vector of n 32-bit keys, runs of EQUAL CONSECUTIVE keys are segments (keys need not be sorted); every line of `vals`
+// along `dim` (n elements) is reduced per segment; keys_out holds one key per run, vals_out has dims[dim] = #runs.
+//
+// What it replaces: the reference CUDA backend loops on the HOST -- per round a block reduce, a cub::DeviceScan, a
+// compaction and a D2H read of a "needs another round" flag (src/backend/cuda/reduce_impl.hpp:88-180,
+// kernel/reduce_by_key.hpp:33-621).  Here:
+//   pass 1  rbk_count_kernel   one streaming pass over the KEYS: runs per 2048-key tile; the last CTA to arrive (ticket)
+//                              turns the counts into exclusive tile bases and publishes the total to a pinned host record
+//                              (the host needs it to size the outputs -- the one unavoidable host round trip).
+//   pass 2  rbk_tile_kernel    dim 0: one CTA per (tile, column): blocked loads, a segmented scan in registers / shuffles,
+//                              every run TAIL writes its reduction straight to out[tile_base + local run index]; heads
+//                              write keys_out.  Only the run that enters a tile from the left is incomplete: its partial is
+//                              written anyway and the tile's (value, has-head) aggregate goes to a side array ...
+//   pass 3  rbk_fixup_kernel   ... which one CTA per column scans (segmented, in tile order) to add the carried-in part to
+//                              the first output of each tile.  Deterministic: no atomics on values, fixed fold order.
+//           rbk_dim_kernel     dim > 0: lanes along the contiguous dim 0, every thread walks its line serially.
+// Traffic (dim 0): keys twice + values once + outputs; the reference's loop re-reads keys and values every round.
+#pragma once
+
+#include "scan_kernels.cuh"
+
+namespace afb {
+
+constexpr int kRbkThreads = 256;
+constexpr int kRbkEPT = 8;                               // consecutive elements per thread
+constexpr int kRbkTile = kRbkThreads * kRbkEPT;          // 2048 keys per tile
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: runs per tile, exclusive bases, total
+// ------------------------------------------------------------------------------------------------
+struct RbkCountArgs {
+    const uint *keys;
+    dim_t n, ntiles;
+    uint *tile_base;                 // [ntiles + 1]
+    uint *ticket;                    // self-resetting arrival counter
+    unsigned long long *host_total;  // pinned record (common.hpp HostRet)
+    uint *host_flag;
+    uint host_seq;
+};
+
+// heads among the EPT keys starting at p0 (bit k: key p0+k starts a run); keys past n never do
+AFB_DI uint rbk_heads(const uint *__restrict__ keys, dim_t n, dim_t p0, uint (&k)[kRbkEPT]) {
+    if (p0 >= n) return 0u;
+    const int nv = (n - p0) >= kRbkEPT ? kRbkEPT : (int)(n - p0);
+    if (nv == kRbkEPT && ((reinterpret_cast<uintptr_t>(keys + p0) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < kRbkEPT / 4; j++) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(keys + p0) + j);
+            k[4 * j] = q.x; k[4 * j + 1] = q.y; k[4 * j + 2] = q.z; k[4 * j + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kRbkEPT; j++) k[j] = (j < nv) ? __ldg(keys + p0 + j) : 0u;
+    }
+    uint hb = 0u;
+    const bool first = (p0 == 0) || (__ldg(keys + p0 - 1) != k[0]);
+    hb |= first ? 1u : 0u;
+#pragma unroll
+    for (int j = 1; j < kRbkEPT; j++) hb |= (k[j] != k[j - 1] ? 1u : 0u) << j;
+    return nv == kRbkEPT ? hb : (hb & ((1u << nv) - 1u));
+}
+
+static __global__ void __launch_bounds__(kRbkThreads) rbk_count_kernel(const RbkCountArgs a) {
+    __shared__ uint sm[kRbkThreads / 32];
+    __shared__ int sm_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (dim_t t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        uint k[kRbkEPT];
+        uint c = __popc(rbk_heads(a.keys, a.n, t * kRbkTile + (dim_t)tid * kRbkEPT, k));
+        c = __reduce_add_sync(0xffffffffu, c);
+        __syncthreads();
+        if (lane == 0) sm[warp] = c;
+        __syncthreads();
+        if (tid == 0) {
+            uint s = 0;
+#pragma unroll
+            for (int w = 0; w < kRbkThreads / 32; w++) s += sm[w];
+            a.tile_base[t] = s;
+        }
+    }
+    // ---- the last CTA to arrive scans the counts in place
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const uint arrived = atomicAdd(a.ticket, 1u);
+        sm_last = (arrived == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!sm_last) return;
+    __threadfence();
+    const dim_t per = (a.ntiles + kRbkThreads - 1) / kRbkThreads;
+    const dim_t lo = (dim_t)tid * per, hi = min(lo + per, a.ntiles);
+    uint sum = 0;
+    for (dim_t i = lo; i < hi; i++) sum += __ldcg(a.tile_base + i);
+    uint inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    __syncthreads();
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    uint before = inc - sum;
+#pragma unroll
+    for (int w = 0; w < kRbkThreads / 32; w++)
+        if (w < warp) before += sm[w];
+    uint run = before;
+    for (dim_t i = lo; i < hi; i++) {
+        const uint c = __ldcg(a.tile_base + i);
+        a.tile_base[i] = run;
+        run += c;
+    }
+    if (tid == kRbkThreads - 1) {
+        a.tile_base[a.ntiles] = run;   // per >= 1 element for the low threads; the last thread's `run` is the total
+        *a.ticket = 0u;
+        *a.host_total = (unsigned long long)run;
+        host_ret_publish(a.host_flag, a.host_seq);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2 (dim 0): per (tile, column) segmented reduction
+// ------------------------------------------------------------------------------------------------
+template<typename Ti, typename To, typename Acc>
+struct RbkArgs {
+    const uint *keys;
+    dim_t n, ntiles;
+    const Ti *vals;
+    ColGeom g;                      // columns of `vals` (g.len == n)
+    const uint *tile_base;
+    uint *keys_out;                 // may be null
+    To *vals_out;                   // column c starts at c * n_reduced
+    dim_t n_reduced;
+    Slot<Seg<Acc>> *tile_agg;       // [ncols * ntiles]
+    ValParams prm;
+};
+
+template<int OP, typename Ti, typename To>
+__global__ void __launch_bounds__(kRbkThreads) rbk_tile_kernel(const RbkArgs<Ti, To, typename compute_of<To>::type> a) {
+    typedef typename compute_of<To>::type Acc;
+    typedef Rule<OP, Ti, Acc> R;
+    typedef SOps<R, Acc, true> S;
+    typedef typename S::State State;
+    constexpr int EPT = kRbkEPT, NW = kRbkThreads / 32;
+    __shared__ State sm_w[NW];
+    __shared__ uint sm_h[NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const dim_t nwork = a.ntiles * a.g.ncols;
+    for (dim_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const dim_t t = w % a.ntiles, c = w / a.ntiles;
+        const dim_t p0 = t * kRbkTile + (dim_t)tid * EPT;
+        uint k[EPT];
+        const uint hb = rbk_heads(a.keys, a.n, p0, k);
+        const int nv = p0 >= a.n ? 0 : ((a.n - p0) >= EPT ? EPT : (int)(a.n - p0));
+        // is the element after this thread's last one a head (or the end of the line)?
+        bool next_head = true;
+        if (p0 + EPT < a.n) next_head = __ldg(a.keys + p0 + EPT) != k[EPT - 1];
+        const Ti *col = a.vals + col_offset(a.g, c);
+        Acc x[EPT];
+        Acc run = R::init();
+        Ti raw[EPT];
+        constexpr size_t kAlign = sizeof(Ti) * EPT >= 16 ? 16 : sizeof(Ti) * EPT;
+        const bool vec = nv == EPT && (reinterpret_cast<uintptr_t>(col + p0) % kAlign) == 0;
+        if (vec) load_elems<Ti, EPT>(col + p0, raw);
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+            Acc v = R::init();
+            if (j < nv) {
+                v = R::pre(vec ? raw[j] : ldg_stream<Ti>(col + p0 + j));
+                if (a.prm.change_nan) v = nan_swap<Acc>(v, a.prm.nanval);
+            }
+            // a run's first element is taken as is (the reference seeds the accumulator with it, reduce.hpp:146-151)
+            run = (j == 0 || ((hb >> j) & 1u)) ? v : R::join(run, v);
+            x[j] = run;
+        }
+        State inc = State{run, hb != 0u ? 1 : 0};
+        uint hinc = __popc(hb);
+        const uint hc = hinc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const State o = shfl_up(inc, d);
+            const uint ho = __shfl_up_sync(0xffffffffu, hinc, d);
+            if (lane >= d) {
+                inc = S::join(o, inc);
+                hinc += ho;
+            }
+        }
+        State exc = shfl_up(inc, 1);
+        if (lane == 0) exc = S::identity();
+        __syncthreads();   // protects sm_* against the previous work item
+        if (lane == 31) {
+            sm_w[warp] = inc;
+            sm_h[warp] = hinc;
+        }
+        __syncthreads();
+        State before = S::identity();
+        uint hbefore = hinc - hc;
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            if (q < warp) {
+                before = S::join(before, sm_w[q]);
+                hbefore += sm_h[q];
+            }
+        }
+        const State prefix = S::join(before, exc);   // the tile's elements in front of this thread
+        const uint base = __ldg(a.tile_base + t);
+        To *out = a.vals_out + c * a.n_reduced;
+#pragma unroll
+        for (int j = 0; j < EPT; j++) {
+            if (j < nv) {
+                const uint upto = hb & ((2u << j) - 1u);              // heads among this thread's elements 0..j
+                const uint seg = base + hbefore + __popc(upto) - 1u;  // (base - 1: the run that entered the tile from the left)
+                const bool head = (hb >> j) & 1u;
+                const bool tail = (j + 1 < nv) ? ((hb >> (j + 1)) & 1u) : ((p0 + j + 1 >= a.n) || (j + 1 == EPT && next_head));
+                if (head && c == 0 && a.keys_out) a.keys_out[seg] = k[j];
+                if (tail) out[seg] = conv<To, Acc>(upto == 0u ? R::join(prefix.val, x[j]) : x[j]);
+            }
+        }
+        if (tid == kRbkThreads - 1) a.tile_agg[c * a.ntiles + t].v = S::join(prefix, State{run, hb != 0u ? 1 : 0});
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 3 (dim 0): add what a run accumulated in earlier tiles to the tile that holds its tail
+// ------------------------------------------------------------------------------------------------
+template<int OP, typename To>
+__global__ void __launch_bounds__(kRbkThreads) rbk_fixup_kernel(const uint *__restrict__ keys, dim_t ntiles,
+                                                                 const uint *__restrict__ tile_base,
+                                                                 const Slot<Seg<typename compute_of<To>::type>> *__restrict__ tile_agg,
+                                                                 To *vals_out, dim_t n_reduced) {
+    typedef typename compute_of<To>::type Acc;
+    typedef Rule<OP, To, Acc> R;
+    typedef SOps<R, Acc, true> S;
+    typedef typename S::State State;
+    constexpr int NW = kRbkThreads / 32;
+    __shared__ State sm_w[NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const dim_t c = blockIdx.x;
+    const Slot<State> *agg = tile_agg + c * ntiles;
+    To *out = vals_out + c * n_reduced;
+    const dim_t per = (ntiles + kRbkThreads - 1) / kRbkThreads;
+    const dim_t lo = (dim_t)tid * per, hi = min(lo + per, ntiles);
+    State tot = S::identity();
+    for (dim_t t = lo; t < hi; t++) tot = S::join(tot, agg[t].v);
+    State inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const State o = shfl_up(inc, d);
+        if (lane >= d) inc = S::join(o, inc);
+    }
+    State exc = shfl_up(inc, 1);
+    if (lane == 0) exc = S::identity();
+    if (lane == 31) sm_w[warp] = inc;
+    __syncthreads();
+    State carry = S::identity();
+#pragma unroll
+    for (int q = 0; q < NW; q++)
+        if (q < warp) carry = S::join(carry, sm_w[q]);
+    carry = S::join(carry, exc);
+    for (dim_t t = lo; t < hi; t++) {
+        if (t > 0) {
+            const dim_t p = t * kRbkTile;
+            const bool starts_run = __ldg(keys + p) != __ldg(keys + p - 1);
+            const uint b = __ldg(tile_base + t), heads = __ldg(tile_base + t + 1) - b;
+            // the run entering from the left ends in this tile iff the tile has a head or is the last one
+            if (!starts_run && (heads > 0u || t == ntiles - 1)) {
+                To *o = out + (b - 1u);
+                *o = conv<To, Acc>(R::join(carry.val, conv<Acc, To>(*o)));
+            }
+        }
+        carry = S::join(carry, agg[t].v);
+    }
+}
+
+// keys_out for the dim > 0 path: one key per run, positions from the tile bases
+static __global__ void __launch_bounds__(kRbkThreads) rbk_keys_out_kernel(const uint *__restrict__ keys, dim_t n, dim_t ntiles,
+                                                                    const uint *__restrict__ tile_base, uint *keys_out) {
+    __shared__ uint sm_h[kRbkThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (dim_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        uint k[kRbkEPT];
+        const uint hb = rbk_heads(keys, n, t * kRbkTile + (dim_t)tid * kRbkEPT, k);
+        const uint hc = __popc(hb);
+        uint hinc = hc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint o = __shfl_up_sync(0xffffffffu, hinc, d);
+            if (lane >= d) hinc += o;
+        }
+        __syncthreads();
+        if (lane == 31) sm_h[warp] = hinc;
+        __syncthreads();
+        uint pos = __ldg(tile_base + t) + hinc - hc;
+#pragma unroll
+        for (int q = 0; q < kRbkThreads / 32; q++)
+            if (q < warp) pos += sm_h[q];
+#pragma unroll
+        for (int j = 0; j < kRbkEPT; j++)
+            if ((hb >> j) & 1u) keys_out[pos++] = k[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dim > 0: one thread per line, lanes along the contiguous dim 0
+// ------------------------------------------------------------------------------------------------
+template<typename Ti, typename To>
+struct RbkDimArgs {
+    const uint *keys;
+    const Ti *vals;
+    To *vals_out;
+    DimGeom g;          // len = n, sd = input stride of the reduced dim; oa / ob = output strides of the batch dims
+    dim_t od;           // output stride of the reduced dim
+    ValParams prm;
+};
+
+template<int OP, typename Ti, typename To>
+__global__ void __launch_bounds__(256) rbk_dim_kernel(const RbkDimArgs<Ti, To> a) {
+    typedef typename compute_of<To>::type Acc;
+    typedef Rule<OP, Ti, Acc> R;
+    const dim_t x0 = (dim_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x0 >= a.g.d0) return;
+    for (dim_t batch = blockIdx.y; batch < a.g.na * a.g.nb; batch += gridDim.y) {
+        const dim_t ia = batch % a.g.na, ib = batch / a.g.na;
+        const Ti *in = a.vals + ia * a.g.sa + ib * a.g.sb + x0;
+        To *out = a.vals_out + ia * a.g.oa + ib * a.g.ob + x0;
+        Acc acc = R::init();
+        uint prev = 0;
+        dim_t seg = 0;
+        for (dim_t i = 0; i < a.g.len; i++) {
+            const uint key = __ldg(a.keys + i);
+            Acc v = R::pre(ldg_stream<Ti>(in + i * a.g.sd));
+            if (a.prm.change_nan) v = nan_swap<Acc>(v, a.prm.nanval);
+            if (i == 0) {
+                acc = v;
+            } else if (key != prev) {
+                out[seg * a.od] = conv<To, Acc>(acc);
+                seg++;
+                acc = v;
+            } else {
+                acc = R::join(acc, v);
+            }
+            prev = key;
+        }
+        if (a.g.len > 0) out[seg * a.od] = conv<To, Acc>(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template<int OP, typename Ti, typename To>
+void run_rbk(const LaunchCtx &c, const void *keys, dim_t n, const View &vals, int dim, bool change_nan, double nanval,
+             const unsigned *tile_base, void *keys_out, void *vals_out, dim_t n_reduced) {
+    typedef typename compute_of<To>::type Acc;
+    const dim_t ntiles = (n + kRbkTile - 1) / kRbkTile;
+    ValParams prm;
+    prm.change_nan = change_nan ? 1 : 0;
+    prm.nanval = nanval;
+    if (dim == 0) {
+        RbkArgs<Ti, To, Acc> a;
+        a.keys = (const uint *)keys;
+        a.n = n;
+        a.ntiles = ntiles;
+        a.vals = (const Ti *)vals.ptr;
+        a.g = col_geom(vals);
+        a.tile_base = tile_base;
+        a.keys_out = (uint *)keys_out;
+        a.vals_out = (To *)vals_out;
+        a.n_reduced = n_reduced;
+        a.prm = prm;
+        if (a.g.ncols == 0) return;
+        a.tile_agg = (Slot<Seg<Acc>> *)c.scratch->need_partials((size_t)ntiles * a.g.ncols * sizeof(Slot<Seg<Acc>>));
+        dim_t grid = ntiles * a.g.ncols;
+        const dim_t cap = (dim_t)c.sms * 32;
+        if (grid > cap) grid = cap;
+        rbk_tile_kernel<OP, Ti, To><<<(unsigned)grid, kRbkThreads, 0, c.stream>>>(a);
+        post_launch_check("rbk_tile_kernel");
+        if (a.g.ncols > 0x7fffffffLL) fail(AF_ERR_SIZE, "reduce by key: too many columns");
+        rbk_fixup_kernel<OP, To><<<(unsigned)a.g.ncols, kRbkThreads, 0, c.stream>>>((const uint *)keys, ntiles, tile_base,
+                                                                                    a.tile_agg, (To *)vals_out, n_reduced);
+        post_launch_check("rbk_fixup_kernel");
+        note_launches(2);
+        return;
+    }
+    if (keys_out) {
+        dim_t grid = ntiles;
+        const dim_t cap = (dim_t)c.sms * 16;
+        if (grid > cap) grid = cap;
+        rbk_keys_out_kernel<<<(unsigned)grid, kRbkThreads, 0, c.stream>>>((const uint *)keys, n, ntiles, tile_base, (uint *)keys_out);
+        post_launch_check("rbk_keys_out_kernel");
+        note_launches(1);
+    }
+    RbkDimArgs<Ti, To> a;
+    a.keys = (const uint *)keys;
+    a.vals = (const Ti *)vals.ptr;
+    a.vals_out = (To *)vals_out;
+    DimGeom &g = a.g;
+    g.d0 = vals.dims[0];
+    g.len = n;
+    g.sd = vals.strides[dim];
+    int others[2], m = 0;
+    for (int i = 1; i < 4; i++)
+        if (i != dim) others[m++] = i;
+    g.na = vals.dims[others[0]];
+    g.sa = vals.strides[others[0]];
+    g.nb = vals.dims[others[1]];
+    g.sb = vals.strides[others[1]];
+    dim_t od[4] = {vals.dims[0], vals.dims[1], vals.dims[2], vals.dims[3]}, os[4];
+    od[dim] = n_reduced;
+    dense_strides(od, os);
+    g.oa = os[others[0]];
+    g.ob = os[others[1]];
+    a.od = os[dim];
+    a.prm = prm;
+    if (g.d0 == 0 || g.na * g.nb == 0) return;
+    dim_t gy = g.na * g.nb;
+    if (gy > 65535) gy = 65535;
+    const int threads = g.d0 >= 256 ? 256 : (g.d0 >= 128 ? 128 : (g.d0 >= 64 ? 64 : 32));
+    const dim_t gx = (g.d0 + threads - 1) / threads;
+    rbk_dim_kernel<OP, Ti, To><<<dim3((unsigned)gx, (unsigned)gy), threads, 0, c.stream>>>(a);
+    post_launch_check("rbk_dim_kernel");
+    note_launches(1);
+}
+
+// families, one translation unit each (rbk_sum.cu, rbk_minmax.cu, rbk_logic.cu)
+bool rbk_family_sum(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const void *keys, dim_t n, const View &vals, int dim,
+                    bool cn, double nv, const unsigned *tile_base, void *keys_out, void *vals_out, dim_t n_reduced);
+bool rbk_family_minmax(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const void *keys, dim_t n, const View &vals, int dim,
+                       bool cn, double nv, const unsigned *tile_base, void *keys_out, void *vals_out, dim_t n_reduced);
+bool rbk_family_logic(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const void *keys, dim_t n, const View &vals, int dim,
+                      bool cn, double nv, const unsigned *tile_base, void *keys_out, void *vals_out, dim_t n_reduced);
+
+}  // namespace afb

@@ -110,6 +110,9 @@ void run_cols(const LaunchCtx &c, const View &in, const typename P::Params &prm,
     a.out = out;
     a.partials = nullptr;
     a.tickets = nullptr;
+    a.host_flag = nullptr;
+    a.host_seq = 0;
+    a.host_out = out;
     if (bpc / csize > 1) {
         a.partials = (Slot<Acc> *)c.scratch->need_partials((size_t)g.ncols * (bpc / csize) * sizeof(Slot<Acc>));
         a.tickets = c.scratch->need_tickets((size_t)g.ncols);
@@ -128,7 +131,8 @@ void run_cols(const LaunchCtx &c, const View &in, const typename P::Params &prm,
 // `in` must be a linear view (the API layer materialises non-linear views with small dim 0 first) or a
 // strided view with long columns.
 template<typename P>
-void run_all(const LaunchCtx &c, const View &in, const typename P::Params &prm, const typename P::Out &out) {
+void run_all(const LaunchCtx &c, const View &in, const typename P::Params &prm, const typename P::Out &out,
+             const HostRet *ret = nullptr) {
     typedef typename P::Acc Acc;
     typedef typename P::In In;
     ColGeom g = col_geom(in);
@@ -169,6 +173,9 @@ void run_all(const LaunchCtx &c, const View &in, const typename P::Params &prm, 
     a.out = out;
     a.partials = (Slot<Acc> *)c.scratch->need_partials((size_t)(grid / csize) * sizeof(Slot<Acc>));
     a.tickets = c.scratch->need_tickets(1);
+    a.host_flag = ret ? ret->flag : nullptr;
+    a.host_seq = ret ? ret->seq : 0u;
+    a.host_out = P::host_out(ret ? ret->host : nullptr);
     if (csize > 1)
         launch_with_cluster(span_kernel<P>, dim3((unsigned)grid), dim3(kThreads), dim3(csize, 1, 1), c.stream, a);
     else

@@ -45,6 +45,7 @@ template<int OP, typename Ti, typename To> struct ValPolicy {
     typedef Rule<OP, Ti, Acc> R;
     typedef ValParams Params;
     struct Out { To *val; };
+    static Out host_out(void *rec) { return Out{(To *)rec}; }
     AFB_DI static Acc init() { return R::init(); }
     AFB_DI static Acc load(const Params &p, In x, uint) {
         Acc v = R::pre(x);
@@ -97,6 +98,7 @@ template<int OP, typename T> struct ArgPolicy {
     typedef Arg<T> Acc;
     typedef ArgParams Params;
     struct Out { T *val; uint *loc; };
+    static Out host_out(void *rec) { return Out{(T *)rec, (uint *)((char *)rec + 32)}; }   // value at +0, index at +32
     // Internally element i carries rank i+1, so that "no candidate yet" (rank 0 for min, UINT_MAX for max)
     // loses every tie against a real element -- distinct values can share an ordering key (b8 compares
     // `v > 0`, 64-bit integers compare as double, complex compares magnitudes).
@@ -172,6 +174,7 @@ template<int OP, typename T> struct FirstPolicy {
     typedef Arg<T> Acc;
     typedef ValParams Params;
     struct Out { T *val; };
+    static Out host_out(void *rec) { return Out{(T *)rec}; }
     AFB_DI static T ident() { return OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(); }
     AFB_DI static Acc init() { return Acc{ident(), 0u}; }
     AFB_DI static Acc load(const Params &, In x, uint idx) { return Acc{is_nan<T>(x) ? ident() : x, idx + 1u}; }
@@ -309,6 +312,11 @@ struct SpanArgs {
     typename P::Out out;
     Slot<typename P::Acc> *partials;   // [ncols * bpc / csize]  or  [gridDim.x / csize] in "all" mode
     uint *tickets;               // [ncols] or [1]
+    // "all" mode, optional: the final value also goes to a pinned host record and its flag is raised (no D2H copy, no
+    // stream synchronisation on the host side: common.hpp HostRet)
+    typename P::Out host_out;
+    uint *host_flag;
+    uint host_seq;
 };
 
 template<typename P>
@@ -358,7 +366,13 @@ __global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
 
     // ---- level 3: one partial per (cluster of) CTA(s); the last arriver folds them in index order
     if (nparts == 1) {
-        if (tid == 0) P::store(a.out, (size_t)col, acc);
+        if (tid == 0) {
+            P::store(a.out, (size_t)col, acc);
+            if (a.host_flag) {
+                P::store(a.host_out, 0, acc);
+                host_ret_publish(a.host_flag, a.host_seq);
+            }
+        }
         return;
     }
     Slot<Acc> *slots = a.partials + (a.all ? 0 : (size_t)col * nparts);
@@ -378,6 +392,10 @@ __global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
     if (tid == 0) {
         P::store(a.out, (size_t)col, fin);
         *ticket = 0u;  // self-reset: the next launch on this stream finds it clean
+        if (a.host_flag) {
+            P::store(a.host_out, 0, fin);
+            host_ret_publish(a.host_flag, a.host_seq);
+        }
     }
 }
 

@@ -25,7 +25,19 @@ struct WhereArgs {
     uint epoch;
     uint base;                     // added to every index (sharded where)
     int vec_ok;
+    unsigned long long *host_total;   // optional pinned copy of the count + flag (common.hpp HostRet)
+    uint *host_flag;
+    uint host_seq;
 };
+
+// the total goes to device memory and, when asked for, to the pinned host record (one thread calls this)
+template<typename A> AFB_DI void where_publish_total(const A &a, unsigned long long total) {
+    *a.total = total;
+    if (a.host_flag) {
+        *a.host_total = total;
+        host_ret_publish(a.host_flag, a.host_seq);
+    }
+}
 
 template<typename T>
 __global__ void __launch_bounds__(kScanThreads) where_kernel(const WhereArgs<T> a) {
@@ -116,7 +128,7 @@ __global__ void __launch_bounds__(kScanThreads) where_kernel(const WhereArgs<T> 
         }
         if (lane == 0) {
             sm_prefix = excl;
-            if (tile == a.ntiles - 1) *a.total = (unsigned long long)excl + tile_total;
+            if (tile == a.ntiles - 1) where_publish_total(a, (unsigned long long)excl + tile_total);
         }
     }
     __syncthreads();
@@ -137,7 +149,8 @@ __global__ void __launch_bounds__(kScanThreads) where_kernel(const WhereArgs<T> 
 }
 
 template<typename T>
-static void run_where_simple(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base) {
+static void run_where_simple(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base,
+                             const HostRet *ret) {
     WhereArgs<T> a;
     a.in = (const T *)in.ptr;
     a.n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
@@ -151,6 +164,9 @@ static void run_where_simple(const LaunchCtx &c, const View &in, uint *out, unsi
     a.tile_counter = c.scratch->tile_counter;
     a.base = base;
     a.vec_ok = aligned_to(in.ptr, 16) ? 1 : 0;
+    a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
+    a.host_flag = ret ? ret->flag : nullptr;
+    a.host_seq = ret ? ret->seq : 0u;
     where_kernel<T><<<(unsigned)a.ntiles, kScanThreads, 0, c.stream>>>(a);
     note_launches(1);
     post_launch_check("where_kernel");
@@ -178,7 +194,11 @@ struct ChainWhereArgs {
     unsigned long long *ticket;
     unsigned long long ticket_base;
     unsigned long long *debug;     // optional per-CTA cycle counters of pipe_where_kernel (AFB200_PIPE_DEBUG=1)
+    unsigned long long *host_total;   // optional pinned copy of the count + flag (common.hpp HostRet)
+    uint *host_flag;
+    uint host_seq;
 };
+
 
 // bit k of the result: element k of the 16-byte vector is non-zero
 template<typename T> AFB_DI uint nonzero_mask(const Vec16 &v) {
@@ -358,7 +378,7 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_where_kernel(const Cha
             }
             if (lane == 0) {
                 sm_prefix[pb] = excl;
-                if (tile == a.ntiles - 1) *a.total = (unsigned long long)excl + tile_total;
+                if (tile == a.ntiles - 1) where_publish_total(a, (unsigned long long)excl + tile_total);
             }
         }
         __syncthreads();
@@ -540,7 +560,7 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
             sm_wp[slot][2 * lane] = R + sm_wexc[slot][2 * lane];
             sm_wp[slot][2 * lane + 1] = R + sm_wexc[slot][2 * lane + 1];
             const uint total = sm_total[slot];
-            if (lane == 0 && tile == a.ntiles - 1) *a.total = (unsigned long long)R + total;
+            if (lane == 0 && tile == a.ntiles - 1) where_publish_total(a, (unsigned long long)R + total);
             __syncwarp();
             if (lane == 0) mbar_arrive(&lb_bar[slot]);
             R += total;
@@ -685,7 +705,8 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
 }
 
 template<typename T>
-static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base) {
+static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base,
+                      const HostRet *ret) {
     const dim_t n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
     constexpr dim_t CT = (dim_t)kChainThreads * kCW_U * VecN<T>::value;
     if (aligned_to(in.ptr, 16) && aligned_to(out, 16) && n >= 2 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
@@ -707,6 +728,9 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
         a.gen = c.scratch->next_wepoch(c.stream);
         a.base = base;
+        a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
+        a.host_flag = ret ? ret->flag : nullptr;
+        a.host_seq = ret ? ret->seq : 0u;
         dim_t grid = (dim_t)c.sms;
         if (grid > a.ntiles) grid = a.ntiles;
         a.ticket = c.scratch->chain_ticket;
@@ -754,6 +778,9 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
         a.gen = c.scratch->next_wepoch(c.stream);
         a.base = base;
+        a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
+        a.host_flag = ret ? ret->flag : nullptr;
+        a.host_seq = ret ? ret->seq : 0u;
         int ctas = env_int("AFB200_CHAIN_CTAS_PER_SM", resident[dv]);
         if (ctas > resident[dv]) ctas = resident[dv];
         dim_t grid = (dim_t)c.sms * ctas;
@@ -766,25 +793,25 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         post_launch_check("chain_where_kernel");
         return;
     }
-    run_where_simple<T>(c, in, out, d_count, base);
+    run_where_simple<T>(c, in, out, d_count, base, ret);
 }
 
 bool launch_where(const LaunchCtx &c, af_dtype t, const View &in, unsigned *out, unsigned long long *d_count,
-                  unsigned base) {
+                  unsigned base, const HostRet *ret) {
     switch (t) {
-        case f32: run_where<float>(c, in, out, d_count, base); return true;
-        case f64: run_where<double>(c, in, out, d_count, base); return true;
-        case c32: run_where<cfloat>(c, in, out, d_count, base); return true;
-        case c64: run_where<cdouble>(c, in, out, d_count, base); return true;
-        case s32: run_where<int>(c, in, out, d_count, base); return true;
-        case u32: run_where<uint>(c, in, out, d_count, base); return true;
-        case s64: run_where<intl>(c, in, out, d_count, base); return true;
-        case u64: run_where<uintl>(c, in, out, d_count, base); return true;
-        case s16: run_where<short>(c, in, out, d_count, base); return true;
-        case u16: run_where<ushort>(c, in, out, d_count, base); return true;
-        case s8: run_where<schar>(c, in, out, d_count, base); return true;
-        case u8: run_where<uchar>(c, in, out, d_count, base); return true;
-        case b8: run_where<b8_t>(c, in, out, d_count, base); return true;
+        case f32: run_where<float>(c, in, out, d_count, base, ret); return true;
+        case f64: run_where<double>(c, in, out, d_count, base, ret); return true;
+        case c32: run_where<cfloat>(c, in, out, d_count, base, ret); return true;
+        case c64: run_where<cdouble>(c, in, out, d_count, base, ret); return true;
+        case s32: run_where<int>(c, in, out, d_count, base, ret); return true;
+        case u32: run_where<uint>(c, in, out, d_count, base, ret); return true;
+        case s64: run_where<intl>(c, in, out, d_count, base, ret); return true;
+        case u64: run_where<uintl>(c, in, out, d_count, base, ret); return true;
+        case s16: run_where<short>(c, in, out, d_count, base, ret); return true;
+        case u16: run_where<ushort>(c, in, out, d_count, base, ret); return true;
+        case s8: run_where<schar>(c, in, out, d_count, base, ret); return true;
+        case u8: run_where<uchar>(c, in, out, d_count, base, ret); return true;
+        case b8: run_where<b8_t>(c, in, out, d_count, base, ret); return true;
         default: return false;
     }
 }

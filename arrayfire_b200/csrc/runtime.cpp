@@ -80,6 +80,7 @@ struct Device {
     Pool pool;
     std::mutex op_mu;
     std::once_flag once;
+    std::once_flag scratch_once;
 };
 
 int g_ndev = -1;
@@ -173,7 +174,7 @@ LaunchCtx ctx_for_active_device() {
     int d = active_device();
     Device &D = dev(d);
     AFB_CUDA(cudaSetDevice(d));
-    D.scratch.ensure_basics();
+    std::call_once(D.scratch_once, [&] { D.scratch.ensure_basics(); });   // callers may race here without the op mutex
     return LaunchCtx{d, D.stream, D.sms, &D.scratch};
 }
 
@@ -366,8 +367,37 @@ void Scratch::ensure_basics() {
     chain_base = 0;
     AFB_CUDA(cudaMalloc(&dev_scalar, 4096));
     AFB_CUDA(cudaMemsetAsync(dev_scalar, 0, 4096, s));
-    AFB_CUDA(cudaMallocHost(&host_pinned, 4096));
-    host_pinned_bytes = 4096;
+    AFB_CUDA(cudaMallocHost(&host_pinned, 8192));
+    memset(host_pinned, 0, 8192);
+    host_pinned_bytes = 8192;
+}
+
+constexpr unsigned kRetSlots = 64;
+
+HostRet Scratch::next_host_ret() {
+    if (++ret_seq == 0) ++ret_seq;
+    const unsigned slot = ret_seq % kRetSlots;
+    unsigned char *rec = (unsigned char *)host_pinned + 4096 + (size_t)slot * 64;
+    HostRet r;
+    r.host = rec;
+    r.flag = (unsigned *)(rec + 60);
+    r.seq = ret_seq;
+    r.dev = (unsigned char *)dev_scalar + (size_t)slot * 64;
+    return r;
+}
+
+void wait_host_ret(const LaunchCtx &c, const HostRet &r) {
+    volatile unsigned *flag = r.flag;
+    unsigned long long spins = 0;
+    while (*flag != r.seq) {
+        if ((++spins & 0x3ffff) == 0) {
+            cudaError_t e = cudaStreamQuery(c.stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) AFB_CUDA(e);
+            if (e == cudaSuccess && *flag != r.seq)
+                fail(AF_ERR_INTERNAL, "a kernel finished without publishing its host result (seq %u, flag %u)", r.seq, *flag);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
 }
 
 void *Scratch::need_wtiles(size_t bytes, cudaStream_t s) {

@@ -62,6 +62,15 @@ typedef enum {
 } af_backend;
 typedef enum { AF_BINARY_ADD = 0, AF_BINARY_MUL = 1, AF_BINARY_MIN = 2, AF_BINARY_MAX = 3 } af_binary_op;
 typedef struct af_seq { double begin, end, step; } af_seq;
+/* include/af/index.h:19-31 */
+typedef struct af_index_t {
+    union {
+        af_array arr;
+        af_seq seq;
+    } idx;
+    bool isSeq;
+    bool isBatch;
+} af_index_t;
 
 /* ===================== hot path: reductions along a dimension ==========================
  * include/af/algorithm.h:708-776,1095-1140; src/api/c/reduce.cpp:461-497 */
@@ -103,6 +112,23 @@ AFAPI af_err af_imax(af_array *out, af_array *idx, const af_array in, const int 
 AFAPI af_err af_imin_all(double *real, double *imag, unsigned *idx, const af_array in);
 AFAPI af_err af_imax_all(double *real, double *imag, unsigned *idx, const af_array in);
 
+/* ===================== next row: reductions by key, ragged max ========
+ * src/api/c/reduce.cpp:500-554, 1076-1078; include/af/algorithm.h:777-1093.  `keys` is a vector of s32 / u32 with
+ * vals.dims[dim] elements; runs of equal consecutive keys are reduced; keys_out gets one key per run. */
+AFAPI af_err af_sum_by_key(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals, const int dim);
+AFAPI af_err af_sum_by_key_nan(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals,
+                               const int dim, const double nanval);
+AFAPI af_err af_product_by_key(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals, const int dim);
+AFAPI af_err af_product_by_key_nan(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals,
+                                   const int dim, const double nanval);
+AFAPI af_err af_min_by_key(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals, const int dim);
+AFAPI af_err af_max_by_key(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals, const int dim);
+AFAPI af_err af_count_by_key(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals, const int dim);
+AFAPI af_err af_all_true_by_key(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals, const int dim);
+AFAPI af_err af_any_true_by_key(af_array *keys_out, af_array *vals_out, const af_array keys, const af_array vals, const int dim);
+/* (value, index) maximum of every line along dim over its first ragged_len[line] elements (u32 lengths) */
+AFAPI af_err af_max_ragged(af_array *val, af_array *idx, const af_array in, const af_array ragged_len, const int dim);
+
 /* ===================== hot path: scans =================================================
  * src/api/c/scan.cpp:118-157 (af_accum), :159-223 (af_scan), :225-283 (af_scan_by_key) */
 AFAPI af_err af_accum(af_array *out, const af_array in, const int dim);
@@ -141,6 +167,36 @@ AFAPI af_err af_constant(af_array *arr, const double val, const unsigned ndims, 
                          const af_dtype type);                                               /* data.cpp:45 */
 AFAPI af_err af_index(af_array *out, const af_array in, const unsigned ndims, const af_seq *const index); /* index.cpp:84 */
 AFAPI af_err af_get_size_of(size_t *size, af_dtype type);
+
+/* ===================== array handling the C++ wrapper needs around the path ============
+ * (src/api/cpp/array.cpp, data.cpp, index.cpp call these; api_extra.cpp) */
+AFAPI af_err af_moddims(af_array *out, const af_array in, const unsigned ndims, const dim_t *const dims); /* moddims.cpp:42 */
+AFAPI af_err af_flat(af_array *out, const af_array in);                                        /* moddims.cpp:84 */
+AFAPI af_err af_cast(af_array *out, const af_array in, const af_dtype type);                   /* cast.cpp:34 */
+/* af_seq / span indexers only (views); array indexers return AF_ERR_NOT_SUPPORTED.  index.cpp:217 */
+AFAPI af_err af_index_gen(af_array *out, const af_array in, const dim_t ndims, const af_index_t *indices);
+AFAPI af_seq af_make_seq(double begin, double end, double step);                               /* seq.h:242 */
+AFAPI af_err af_constant_complex(af_array *arr, const double real, const double imag, const unsigned ndims,
+                                 const dim_t *const dims, const af_dtype type);               /* data.cpp:66 */
+AFAPI af_err af_constant_long(af_array *arr, const long long val, const unsigned ndims, const dim_t *const dims);
+AFAPI af_err af_constant_ulong(af_array *arr, const unsigned long long val, const unsigned ndims, const dim_t *const dims);
+AFAPI af_err af_is_row(bool *result, const af_array arr);                                      /* array.cpp:379-475 */
+AFAPI af_err af_is_column(bool *result, const af_array arr);
+AFAPI af_err af_is_complex(bool *result, const af_array arr);
+AFAPI af_err af_is_real(bool *result, const af_array arr);
+AFAPI af_err af_is_double(bool *result, const af_array arr);
+AFAPI af_err af_is_single(bool *result, const af_array arr);
+AFAPI af_err af_is_half(bool *result, const af_array arr);
+AFAPI af_err af_is_realfloating(bool *result, const af_array arr);
+AFAPI af_err af_is_floating(bool *result, const af_array arr);
+AFAPI af_err af_is_integer(bool *result, const af_array arr);
+AFAPI af_err af_is_bool(bool *result, const af_array arr);
+AFAPI af_err af_is_sparse(bool *result, const af_array arr);
+AFAPI af_err af_get_allocated_bytes(size_t *bytes, const af_array arr);                       /* internal.cpp */
+AFAPI af_err af_eval_multiple(const int num, af_array *arrays);                                /* array.cpp:258 */
+AFAPI af_err af_set_manual_eval_flag(bool flag);
+AFAPI af_err af_get_manual_eval_flag(bool *flag);
+AFAPI af_err af_device_info(char *d_name, char *d_platform, char *d_toolkit, char *d_compute); /* device.cpp:173 */
 
 /* ===================== device / memory / error =========================================
  * src/api/c/device.cpp:57-405, memory.cpp:54-370, error.cpp:19-45, include/af/cuda.h:50-75 */

@@ -268,6 +268,77 @@ void ireduce_everything(const void *vin, const dim_t *dims, const dim_t *strides
     *loc       = t.idx;
 }
 
+template<int OP, typename T>
+void ireduce_ragged_lines(const void *vin, const dim_t *dims, const dim_t *strides, int dim, const uint32_t *rlen,
+                          void *vout, uint32_t *loc) {
+    const T *in = (const T *)vin;
+    T *out      = (T *)vout;
+    if (empty(dims)) return;
+    Shape sh = mk(dims, strides);
+    dim_t od[4] = {dims[0], dims[1], dims[2], dims[3]}, os[4];
+    od[dim] = 1;
+    dense_strides(od, os);
+    const dim_t len = dims[dim], step = strides[dim];
+    for_each_line(sh, os, dim, [&](dim_t ib, dim_t ob) {
+        Tracker<OP, T> t(in[ib], 0);   // element 0 seeds the result even when the ragged length is 0
+        const dim_t lim = std::min<dim_t>(len, (dim_t)rlen[ob]);
+        for (dim_t i = 0; i < lim; i++) t.offer(in[ib + i * step], (uint32_t)i);
+        out[ob] = t.val;
+        loc[ob] = t.idx;
+    });
+}
+
+// ---- reduce by key -----------------------------------------------------------
+// One pass over the keys finds the runs of equal consecutive keys (kernel/reduce.hpp:64-86); every line of `vals`
+// along `dim` is then folded run by run: the first element of a run is taken as is, the others as
+// acc = combine(transform(x_i), acc) (kernel/reduce.hpp:131-158).
+template<typename Tk> long long count_runs(const void *vkeys, dim_t n, void *vkeys_out) {
+    const Tk *keys = (const Tk *)vkeys;
+    Tk *out        = (Tk *)vkeys_out;
+    long long runs = 0;
+    for (dim_t i = 0; i < n; i++) {
+        if (i == 0 || keys[i] != keys[i - 1]) {
+            if (out) out[runs] = keys[i];
+            runs++;
+        }
+    }
+    return runs;
+}
+
+template<int OP, typename Ti, typename To, typename Tk>
+void reduce_by_key_lines(const void *vkeys, const void *vin, const dim_t *dims, const dim_t *strides, int dim,
+                         bool change_nan, double nanval, long long runs, void *vout) {
+    using Tc = compute_t<To>;
+    using R  = Rule<OP, Ti, Tc>;
+    const Tk *keys = (const Tk *)vkeys;
+    const Ti *in   = (const Ti *)vin;
+    To *out        = (To *)vout;
+    if (empty(dims)) return;
+    Shape sh = mk(dims, strides);
+    dim_t od[4] = {dims[0], dims[1], dims[2], dims[3]}, os[4];
+    od[dim] = runs;
+    dense_strides(od, os);
+    const dim_t len = dims[dim], step = strides[dim], ostep = os[dim];
+    for_each_line(sh, os, dim, [&](dim_t ib, dim_t ob) {
+        dim_t seg = 0;
+        Tc acc    = R::init();
+        for (dim_t i = 0; i < len; i++) {
+            Tc v = R::pre(in[ib + i * step]);
+            if (change_nan) v = nan_swap(v, nanval);
+            if (i == 0) {
+                acc = R::join(v, acc);   // the first run starts from init() (reduce.hpp:137,146-148)
+            } else if (keys[i] != keys[i - 1]) {
+                out[ob + seg * ostep] = (To)acc;
+                seg++;
+                acc = v;
+            } else {
+                acc = R::join(v, acc);
+            }
+        }
+        out[ob + seg * ostep] = (To)acc;
+    });
+}
+
 // ---- scan ------------------------------------------------------------------
 template<int OP, typename Ti, typename To>
 void scan_lines(const void *vin, const dim_t *dims, const dim_t *strides, int dim, bool inclusive,
@@ -523,6 +594,64 @@ int orc_scan_by_key(int op, int t, int tk, const void *key, const orc_dim_t kstr
 long long orc_where(int t, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], uint32_t *out) {
 #define X(code, T) if (t == code) return where_hits<T>(in, dims, strides, out);
     FOR_NO_HALF_TYPES(X)
+#undef X
+    return -1;
+}
+
+}  // extern "C"
+
+template<int OP, typename Ti, typename To>
+static long long rbk_key(int tk, const void *keys, const void *vals, const orc_dim_t *dims, const orc_dim_t *strides, int dim,
+                         bool cn, double nv, void *keys_out, void *vals_out) {
+    const orc_dim_t n = dims[dim];
+    long long runs;
+    if (tk == ORC_S32) runs = count_runs<int>(keys, n, keys_out);
+    else if (tk == ORC_U32) runs = count_runs<unsigned>(keys, n, keys_out);
+    else return -1;
+    if (vals_out) {
+        if (tk == ORC_S32) reduce_by_key_lines<OP, Ti, To, int>(keys, vals, dims, strides, dim, cn, nv, runs, vals_out);
+        else reduce_by_key_lines<OP, Ti, To, unsigned>(keys, vals, dims, strides, dim, cn, nv, runs, vals_out);
+    }
+    return runs;
+}
+
+extern "C" {
+
+long long orc_reduce_by_key(int op, int ti, int to, int tk, const void *keys, const void *vals, const orc_dim_t dims[4],
+                            const orc_dim_t strides[4], int dim, int change_nan, double nanval, void *keys_out,
+                            void *vals_out) {
+#define CALL(OP, Ti, To) return rbk_key<OP, Ti, To>(tk, keys, vals, dims, strides, dim, change_nan != 0, nanval, keys_out, vals_out);
+    if (op == ORC_OP_MIN || op == ORC_OP_MAX) {
+#define X(code, T) if (ti == code && to == code) { if (op == ORC_OP_MIN) CALL(ORC_OP_MIN, T, T) else CALL(ORC_OP_MAX, T, T) }
+        FOR_ALL_TYPES(X)
+#undef X
+    } else if (op == ORC_OP_ADD || op == ORC_OP_MUL) {
+#define X(ci, Ti, co, To) if (ti == ci && to == co) { if (op == ORC_OP_ADD) CALL(ORC_OP_ADD, Ti, To) else CALL(ORC_OP_MUL, Ti, To) }
+        FOR_SUM_PAIRS(X)
+#undef X
+    } else if (op == ORC_OP_NOTZERO) {
+#define X(code, T) if (ti == code && to == ORC_U32) CALL(ORC_OP_NOTZERO, T, unsigned)
+        FOR_ALL_TYPES(X)
+#undef X
+    } else if (op == ORC_OP_AND || op == ORC_OP_OR) {
+#define X(code, T) if (ti == code && to == ORC_B8) { if (op == ORC_OP_AND) CALL(ORC_OP_AND, T, b8_t) else CALL(ORC_OP_OR, T, b8_t) }
+        FOR_ALL_TYPES(X)
+#undef X
+    }
+#undef CALL
+    return -1;
+}
+
+int orc_ireduce_ragged(int op, int t, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], int dim,
+                       const uint32_t *rlen, void *out_val, uint32_t *out_loc) {
+    if (op != ORC_OP_MIN && op != ORC_OP_MAX) return -1;
+#define X(code, T)                                                                                          \
+    if (t == code) {                                                                                        \
+        if (op == ORC_OP_MIN) ireduce_ragged_lines<ORC_OP_MIN, T>(in, dims, strides, dim, rlen, out_val, out_loc); \
+        else ireduce_ragged_lines<ORC_OP_MAX, T>(in, dims, strides, dim, rlen, out_val, out_loc);           \
+        return 0;                                                                                           \
+    }
+    FOR_ALL_TYPES(X)
 #undef X
     return -1;
 }

@@ -90,6 +90,19 @@ int ORC_FN(scan_by_key)(int op, int t, int tk, const void *key, const orc_dim_t 
 long long ORC_FN(where)(int t, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4],
                         uint32_t *out);
 
+/* detail::reduce_by_key<op,Ti,Tk,To>(keys_out, vals_out, keys, vals, dim, change_nan, nanval)
+ * (cpu/reduce.cpp:73-108, cpu/kernel/reduce.hpp:64-160).  `keys`: n dense keys of dtype tk (s32 / u32), n == dims[dim].
+ * Returns the number of runs (or -1 for an unsupported triple).  With vals_out == NULL only the count is computed;
+ * otherwise keys_out holds one key per run and vals_out is the dense array with dims[dim] = runs. */
+long long ORC_FN(reduce_by_key)(int op, int ti, int to, int tk, const void *keys, const void *vals,
+                                const orc_dim_t dims[4], const orc_dim_t strides[4], int dim, int change_nan,
+                                double nanval, void *keys_out, void *vals_out);
+
+/* detail::rreduce<op,T>(out, loc, in, dim, rlen) (cpu/ireduce.cpp:47-57, kernel/ireduce.hpp:86-104): ireduce of every line
+ * over its first min(len, rlen[line]) elements; rlen is dense over the output dims */
+int ORC_FN(ireduce_ragged)(int op, int t, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4],
+                           int dim, const uint32_t *rlen, void *out_val, uint32_t *out_loc);
+
 /* 1 if this library was built from the reference's own headers, 0 for the restatement */
 int ORC_FN(is_reference)(void);
 

@@ -203,6 +203,42 @@ class Oracle:
             raise TypeError("scan_by_key: unsupported (%s, key %s)" % (DTYPE_NAMES[t], DTYPE_NAMES[tk]))
         return out
 
+    def reduce_by_key(self, op, keys, x, dim, to, ti=None, tk=None, change_nan=False, nanval=0.0):
+        """(keys_out, vals_out): runs of equal consecutive keys reduced along `dim` (two calls: count, then reduce)"""
+        ptr, d, st, keep = as_view(x)
+        ti = code_of(np.asarray(x), ti)
+        k = np.ascontiguousarray(np.asarray(keys).reshape(-1))
+        tk = code_of(k, tk)
+        assert k.size == d[dim]
+        fn = self._fn("reduce_by_key")
+        fn.restype = ctypes.c_longlong
+        args = (op, ti, to, tk, ctypes.c_void_p(k.ctypes.data), ctypes.c_void_p(ptr), _dim_arr(d), _dim_arr(st), dim,
+                int(change_nan), ctypes.c_double(nanval))
+        runs = fn(*args, None, None)
+        if runs < 0:
+            raise TypeError("reduce_by_key: no (op=%d, %s -> %s, key %s) instantiation" % (op, DTYPE_NAMES[ti], DTYPE_NAMES[to], DTYPE_NAMES[tk]))
+        od = list(d)
+        od[dim] = runs
+        kout = np.zeros(runs, dtype=k.dtype)
+        vout = np.zeros(od, dtype=NP_OF[to], order="F")
+        fn(*args, ctypes.c_void_p(kout.ctypes.data), ctypes.c_void_p(vout.ctypes.data))
+        return kout, vout
+
+    def ireduce_ragged(self, op, x, dim, rlen, t=None):
+        ptr, d, st, keep = as_view(x)
+        t = code_of(np.asarray(x), t)
+        od = list(d)
+        od[dim] = 1
+        r = np.asfortranarray(np.asarray(rlen, dtype=np.uint32).reshape(od, order="F"))
+        val = np.zeros(od, dtype=NP_OF[t], order="F")
+        loc = np.zeros(od, dtype=np.uint32, order="F")
+        rc = self._fn("ireduce_ragged")(op, t, ctypes.c_void_p(ptr), _dim_arr(d), _dim_arr(st), dim,
+                                        ctypes.c_void_p(r.ctypes.data), ctypes.c_void_p(val.ctypes.data),
+                                        ctypes.c_void_p(loc.ctypes.data))
+        if rc != 0:
+            raise TypeError("ireduce_ragged: unsupported")
+        return val, loc
+
     def where(self, x, t=None):
         ptr, d, st, keep = as_view(x)
         t = code_of(np.asarray(x), t)
@@ -414,6 +450,69 @@ class AfOracle:
             raise AfTypeError
         cast = np.asarray(keep).astype(NP_OF[to], order="F") if to != ti else keep  # castArray<Ti>(in)
         return to, self.o.scan_by_key(_BINOP[op], key, cast, dim, inclusive, to, tk)
+
+    # reductions by key (api/c/reduce.cpp:122-304, 500-554) -------------------------------------------
+    def _by_key(self, fam, op, keys, x, dim, dtype, key_dtype, change_nan=False, nanval=0.0):
+        self._check_dim(dim)
+        _, d, _, keep = as_view(x)
+        kd = dims4(np.asarray(keys).shape)
+        ti = code_of(np.asarray(x), dtype)
+        tk = code_of(np.asarray(keys), key_dtype)
+        nons = sum(1 for v in kd if v not in (0, 1))
+        if not (nons == 1 and sum(1 for v in kd if v == 1) == 3):
+            raise AfArgError("keys must be a vector")
+        klen = int(np.prod(kd)) if fam == "type" else kd[0]
+        if d[dim] != klen:
+            raise AfArgError("key length")
+        if tk not in (S32, U32):
+            raise AfTypeError
+        if fam == "promote":
+            if ti == B8:
+                op, to = OP_NOTZERO, U32
+            elif ti in _SUM_TO:
+                to = _SUM_TO[ti]
+            else:
+                raise AfTypeError
+        elif fam == "common":
+            to = ti
+        else:
+            to = U32 if op == OP_NOTZERO else B8
+        kout, vout = self.o.reduce_by_key(op, keys, x, dim, to, ti, tk, change_nan, nanval)
+        return tk, kout, to, vout
+
+    def sum_by_key(self, keys, x, dim, dtype=None, key_dtype=None, nanval=None):
+        return self._by_key("promote", OP_ADD, keys, x, dim, dtype, key_dtype, nanval is not None, nanval or 0.0)
+
+    def product_by_key(self, keys, x, dim, dtype=None, key_dtype=None, nanval=None):
+        return self._by_key("promote", OP_MUL, keys, x, dim, dtype, key_dtype, nanval is not None, nanval or 0.0)
+
+    def min_by_key(self, keys, x, dim, dtype=None, key_dtype=None):
+        return self._by_key("common", OP_MIN, keys, x, dim, dtype, key_dtype)
+
+    def max_by_key(self, keys, x, dim, dtype=None, key_dtype=None):
+        return self._by_key("common", OP_MAX, keys, x, dim, dtype, key_dtype)
+
+    def count_by_key(self, keys, x, dim, dtype=None, key_dtype=None):
+        return self._by_key("type", OP_NOTZERO, keys, x, dim, dtype, key_dtype)
+
+    def all_true_by_key(self, keys, x, dim, dtype=None, key_dtype=None):
+        return self._by_key("type", OP_AND, keys, x, dim, dtype, key_dtype)
+
+    def any_true_by_key(self, keys, x, dim, dtype=None, key_dtype=None):
+        return self._by_key("type", OP_OR, keys, x, dim, dtype, key_dtype)
+
+    def max_ragged(self, x, rlen, dim, dtype=None):
+        """af_max_ragged (api/c/reduce.cpp:1002-1078)"""
+        if not (0 <= dim < 4):
+            raise AfArgError("dim")
+        _, d, _, keep = as_view(x)
+        if af_ndims(d) == 0:
+            raise AfArgError("ndims > 0")
+        ti = code_of(np.asarray(x), dtype)
+        if dim >= af_ndims(d):
+            return ti, np.array(keep, copy=True, order="F").reshape(d, order="F"), np.zeros(d, np.uint32, order="F")
+        v, l = self.o.ireduce_ragged(OP_MAX, x, dim, rlen, ti)
+        return ti, v, l
 
     def where(self, x, dtype=None):
         _, d, _, keep = as_view(x)

@@ -24,6 +24,8 @@
 #include <math.hpp>
 
 #include <cstdint>
+#include <cstring>
+#include <vector>
 
 #define ORC_PREFIX ref
 #include "oracle_abi.h"
@@ -298,6 +300,96 @@ int ref_scan_by_key(int op, int t, int tk, const void *key, const orc_dim_t ks[4
 long long ref_where(int t, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], uint32_t *out) {
 #define X(c, T) if (t == c) return do_where<T>(in, dims, strides, out);
     NO_HALF_TYPES(X)
+#undef X
+    return -1;
+}
+
+// ---- reduce_by_key: the reference's own two steps (cpu/reduce.cpp:73-108): kernel::n_reduced_keys, then
+// kernel::reduce_dim_by_key<op,Ti,Tk,To,ndims>
+}  // extern "C"
+
+namespace {
+template<af_op_t op, typename Ti, typename To, typename Tk>
+long long do_rbk(const void *keys, const void *vals, const orc_dim_t *dims, const orc_dim_t *strides, int dim, bool cn,
+                 double nv, void *keys_out, void *vals_out) {
+    const orc_dim_t n = dims[dim];
+    dim4 kd(n, 1, 1, 1);
+    std::vector<Tk> full((size_t)n);
+    int n_reduced = 0;
+    kernel::n_reduced_keys<Tk>(Param<Tk>(full.data(), kd, dense(kd)), &n_reduced, CParam<Tk>((const Tk *)keys, kd, dense(kd)));
+    if (keys_out) memcpy(keys_out, full.data(), sizeof(Tk) * (size_t)n_reduced);
+    if (!vals_out) return n_reduced;
+    dim4 idims = D(dims), odims = D(dims);
+    odims[dim] = n_reduced;
+    Param<To> o((To *)vals_out, odims, dense(odims));
+    CParam<Ti> v((const Ti *)vals, idims, D(strides));
+    CParam<Tk> k((const Tk *)keys, kd, dense(kd));
+    switch (ndims_of(idims)) {
+        case 1: kernel::reduce_dim_by_key<op, Ti, Tk, To, 1>()(o, 0, k, v, 0, &n_reduced, dim, cn, nv); break;
+        case 2: kernel::reduce_dim_by_key<op, Ti, Tk, To, 2>()(o, 0, k, v, 0, &n_reduced, dim, cn, nv); break;
+        case 3: kernel::reduce_dim_by_key<op, Ti, Tk, To, 3>()(o, 0, k, v, 0, &n_reduced, dim, cn, nv); break;
+        default: kernel::reduce_dim_by_key<op, Ti, Tk, To, 4>()(o, 0, k, v, 0, &n_reduced, dim, cn, nv); break;
+    }
+    return n_reduced;
+}
+template<af_op_t op, typename Ti, typename To>
+long long do_rbk_key(int tk, const void *keys, const void *vals, const orc_dim_t *dims, const orc_dim_t *strides, int dim,
+                     bool cn, double nv, void *keys_out, void *vals_out) {
+    if (tk == ORC_S32) return do_rbk<op, Ti, To, int>(keys, vals, dims, strides, dim, cn, nv, keys_out, vals_out);
+    if (tk == ORC_U32) return do_rbk<op, Ti, To, uint>(keys, vals, dims, strides, dim, cn, nv, keys_out, vals_out);
+    return -1;
+}
+template<af_op_t op, typename T>
+int do_ragged(const void *in, const orc_dim_t *dims, const orc_dim_t *strides, int dim, const uint32_t *rlen, void *out,
+              uint32_t *loc) {
+    dim4 idims = D(dims), odims = D(dims);
+    if (idims.elements() == 0) return 0;
+    odims[dim] = 1;
+    Param<T> o((T *)out, odims, dense(odims));
+    Param<uint> l((uint *)loc, odims, dense(odims));
+    CParam<T> i((const T *)in, idims, D(strides));
+    CParam<uint> r((const uint *)rlen, odims, dense(odims));
+    switch (ndims_of(idims)) {
+        case 1: kernel::ireduce_dim<op, T, 1>()(o, l, 0, i, 0, dim, r); break;
+        case 2: kernel::ireduce_dim<op, T, 2>()(o, l, 0, i, 0, dim, r); break;
+        case 3: kernel::ireduce_dim<op, T, 3>()(o, l, 0, i, 0, dim, r); break;
+        default: kernel::ireduce_dim<op, T, 4>()(o, l, 0, i, 0, dim, r); break;
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+long long ref_reduce_by_key(int op, int ti, int to, int tk, const void *keys, const void *vals, const orc_dim_t dims[4],
+                            const orc_dim_t strides[4], int dim, int cn, double nv, void *keys_out, void *vals_out) {
+#define ARGS tk, keys, vals, dims, strides, dim, cn != 0, nv, keys_out, vals_out
+    if (op == ORC_OP_MIN || op == ORC_OP_MAX) {
+#define X(c, T) if (ti == c && to == c) return op == ORC_OP_MIN ? do_rbk_key<af_min_t, T, T>(ARGS) : do_rbk_key<af_max_t, T, T>(ARGS);
+        ALL_TYPES(X)
+#undef X
+    } else if (op == ORC_OP_ADD || op == ORC_OP_MUL) {
+#define X(ci, Ti, co, To) if (ti == ci && to == co) return op == ORC_OP_ADD ? do_rbk_key<af_add_t, Ti, To>(ARGS) : do_rbk_key<af_mul_t, Ti, To>(ARGS);
+        SUM_PAIRS(X)
+#undef X
+    } else if (op == ORC_OP_NOTZERO) {
+#define X(c, T) if (ti == c && to == ORC_U32) return do_rbk_key<af_notzero_t, T, uint>(ARGS);
+        ALL_TYPES(X)
+#undef X
+    } else if (op == ORC_OP_AND || op == ORC_OP_OR) {
+#define X(c, T) if (ti == c && to == ORC_B8) return op == ORC_OP_AND ? do_rbk_key<af_and_t, T, char>(ARGS) : do_rbk_key<af_or_t, T, char>(ARGS);
+        ALL_TYPES(X)
+#undef X
+    }
+#undef ARGS
+    return -1;
+}
+
+int ref_ireduce_ragged(int op, int t, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], int dim,
+                       const uint32_t *rlen, void *out_val, uint32_t *out_loc) {
+    if (op != ORC_OP_MIN && op != ORC_OP_MAX) return -1;
+#define X(c, T) if (t == c) return op == ORC_OP_MIN ? do_ragged<af_min_t, T>(in, dims, strides, dim, rlen, out_val, out_loc) : do_ragged<af_max_t, T>(in, dims, strides, dim, rlen, out_val, out_loc);
+    ALL_TYPES(X)
 #undef X
     return -1;
 }

@@ -1,0 +1,190 @@
+"""`-m gpu`: the known-answer vectors the reference's own tests hold for this path (tests/golden/kat.py, each transcribed
+with its /root/reference/test file:line) run through the CUDA path via the C-ABI -- the same cases
+tests/test_oracle_golden.py pins the oracle with -- plus the reference tests that only make sense on a device:
+Accum.MaxDim / Where.MaxDim (grid-dimension folding, test/scan.cpp:168-210, test/where.cpp:121-132) and
+FixOverflowWrite (test/scan_by_key.cpp:225-243)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.golden import kat
+from tests.gpu_util import gpu_available
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def af():
+    if not gpu_available():
+        pytest.skip("no CUDA device")
+    import arrayfire_b200
+    return arrayfire_b200
+
+
+def dev(af, x):
+    """device array of a (possibly strided) numpy view: the parent goes up whole and af_index makes the view"""
+    x = np.asarray(x)
+    base = x.base if (x.base is not None and not x.flags["F_CONTIGUOUS"]) else None
+    if base is None:
+        return af.Array.from_numpy(np.asfortranarray(x))
+    parent = np.asarray(base)
+    off = (x.__array_interface__["data"][0] - parent.__array_interface__["data"][0]) // x.itemsize
+    idx = np.unravel_index(off, parent.shape, order="F")
+    seqs = [af.seq(int(i0), int(i0) + n - 1, 1) for i0, n in zip(idx, x.shape)]
+    return af.Array.from_numpy(parent).index(*seqs)
+
+
+@pytest.mark.parametrize("case", kat.IREDUCE_DIM, ids=lambda c: c[0])
+def test_ireduce_dim(af, case):
+    name, cite, op, x, dim, gold_val, gold_idx = case
+    val, idx = getattr(af, op)(dev(af, x), dim)
+    np.testing.assert_array_equal(val.to_numpy().reshape(-1, order="F"), gold_val)
+    assert idx.to_numpy().reshape(-1, order="F").tolist() == gold_idx
+    assert idx.dtype == po.U32
+
+
+@pytest.mark.parametrize("case", kat.IREDUCE_ALL, ids=lambda c: c[0])
+def test_ireduce_all(af, case):
+    name, cite, op, x, gold_val, gold_idx = case
+    val, idx = getattr(af, op)(dev(af, x))
+    assert val == float(gold_val) and idx == gold_idx
+
+
+@pytest.mark.parametrize("case", kat.DIMWISE, ids=lambda c: c[0])
+def test_dimwise(af, case):
+    name, cite, op, x, dim, gold, gdims = case
+    out = getattr(af, op)(dev(af, x), dim)
+    assert out.dtype == po.F32 and out.dims == gdims
+    assert out.to_numpy().reshape(-1, order="F").tolist() == gold
+
+
+def test_ireduce_dim_ge_ndims(af):
+    """test/ireduce.cpp:176-194"""
+    x = np.asfortranarray(np.random.default_rng(0).random((10, 10, 1)).astype(np.float32))
+    for op in ("imin", "imax"):
+        v, l = getattr(af, op)(af.Array.from_numpy(x), 2)
+        np.testing.assert_array_equal(v.to_numpy().reshape(10, 10), x.reshape(10, 10))
+        assert not l.to_numpy().any()
+
+
+@pytest.mark.parametrize("case", list(kat.exclusive_ones_cases()), ids=lambda c: c[0])
+def test_exclusive_scan_of_ones(af, case):
+    name, x, dim, gold = case
+    out = af.scan(af.Array.from_numpy(x), dim, af.AF_BINARY_ADD, False)
+    assert out.dtype == po.S32
+    np.testing.assert_array_equal(out.to_numpy().reshape(po.dims4(gold.shape), order="F"), gold.reshape(po.dims4(gold.shape), order="F"))
+
+
+SBK = [(op, incl, dims, dim, np_dt, lo, hi)
+       for op in (0, 2, 3) for incl in (True, False)
+       for dims, dim in (((16 * 1024, 64), 0), ((1024, 128), 1))
+       for np_dt, lo, hi in ((np.int32, -15, 15), (np.float32, -5, 5))]
+
+
+@pytest.mark.parametrize("op,incl,dims,dim,np_dt,lo,hi", SBK)
+def test_scan_by_key_reference_generator(af, port_oracle, op, incl, dims, dim, np_dt, lo, hi):
+    """test/scan_by_key.cpp:111-195 with the reference test's own verify<>, and bit-exact against the oracle"""
+    key, data = kat.scan_by_key_case(dims, dim, [37, 256], 0, 15, lo, hi, np_dt)
+    out = af.scan_by_key(af.Array.from_numpy(key), af.Array.from_numpy(data), dim, op, incl).to_numpy()
+    assert kat.scan_by_key_verify(dims, data, key, out, dim, op, incl, 1e-3) == 0
+    want = port_oracle.scan_by_key(key, data, dim, op, incl)[1]
+    assert out.reshape(-1, order="F").tobytes() == want.reshape(-1, order="F").tobytes()
+
+
+def test_scan_by_key_simple(af):
+    """test/scan_by_key.cpp:197-223 Simple_0 / Simple_1"""
+    for dims, dim in (((16, 8, 2, 1), 0), ((8, 256 + 128, 1, 1), 1)):
+        key, data = kat.scan_by_key_case(dims, dim, [4, 8], 0, 15, 2, 4, np.int32)
+        out = af.scan_by_key(af.Array.from_numpy(key), af.Array.from_numpy(data), dim, af.AF_BINARY_ADD, False).to_numpy()
+        assert kat.scan_by_key_verify(dims, data, key, out, dim, 0, False, 1e-5) == 0
+
+
+def test_scan_by_key_fix_overflow_write(af):
+    """test/scan_by_key.cpp:225-243 FixOverflowWrite: N = 41000, keys all equal; a following allocation must not be
+    clobbered by an out-of-bounds write of the scan"""
+    n = 41000
+    keys = af.constant(0, (n,), af.s32)
+    vals = af.constant(1.0, (n,), af.f32)
+    guard = af.constant(0.0, (64, 1), af.f32)
+    out = af.scan_by_key(keys, vals, 0, af.AF_BINARY_ADD, True)
+    np.testing.assert_array_equal(out.to_numpy().reshape(-1), np.arange(1, n + 1, dtype=np.float32))
+    assert af.sum_all(guard) == 0.0
+    assert af.sum_all(vals) == float(n)
+
+
+def test_accum_max_dim(af):
+    """test/scan.cpp:168-210 Accum.MaxDim: dims beyond 65535 * 32 along dims 1..3 (grid folding in the reference)"""
+    n = 65535 * 32 + 1
+    for shape, dim in (((1, n), 0), ((1, 1, n), 0), ((1, 1, 1, n), 0), ((2, n), 1), ((1, 2, n // 2 + 3), 2)):
+        x = af.constant(1.0, shape, af.f32)
+        out = af.accum(x, dim).to_numpy().reshape(shape, order="F")
+        want = np.cumsum(np.ones(shape, np.float32), axis=dim)
+        np.testing.assert_array_equal(out, want)
+
+
+def test_where_max_dim_and_empty(af):
+    """test/where.cpp:121-132 (MaxDim) and :134-138 (ISSUE_1259: no hits -> 0 elements)"""
+    n = 65535 * 32 + 2
+    host = (np.arange(n) % 2 == 0)
+    for shape in ((1, n), (1, 1, n), (1, 1, 1, n)):
+        x = np.asfortranarray(host.reshape(shape, order="F"))
+        got = af.where(af.Array.from_numpy(x)).to_numpy().reshape(-1)
+        np.testing.assert_array_equal(got, (2 * np.arange(n // 2)).astype(np.uint32))
+    a = np.asfortranarray(np.random.default_rng(1).random((10, 10, 10)).astype(np.float32))
+    r = af.where(af.Array.from_numpy((a > 2)))
+    assert r.elements == 0 and r.dtype == po.U32
+
+
+def test_global_reductions_match_serial_host_loop(af):
+    """test/reduce.cpp:992-1049"""
+    rng = np.random.default_rng(7)
+    a = np.round(2 * rng.random(10000)).astype(np.float32)
+    gold = np.float32(0)
+    for v in a:
+        gold = np.float32(gold + v)
+    assert af.sum_all(af.Array.from_numpy(a)) == float(gold)
+    b = (a != 0)
+    assert af.count_all(af.Array.from_numpy(b)) == int(b.sum())
+    d = rng.random(10000)
+    assert af.min_all(af.Array.from_numpy(d)) == d.min()
+    f = rng.random(10000).astype(np.float32)
+    assert af.max_all(af.Array.from_numpy(f)) == float(f.max())
+
+
+def test_nan_rules(af):
+    """test/reduce.cpp:1147-1169, 1236-1299"""
+    rng = np.random.default_rng(8)
+    A = rng.random(10000).astype(np.float32)
+    A[A < 0.25] = np.nan
+    gA = af.Array.from_numpy(A)
+    assert af.min_all(gA) == float(np.nanmin(A)) and af.max_all(gA) == float(np.nanmax(A))
+    B = np.round(5 * rng.random(10000)).astype(np.float32)
+    Bn = B.copy()
+    Bn[B == 2] = np.nan
+    assert af.count_all(af.Array.from_numpy(Bn)) == af.count_all(af.Array.from_numpy(B))
+    assert np.isnan(af.sum_all(gA))
+    s = af.sum_all(gA, nanval=0.0)
+    assert abs(s / 10000 - np.nansum(A.astype(np.float64)) / 10000) < 1e-5
+    P = rng.random(5).astype(np.float32)
+    P[2] = np.nan
+    gP = af.Array.from_numpy(P)
+    assert np.isnan(af.product_all(gP))
+    assert abs(af.product_all(gP, nanval=1.0) - np.nanprod(P)) < 1e-5
+    Z = (rng.random(10000) > 0.5).astype(np.float32)
+    Zn = Z.copy()
+    Zn[Z == 0] = np.nan
+    assert af.any_true_all(af.Array.from_numpy(Zn)) == 1 and af.all_true_all(af.Array.from_numpy(Zn)) == 1
+    assert af.any_true_all(af.Array.from_numpy(Z)) == 1 and af.all_true_all(af.Array.from_numpy(Z)) == 0
+
+
+def test_b8_rules(af):
+    """test/reduce.cpp:1357-1374: b8 product == allTrue; b8 sum == count"""
+    rng = np.random.default_rng(9)
+    A = rng.integers(0, 2, (5, 5)).astype(bool, order="F")
+    g = af.Array.from_numpy(A)
+    p, a = af.product(g, 0), af.all_true(g, 0)
+    assert p.dtype == a.dtype == po.B8
+    np.testing.assert_array_equal(p.to_numpy(), a.to_numpy())
+    s = af.sum(g, 0)
+    assert s.dtype == po.U32
+    np.testing.assert_array_equal(s.to_numpy().reshape(-1), A.sum(axis=0).astype(np.uint32))

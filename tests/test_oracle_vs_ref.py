@@ -136,3 +136,34 @@ def test_where_bitwise(port_oracle, ref_oracle, code):
         base = rand(rng, code, shape, nan_frac=0.1, small=True)
         for x in views(rng, base):
             same(port_oracle.where(x, dtype=code), ref_oracle.where(x, dtype=code))
+
+
+@pytest.mark.parametrize("code", ALL)
+def test_reduce_by_key_and_ragged_bitwise(port_oracle, ref_oracle, code):
+    """the restated by-key reductions / ragged max against the reference's own
+    kernel::n_reduced_keys + kernel::reduce_dim_by_key and kernel::ireduce_dim with ragged lengths"""
+    rng = np.random.default_rng(900 + code)
+    for shape in [(2,), (9,), (300,), (6, 4), (3, 7, 2), (2, 3, 4, 5), (130, 3)]:
+        base = rand(rng, code, shape, nan_frac=0.1, small=True)
+        for dim in range(len(shape)):
+            n = shape[dim]
+            if n < 2:
+                continue
+            keys = np.repeat(rng.integers(0, 3, n), rng.integers(1, 5, n))[:n].astype(np.int32 if dim % 2 else np.uint32)
+            for name in ("sum_by_key", "product_by_key", "min_by_key", "max_by_key", "count_by_key", "all_true_by_key",
+                         "any_true_by_key"):
+                p = getattr(port_oracle, name)(keys, base, dim, dtype=code)
+                r = getattr(ref_oracle, name)(keys, base, dim, dtype=code)
+                assert p[0] == r[0] and p[2] == r[2]
+                same(p[1], r[1])
+                same(p[3], r[3])
+            p = port_oracle.sum_by_key(keys, base, dim, dtype=code, nanval=3.0)
+            r = ref_oracle.sum_by_key(keys, base, dim, dtype=code, nanval=3.0)
+            same(p[3], r[3])
+            od = list(po.dims4(shape))
+            od[dim] = 1
+            rl = rng.integers(0, n + 2, od).astype(np.uint32)
+            p = port_oracle.max_ragged(base, rl, dim, dtype=code)
+            r = ref_oracle.max_ragged(base, rl, dim, dtype=code)
+            same(p[1], r[1])
+            same(p[2], r[2])
