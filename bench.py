@@ -231,16 +231,28 @@ def run_cpu(steps, warmup, scale, label):
     return {"value": gbs, "unit": "GB/s", "cores": 1, "kind": kind, "sample": sample}, dt / steps * 1e3, w
 
 
+def reference_scale(steps, warmup, budget_s=150.0, full_step_s=16.0):
+    """largest power-of-two fraction of the BASELINE sizes (at most 1, at least 1/64) whose steps + warmup passes fit the
+    time budget: the reference's serial CPU kernels stream ~1.5 GB/s, i.e. ~16 s for one full-size pass of the suite"""
+    scale = 1.0
+    while scale > 1.0 / 64 and (steps + warmup) * full_step_s * scale > budget_s:
+        scale /= 2
+    return scale
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    base, ms, w = run_cpu(args.steps, args.warmup, 1.0 / 64, "reference CPU path (serial, 1 worker thread like libafcpu)")
+    scale = args.scale if args.scale < 1.0 else reference_scale(args.steps, args.warmup)
+    base, ms, w = run_cpu(args.steps, args.warmup, scale, "reference CPU path (serial, 1 worker thread like libafcpu)")
     line = {
         "impl": "reference", "metric": "effective_GBps_reduce_scan_where", "value": base["value"], "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32/s32/u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": base["sample"]},
+        # same op list as the GPU arm, every size multiplied by `scale` (1.0 = BASELINE sizes): NOT the same configuration
+        # unless scale == 1
+        "config": {"workload": WORKLOAD, "scale": scale, "same_config_as_gpu_arm": scale == 1.0, "sample": base["sample"]},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

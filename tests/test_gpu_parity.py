@@ -255,6 +255,130 @@ def test_where_nan_counts_as_nonzero(af, orc):
     assert got.tolist() == orc.where(x).tolist() == [1, 2, 5]
 
 
+@pytest.mark.parametrize("code", ALL)
+def test_nan_variants_and_all_array_twins(af, orc, code):
+    """af_product_nan, af_sum_nan_all / af_product_nan_all (scalar and _array forms) and every *_all_array twin"""
+    rng = np.random.default_rng(8500 + code)
+    for shape in [(7,), (1000,), (5, 3), (33, 1, 4), (70001,), (300, 1000)]:
+        small = rand_data(rng, code, (11,) + shape[1:], nan_frac=0.2, small=True) if len(shape) > 1 else rand_data(rng, code, (11,), nan_frac=0.2, small=True)
+        base = rand_data(rng, code, shape, nan_frac=0.05, exact=True)
+        for x, sl in views_of(rng, base):
+            g = to_gpu(af, base, sl, dtype=code)
+            pairs = [("sum_all_array", "sum_all", {}), ("min_all_array", "min_all", {}), ("max_all_array", "max_all", {}),
+                     ("count_all_array", "count_all", {}), ("all_true_all_array", "all_true_all", {}),
+                     ("any_true_all_array", "any_true_all", {})]
+            for gname, oname, kw in pairs:
+                if oname == "sum_all":
+                    t, want = orc.sum_all(x, dtype=code, scalar_api=False)
+                else:
+                    t, want = getattr(orc, oname)(x, dtype=code)
+                arr = getattr(af, gname)(g)
+                assert arr.dtype == t and arr.dims == (1, 1, 1, 1), (gname, shape)
+                same_bits(arr.to_numpy().reshape(1), want, "%s %s" % (gname, shape))
+            t, want = orc.sum_nan_all(x, 2.0, dtype=code, scalar_api=False)
+            same_bits(af.sum_all_array(g, nanval=2.0).to_numpy().reshape(1), want, "sum_nan_all_array %s" % (shape,))
+            t, want = orc.sum_nan_all(x, 2.0, dtype=code)
+            got = af.sum_all(g, nanval=2.0)
+            assert got == (complex(want[0]) if code in (po.C32, po.C64) else float(want[0])) or (got != got and want[0] != want[0])
+        # products: integer types wrap identically in any order; float types only on a 9-element line of tiny
+        # integers, where every partial product is exactly representable
+        if code in IS_FLOAT:
+            small = small.reshape(-1, order="F")[:9].copy()
+            small = np.where(small == small, np.clip(small.real, -2, 2), small).astype(small.dtype)
+        gs = af.Array.from_numpy(small, dtype=code)
+        for dim in range(small.ndim):
+            t, want = orc.product_nan(small, dim, 1.0, dtype=code)
+            got = af.product(gs, dim, nanval=1.0)
+            assert got.dtype == t
+            same_bits(got.to_numpy(), d4(want), "product_nan %s dim%d" % (small.shape, dim))
+            t, want = orc.product(small, dim, dtype=code)
+            same_bits(af.product(gs, dim).to_numpy(), d4(want), "product %s dim%d" % (small.shape, dim))
+        line = small.reshape(-1, order="F")[:9].copy()
+        gl = af.Array.from_numpy(line, dtype=code)
+        t, want = orc.product_nan_all(line, 1.0, dtype=code, scalar_api=False)
+        same_bits(af.product_all_array(gl, nanval=1.0).to_numpy().reshape(1), want, "product_nan_all_array")
+        t, want = orc.product_all(line, dtype=code, scalar_api=False)
+        same_bits(af.product_all_array(gl).to_numpy().reshape(1), want, "product_all_array")
+        t, want = orc.product_nan_all(line, 1.0, dtype=code)
+        got = af.product_all(gl, nanval=1.0)
+        w0 = complex(want[0]) if code in (po.C32, po.C64) else float(want[0])
+        assert got == w0 or (got != got and w0 != w0), ("product_nan_all", got, want)
+
+
+def test_lifecycle_and_memory_calls(af):
+    """af_constant / af_write_array / af_get_scalar / af_retain_array / af_copy_array / af_alloc_device + af_device_array /
+    af_lock_array + af_get_device_ptr / af_device_mem_info / af_device_gc (src/api/c/array.cpp, memory.cpp, data.cpp)"""
+    import ctypes
+    lib = af.lib
+    vp = ctypes.c_void_p
+
+    def mem_info():
+        v = [ctypes.c_size_t() for _ in range(4)]
+        af._check(lib.af_device_mem_info(*[ctypes.byref(x) for x in v]))
+        return tuple(x.value for x in v)   # alloc_bytes, alloc_buffers, lock_bytes, lock_buffers
+
+    af.device_gc()
+    base = mem_info()
+    c = af.constant(2.5, (1000, 3), af.f32)
+    assert c.dims == (1000, 3, 1, 1) and af.sum_all(c) == 7500.0
+    assert c.scalar() == np.float32(2.5)
+    now = mem_info()
+    assert now[2] >= base[2] + 12000 and now[3] == base[3] + 1            # one more buffer in use
+    # af_write_array from the host, then read back
+    host = np.arange(3000, dtype=np.float32)
+    af._check(lib.af_write_array(c.handle, vp(host.ctypes.data), ctypes.c_size_t(host.nbytes), ctypes.c_int(1)))   # afHost
+    np.testing.assert_array_equal(c.to_numpy().reshape(-1, order="F"), host)
+    # retain shares the buffer (use count 2), copy does not
+    r = c.retain()
+    cnt = ctypes.c_int()
+    af._check(lib.af_get_data_ref_count(ctypes.byref(cnt), c.handle))
+    assert cnt.value == 2
+    cp = c.copy()
+    af._check(lib.af_get_data_ref_count(ctypes.byref(cnt), cp.handle))
+    assert cnt.value == 1
+    del r
+    af._check(lib.af_get_data_ref_count(ctypes.byref(cnt), c.handle))
+    assert cnt.value == 1
+    # af_write_array device -> device
+    af._check(lib.af_write_array(cp.handle, vp(c.device_ptr()), ctypes.c_size_t(host.nbytes), ctypes.c_int(0)))   # afDevice
+    c.unlock()
+    np.testing.assert_array_equal(cp.to_numpy().reshape(-1, order="F"), host)
+    # af_alloc_device + af_device_array: the library adopts the pointer (and takes it back into the pool on release)
+    p = vp()
+    af._check(lib.af_alloc_device(ctypes.byref(p), ctypes.c_longlong(4096)))
+    assert p.value
+    h = vp()
+    dims = (ctypes.c_longlong * 1)(1024)
+    af._check(lib.af_device_array(ctypes.byref(h), p, 1, dims, af.f32))
+    adopted = af.Array(h)
+    af._check(lib.af_write_array(adopted.handle, vp(host.ctypes.data), ctypes.c_size_t(4096), ctypes.c_int(1)))
+    assert af.sum_all(adopted) == float(host[:1024].sum())
+    # af_get_device_ptr locks: the buffer survives the release of its last handle until the user frees it
+    q = adopted.device_ptr()
+    assert q == p.value
+    locked = ctypes.c_bool()
+    af._check(lib.af_is_locked_array(ctypes.byref(locked), adopted.handle))
+    assert locked.value
+    del adopted
+    again = vp()
+    af._check(lib.af_device_array(ctypes.byref(again), vp(q), 1, dims, af.f32))
+    back = af.Array(again)
+    assert af.sum_all(back) == float(host[:1024].sum())       # the data is still there
+    del back
+    # gc returns cached (unlocked) buffers to the driver
+    del c, cp
+    af.device_gc()
+    end = mem_info()
+    assert end[2] <= base[2] + 4096 and end[0] <= now[0]
+    # af_get_scalar of a view reads the first element of the VIEW
+    x = af.Array.from_numpy(np.arange(20, dtype=np.int32))
+    assert int(x.index(af.seq(7, 12, 1)).scalar()) == 7
+    # step size getter / setter
+    step = ctypes.c_size_t()
+    af._check(lib.af_get_mem_step_size(ctypes.byref(step)))
+    assert step.value == 1024
+
+
 def test_argument_errors(af):
     a = af.Array.from_numpy(np.ones((4, 3), np.float32, order="F"))
     for fn in (af.sum, af.min, af.count, af.accum):
