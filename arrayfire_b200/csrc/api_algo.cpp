@@ -93,7 +93,8 @@ af_err reduce_dimwise(af_array *out, const af_array in_h, int dim, Family fam, O
 // Runs the reduction into `dst` (device, one element of *to; null: the device slot paired with the host record).
 // Non-linear views with short columns are materialised first so the flattening kernel streams long spans.
 // With `ret` the kernel also publishes the value to a pinned host record (no D2H copy / stream synchronisation).
-void reduce_all_into(const Array &in, Op eff, af_dtype to, bool change_nan, double nanval, void *dst, HostRet *ret = nullptr) {
+void reduce_all_into(const Array &in, Op eff, af_dtype to, bool change_nan, double nanval, void *dst, HostRet *ret = nullptr,
+                     const ShardLink *link = nullptr) {
     const Array *src = &in;
     Holder tmp;
     if (!in.is_linear() && in.info.dims[0] < 4096) {
@@ -106,7 +107,7 @@ void reduce_all_into(const Array &in, Op eff, af_dtype to, bool change_nan, doub
         *ret = c.scratch->next_host_ret();
         if (!dst) dst = ret->dev;
     }
-    if (!launch_reduce_all(c, eff, in.info.type, to, view_of(*src), change_nan, nanval, dst, ret))
+    if (!launch_reduce_all(c, eff, in.info.type, to, view_of(*src), change_nan, nanval, dst, ret, link))
         AFB_TYPE_ERROR(1, in.info.type);
 }
 
@@ -228,7 +229,8 @@ af_err ireduce_dimwise(af_array *val, af_array *idx, const af_array in_h, int di
     AFB_API_END
 }
 
-void ireduce_all_into(const Array &in, Op op, void *dval, unsigned *dloc, HostRet *ret = nullptr) {
+void ireduce_all_into(const Array &in, Op op, void *dval, unsigned *dloc, HostRet *ret = nullptr,
+                      const ShardLink *link = nullptr) {
     const Array *src = &in;
     Holder tmp;
     if (!in.is_linear() && in.info.dims[0] < 4096) {
@@ -244,7 +246,7 @@ void ireduce_all_into(const Array &in, Op op, void *dval, unsigned *dloc, HostRe
             dloc = (unsigned *)((char *)ret->dev + 32);
         }
     }
-    if (!launch_ireduce_all(c, op, in.info.type, view_of(*src), dval, dloc, ret)) AFB_TYPE_ERROR(1, in.info.type);
+    if (!launch_ireduce_all(c, op, in.info.type, view_of(*src), dval, dloc, ret, link)) AFB_TYPE_ERROR(1, in.info.type);
 }
 
 af_err ireduce_all_scalar(double *real, double *imag, unsigned *loc, const af_array in_h, Op op) {
@@ -394,7 +396,8 @@ Array *where_finish(Array *big_raw, dim_t h_count) {
     return big.release();
 }
 
-Array *where_impl(const Array &in, unsigned base, dim_t *count_out) {
+Array *where_impl(const Array &in, unsigned base, dim_t *count_out, const ShardLink *link = nullptr, dim_t *offset_out = nullptr,
+                  dim_t *total_out = nullptr) {
     const af_dtype t = in.info.type;
     if (t == f16) AFB_TYPE_ERROR(1, t);
     const dim_t n = in.elements();
@@ -418,11 +421,14 @@ Array *where_impl(const Array &in, unsigned base, dim_t *count_out) {
             OpLock lk(in.device());
             c = ctx_for_active_device();
             ret = c.scratch->next_host_ret();
-            if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), (unsigned long long *)ret.dev, base, &ret))
+            if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), (unsigned long long *)ret.dev, base, &ret, link))
                 AFB_TYPE_ERROR(1, t);
         }
-        wait_host_ret(c, ret);   // the kernel's last tile wrote the count into the pinned record
-        h_count = *(const unsigned long long *)ret.host;
+        wait_host_ret(c, ret);   // the kernel's last tile wrote {count, offset, global count} into the pinned record
+        const unsigned long long *rec = (const unsigned long long *)ret.host;
+        h_count = rec[0];
+        if (offset_out) *offset_out = (dim_t)rec[1];
+        if (total_out) *total_out = (dim_t)rec[2];
     }
     if (count_out) *count_out = (dim_t)h_count;
     const char *e = getenv("AFB200_WHERE_SHRINK_DIV");
@@ -668,6 +674,183 @@ af_err afx_peer_exchange(void *out, const void *payload, const unsigned long lon
     }
     std::atomic_thread_fence(std::memory_order_acquire);
     memcpy(out, hp, (size_t)world * 64);
+    AFB_API_END
+}
+
+// ===================================================================================================
+// afx_sharded_*: whole-array ops over an array sharded across GPUs, combine fused into the kernels
+// (kernels/peer_comm.cuh).  Every rank calls the same op in the same order with its own shard.
+// ===================================================================================================
+}  // extern "C"
+
+namespace {
+constexpr unsigned kCommMagic = 0xAFC0111Eu;
+struct Comm {
+    unsigned magic = kCommMagic;
+    ShardLink link;
+    std::mutex mu;
+};
+Comm *comm_of(void *h) {
+    Comm *c = reinterpret_cast<Comm *>(h);
+    if (!c || c->magic != kCommMagic) fail(AF_ERR_ARG, "invalid afx_comm handle");
+    return c;
+}
+// the link of the next collective op of this communicator (epochs advance in lockstep on every rank)
+ShardLink next_link(Comm *c, unsigned idx_base, int mode) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (++c->link.epoch == 0) ++c->link.epoch;
+    ShardLink l = c->link;
+    l.idx_base = idx_base;
+    l.mode = mode;
+    return l;
+}
+}  // namespace
+
+extern "C" {
+
+af_err afx_comm_create(void **comm, int rank, int world, const unsigned long long *peer_bufs) {
+    AFB_API_BEGIN
+    AFB_ARG(0, comm != nullptr);
+    AFB_ARG(2, world >= 1 && world <= 8);
+    AFB_ARG(1, rank >= 0 && rank < world);
+    AFB_ARG(3, peer_bufs != nullptr || world == 1);
+    Comm *c = new Comm();
+    for (int r = 0; r < 8; r++) c->link.bufs[r] = (r < world && peer_bufs) ? peer_bufs[r] : 0ULL;
+    c->link.rank = rank;
+    c->link.world = world;
+    c->link.epoch = 0;
+    c->link.idx_base = 0;
+    c->link.mode = 0;
+    *comm = c;
+    AFB_API_END
+}
+
+af_err afx_comm_release(void *comm) {
+    AFB_API_BEGIN
+    if (!comm) return AF_SUCCESS;
+    Comm *c = comm_of(comm);
+    c->magic = 0;
+    delete c;
+    AFB_API_END
+}
+
+af_err afx_sharded_reduce_all(double *real, double *imag, void *comm, const af_array in_h, int op, bool change_nan,
+                              double nanval) {
+    AFB_API_BEGIN
+    AFB_ARG(0, real != nullptr);
+    AFB_ARG(4, op >= 0 && op <= 6);
+    Comm *cm = comm_of(comm);
+    Array *in = from_handle(in_h);
+    AFB_ARG(3, in->elements() > 0);
+    check_same_device(*in);
+    const Family fam = (op == OP_ADD || op == OP_MUL) ? FAM_PROMOTE : (op == OP_MIN || op == OP_MAX) ? FAM_COMMON : FAM_TYPE;
+    Op eff;
+    af_dtype to;
+    resolve(fam, (Op)op, in->info.type, &eff, &to);
+    const bool cplx = (in->info.type == c32 || in->info.type == c64);
+    if (cplx && fam != FAM_TYPE) AFB_ARG(1, imag != nullptr);
+    *real = 0;
+    if (imag) *imag = 0;
+    const ShardLink link = next_link(cm, 0u, 0);
+    HostRet ret;
+    reduce_all_into(*in, eff, to, change_nan, nanval, nullptr, &ret, &link);
+    LaunchCtx c = ctx_for_active_device();
+    wait_host_ret(c, ret);
+    decode_scalar(to, ret.host, real, imag);
+    AFB_API_END
+}
+
+af_err afx_sharded_ireduce_all(double *real, double *imag, unsigned *idx, void *comm, const af_array in_h, int op,
+                               unsigned shard_base) {
+    AFB_API_BEGIN
+    AFB_ARG(0, real != nullptr);
+    AFB_ARG(2, idx != nullptr);
+    AFB_ARG(5, op == OP_MIN || op == OP_MAX);
+    Comm *cm = comm_of(comm);
+    Array *in = from_handle(in_h);
+    AFB_ARG(4, in->ndims() > 0);
+    const af_dtype t = in->info.type;
+    if (t == f16) AFB_TYPE_ERROR(4, t);
+    if (t == c32 || t == c64) AFB_ARG(1, imag != nullptr);
+    check_same_device(*in);
+    *real = 0;
+    if (imag) *imag = 0;
+    const ShardLink link = next_link(cm, shard_base, 0);
+    HostRet ret;
+    ireduce_all_into(*in, (Op)op, nullptr, nullptr, &ret, &link);
+    LaunchCtx c = ctx_for_active_device();
+    wait_host_ret(c, ret);
+    decode_scalar(t, ret.host, real, imag);
+    *idx = *(const unsigned *)((const char *)ret.host + 32);
+    AFB_API_END
+}
+
+af_err afx_sharded_scan(af_array *out, void *comm, const af_array key_h, const af_array in_h, af_binary_op op,
+                        bool inclusive_scan) {
+    AFB_API_BEGIN
+    AFB_ARG(0, out != nullptr);
+    AFB_ARG(4, (int)op >= 0 && (int)op <= 3);
+    Comm *cm = comm_of(comm);
+    Array *in = from_handle(in_h);
+    AFB_ARG(3, in->elements() > 0 && in->elements() == in->info.dims[0]);   // a 1-D shard
+    check_same_device(*in);
+    if (key_h) {
+        // ---- segmented: carry-less local scan (+ summary), then ONE kernel exchanges the summaries and repairs the
+        // shard's first segment -- two launches, no host synchronisation
+        Array *key = from_handle(key_h);
+        check_same_device(*key);
+        AFB_ARG(2, key->is_linear());
+        const ShardLink link = next_link(cm, 0u, 0);
+        HostRet slot;
+        {
+            OpLock lk(in->device());
+            LaunchCtx c = ctx_for_active_device();
+            slot = c.scratch->next_host_ret();   // only its 64-byte device half is used: the shard summary
+        }
+        Holder res;
+        res.a = scan_by_key_impl(*key, *in, 0, (int)op, inclusive_scan, nullptr, nullptr, slot.dev);
+        {
+            OpLock lk(in->device());
+            LaunchCtx c = ctx_for_active_device();
+            if (!launch_sbk_exchange_fixup(c, (Op)op, res.a->info.type, key->info.type, res.a->data(), in->elements(), key->data(),
+                                           slot.dev, link))
+                AFB_TYPE_ERROR(3, in->info.type);
+        }
+        *out = res.release();
+        return AF_SUCCESS;
+    }
+    // ---- plain: the shard totals are exchanged inside the reduction kernel, which leaves the fold of the LOWER ranks --
+    // this shard's carry-in -- in device memory; the scan kernel's walkers read it from there.  Two launches, no host
+    // synchronisation; the second read of the shard comes from L2 when the shard fits (126 MB).
+    af_dtype to;
+    if (!scan_promote(in->info.type, &to)) AFB_TYPE_ERROR(3, in->info.type);
+    const af_dtype ti = in->info.type;
+    const bool promoted = ti != to;
+    if (ti == b8 || (promoted && ((int)op == OP_MIN || (int)op == OP_MAX)))
+        fail(AF_ERR_NOT_SUPPORTED, "afx_sharded_scan: no sharded form for this (type, op) pair (b8, or min / max of a promoted type)");
+    const ShardLink link = next_link(cm, 0u, 1);
+    Holder res;
+    res.a = new_array(to, in->info.dims);
+    {
+        OpLock lk(in->device());
+        LaunchCtx c = ctx_for_active_device();
+        HostRet slot = c.scratch->next_host_ret();
+        if (!launch_reduce_all(c, (Op)op, ti, to, view_of(*in), false, 0.0, slot.dev, nullptr, &link)) AFB_TYPE_ERROR(3, ti);
+        if (!launch_scan(c, (Op)op, ti, to, view_of(*in), 0, inclusive_scan, res.a->data(), slot.dev)) AFB_TYPE_ERROR(3, ti);
+    }
+    *out = res.release();
+    AFB_API_END
+}
+
+af_err afx_sharded_where(af_array *idx, dim_t *offset, dim_t *total, void *comm, const af_array in_h, unsigned shard_base) {
+    AFB_API_BEGIN
+    AFB_ARG(0, idx != nullptr);
+    Comm *cm = comm_of(comm);
+    Array *in = from_handle(in_h);
+    AFB_ARG(4, in->elements() > 0);
+    check_same_device(*in);
+    const ShardLink link = next_link(cm, 0u, 0);
+    *idx = where_impl(*in, shard_base, nullptr, &link, offset, total);
     AFB_API_END
 }
 

@@ -177,16 +177,27 @@ struct HostRet {
 };
 void wait_host_ret(const LaunchCtx &c, const HostRet &r);   // spins; surfaces kernel failures as af_err instead of hanging
 
+// One shard of an array spread over several GPUs (one process per GPU): what a kernel needs to exchange its O(1) partial
+// with the other ranks over peer-mapped symmetric buffers and fold the world's partials itself (kernels/peer_comm.cuh).
+struct ShardLink {
+    unsigned long long bufs[8];   // device address of every rank's symmetric buffer (>= 1088 bytes, zeroed once)
+    int rank, world;
+    unsigned epoch;               // 1, 2, 3, ... identical on every rank for the same op
+    unsigned idx_base;            // global index of the shard's first element
+    int mode;                     // reductions: 0 fold of all ranks, 1 fold of the LOWER ranks (carry-in of a sharded scan)
+};
+
 // out: dense array with dims = in.dims but dims[dim] = 1.  Returns false if (op,ti,to) is not instantiated.
 bool launch_reduce(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool change_nan,
                    double nanval, void *out);
 // out: device pointer to ONE element of `to`
 // `ret` (optional): the result is ALSO published to the pinned record (value at host+0, index at host+32)
+// `link` (optional): `in` is one shard; the kernel exchanges partials with the other ranks and folds them in rank order
 bool launch_reduce_all(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, bool change_nan,
-                       double nanval, void *out, const HostRet *ret = nullptr);
+                       double nanval, void *out, const HostRet *ret = nullptr, const ShardLink *link = nullptr);
 bool launch_ireduce(const LaunchCtx &c, Op op, af_dtype t, const View &in, int dim, void *out_val, unsigned *out_loc);
 bool launch_ireduce_all(const LaunchCtx &c, Op op, af_dtype t, const View &in, void *out_val, unsigned *out_loc,
-                        const HostRet *ret = nullptr);
+                        const HostRet *ret = nullptr, const ShardLink *link = nullptr);
 // af_max_ragged: like launch_ireduce(OP_MAX) but line j only looks at its first min(len, rlen[j]) elements
 bool launch_ireduce_ragged(const LaunchCtx &c, Op op, af_dtype t, const View &in, int dim, const unsigned *rlen,
                            void *out_val, unsigned *out_loc);
@@ -199,8 +210,14 @@ bool launch_scan_by_key(const LaunchCtx &c, Op op, af_dtype t, af_dtype tk, cons
 bool launch_scan_fixup(const LaunchCtx &c, Op op, af_dtype t, void *out, dim_t count, const void *carry_host);
 // writes hit indices (+base) to `out` (capacity = elements) and the count to *d_count (device, 8 bytes)
 // `ret` (optional): the count is also published to the pinned record (u64 at host+0)
+// with `link` the kernel also exchanges the shard counts: the record then holds {count, offset of this shard's slice in the
+// global output, global count} (3 x u64)
 bool launch_where(const LaunchCtx &c, af_dtype t, const View &in, unsigned *out, unsigned long long *d_count,
-                  unsigned base, const HostRet *ret = nullptr);
+                  unsigned base, const HostRet *ret = nullptr, const ShardLink *link = nullptr);
+// sharded scan_by_key, after the carry-less local scan (summary mode): ONE kernel exchanges (tail total, has-head, first
+// key, last key) with the other ranks, derives this shard's carry and repairs its first segment in place
+bool launch_sbk_exchange_fixup(const LaunchCtx &c, Op op, af_dtype t, af_dtype tk, void *out, dim_t n, const void *keys,
+                               const void *summary, const ShardLink &link);
 // ---- reductions by key (kernels/rbk_*.cu): keys = n dense 32-bit keys, runs of equal consecutive keys are segments
 // pass 1: number of runs -> published through `ret` (u64); tile_base[t] (device, ntiles + 1 words) = runs starting before tile t
 dim_t rbk_tile_elems();

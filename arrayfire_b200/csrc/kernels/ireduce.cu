@@ -4,13 +4,14 @@
 namespace afb {
 template<int OP, typename T>
 static void ireduce_one(const LaunchCtx &c, const View &in, int dim, bool all, void *out_val, unsigned *out_loc,
-                        const HostRet *ret) {
+                        const HostRet *ret, const ShardLink *link) {
     typedef ArgPolicy<OP, T> P;
     typename P::Params prm;
+    prm.seed = (link && link->world > 1 && link->idx_base != 0) ? 0 : 1;
     typename P::Out o;
     o.val = (T *)out_val;
     o.loc = out_loc;
-    if (all) run_all<P>(c, in, prm, o, ret);
+    if (all) run_all<P>(c, in, prm, o, ret, link);
     else run_reduce<P>(c, in, dim, prm, o);
 }
 // ---- af_max_ragged (/root/reference/src/api/c/reduce.cpp:1002-1078, cpu/kernel/ireduce.hpp:86-104): the (value, index)
@@ -78,12 +79,12 @@ bool launch_ireduce_ragged(const LaunchCtx &c, Op op, af_dtype t, const View &in
 }
 
 static bool route(const LaunchCtx &c, Op op, af_dtype t, const View &in, int dim, bool all, void *v, unsigned *l,
-                  const HostRet *ret) {
+                  const HostRet *ret, const ShardLink *link) {
     if (op != OP_MIN && op != OP_MAX) return false;
 #define X(code, T)                                                              \
     if (t == code) {                                                            \
-        if (op == OP_MIN) ireduce_one<OP_MIN, T>(c, in, dim, all, v, l, ret);        \
-        else ireduce_one<OP_MAX, T>(c, in, dim, all, v, l, ret);                     \
+        if (op == OP_MIN) ireduce_one<OP_MIN, T>(c, in, dim, all, v, l, ret, link);        \
+        else ireduce_one<OP_MAX, T>(c, in, dim, all, v, l, ret, link);                     \
         return true;                                                            \
     }
     AFB_ALL_TYPES(X)
@@ -91,9 +92,10 @@ static bool route(const LaunchCtx &c, Op op, af_dtype t, const View &in, int dim
     return false;
 }
 bool launch_ireduce(const LaunchCtx &c, Op op, af_dtype t, const View &in, int dim, void *v, unsigned *l) {
-    return route(c, op, t, in, dim, false, v, l, nullptr);
+    return route(c, op, t, in, dim, false, v, l, nullptr, nullptr);
 }
-bool launch_ireduce_all(const LaunchCtx &c, Op op, af_dtype t, const View &in, void *v, unsigned *l, const HostRet *ret) {
-    return route(c, op, t, in, 0, true, v, l, ret);
+bool launch_ireduce_all(const LaunchCtx &c, Op op, af_dtype t, const View &in, void *v, unsigned *l, const HostRet *ret,
+                        const ShardLink *link) {
+    return route(c, op, t, in, 0, true, v, l, ret, link);
 }
 }  // namespace afb

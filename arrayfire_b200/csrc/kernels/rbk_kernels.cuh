@@ -172,8 +172,10 @@ __global__ void __launch_bounds__(kRbkThreads) rbk_tile_kernel(const RbkArgs<Ti,
             if (j < nv) {
                 v = R::pre(vec ? raw[j] : ldg_stream<Ti>(col + p0 + j));
                 if (a.prm.change_nan) v = nan_swap<Acc>(v, a.prm.nanval);
+                // the first run of a line starts from init() (reduce.hpp:137,146-148: b8 min / max normalise through it)
+                if (p0 + j == 0) v = R::join(R::init(), v);
             }
-            // a run's first element is taken as is (the reference seeds the accumulator with it, reduce.hpp:146-151)
+            // a later run's first element is taken as is (the reference seeds the accumulator with it, reduce.hpp:152-156)
             run = (j == 0 || ((hb >> j) & 1u)) ? v : R::join(run, v);
             x[j] = run;
         }
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(256) rbk_dim_kernel(const RbkDimArgs<Ti, To> a
             Acc v = R::pre(ldg_stream<Ti>(in + i * a.g.sd));
             if (a.prm.change_nan) v = nan_swap<Acc>(v, a.prm.nanval);
             if (i == 0) {
-                acc = v;
+                acc = R::join(R::init(), v);   // the first run starts from init() (reduce.hpp:137,146-148)
             } else if (key != prev) {
                 out[seg * a.od] = conv<To, Acc>(acc);
                 seg++;

@@ -10,14 +10,14 @@ namespace afb {
 
 template<int OP, typename Ti, typename To>
 inline void reduce_one(const LaunchCtx &c, const View &in, int dim, bool all, bool change_nan, double nanval, void *out,
-                       const HostRet *ret = nullptr) {
+                       const HostRet *ret = nullptr, const ShardLink *link = nullptr) {
     typedef ValPolicy<OP, Ti, To> P;
     typename P::Params prm;
     prm.change_nan = change_nan ? 1 : 0;
     prm.nanval = nanval;
     typename P::Out o;
     o.val = (To *)out;
-    if (all) run_all<P>(c, in, prm, o, ret);
+    if (all) run_all<P>(c, in, prm, o, ret, link);
     else run_reduce<P>(c, in, dim, prm, o);
 }
 
@@ -37,12 +37,12 @@ inline void reduce_one(const LaunchCtx &c, const View &in, int dim, bool all, bo
 
 // each family lives in its own translation unit
 bool reduce_family_minmax(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool all,
-                          bool change_nan, double nanval, void *out, const HostRet *ret);
+                          bool change_nan, double nanval, void *out, const HostRet *ret, const ShardLink *link);
 bool reduce_family_sum(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool all,
-                       bool change_nan, double nanval, void *out, const HostRet *ret);
+                       bool change_nan, double nanval, void *out, const HostRet *ret, const ShardLink *link);
 bool reduce_family_prod(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool all,
-                        bool change_nan, double nanval, void *out, const HostRet *ret);
+                        bool change_nan, double nanval, void *out, const HostRet *ret, const ShardLink *link);
 bool reduce_family_logic(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool all,
-                         bool change_nan, double nanval, void *out, const HostRet *ret);
+                         bool change_nan, double nanval, void *out, const HostRet *ret, const ShardLink *link);
 
 }  // namespace afb

@@ -113,6 +113,9 @@ void run_cols(const LaunchCtx &c, const View &in, const typename P::Params &prm,
     a.host_flag = nullptr;
     a.host_seq = 0;
     a.host_out = out;
+    a.comm = peer_comm_of(nullptr);
+    a.idx_base = 0;
+    a.comm_mode = 0;
     if (bpc / csize > 1) {
         a.partials = (Slot<Acc> *)c.scratch->need_partials((size_t)g.ncols * (bpc / csize) * sizeof(Slot<Acc>));
         a.tickets = c.scratch->need_tickets((size_t)g.ncols);
@@ -132,7 +135,7 @@ void run_cols(const LaunchCtx &c, const View &in, const typename P::Params &prm,
 // strided view with long columns.
 template<typename P>
 void run_all(const LaunchCtx &c, const View &in, const typename P::Params &prm, const typename P::Out &out,
-             const HostRet *ret = nullptr) {
+             const HostRet *ret = nullptr, const ShardLink *link = nullptr) {
     typedef typename P::Acc Acc;
     typedef typename P::In In;
     ColGeom g = col_geom(in);
@@ -176,6 +179,9 @@ void run_all(const LaunchCtx &c, const View &in, const typename P::Params &prm, 
     a.host_flag = ret ? ret->flag : nullptr;
     a.host_seq = ret ? ret->seq : 0u;
     a.host_out = P::host_out(ret ? ret->host : nullptr);
+    a.comm = peer_comm_of(link);
+    a.idx_base = link ? link->idx_base : 0u;
+    a.comm_mode = link ? link->mode : 0;
     if (csize > 1)
         launch_with_cluster(span_kernel<P>, dim3((unsigned)grid), dim3(kThreads), dim3(csize, 1, 1), c.stream, a);
     else

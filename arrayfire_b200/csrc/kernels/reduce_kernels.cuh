@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 
 #include "device_ops.cuh"
+#include "peer_comm.cuh"
 
 namespace afb {
 namespace cg = cooperative_groups;
@@ -53,6 +54,7 @@ template<int OP, typename Ti, typename To> struct ValPolicy {
         return v;
     }
     AFB_DI static Acc join(Acc a, Acc b) { return R::join(a, b); }
+    AFB_DI static Acc globalize(Acc a, uint) { return a; }   // shard partial -> record exchanged between ranks
     AFB_DI static void store(const Out &o, size_t i, Acc a) { o.val[i] = conv<To, Acc>(a); }
     // fold one 16-byte vector of inputs whose first element has index idx0
     AFB_DI static Acc fold16(const Params &p, Acc acc, const Vec16 &v, uint idx0) {
@@ -90,7 +92,9 @@ template<> struct NativeOrder<__half> {
     AFB_DI static float cmp(__half v) { return __half2float(v); }
 };
 
-struct ArgParams {};
+struct ArgParams {
+    int seed = 1;   // 0: this is not the first shard of a sharded array -- its element 0 is not the reduction's seed
+};
 
 template<int OP, typename T> struct ArgPolicy {
     static constexpr bool kSplitAcc = NativeOrder<T>::value;   // break the compare/select chain of the streaming path
@@ -106,13 +110,18 @@ template<int OP, typename T> struct ArgPolicy {
         if (OP == OP_MIN) return Acc{Lim<T>::hi(), 0u};
         return Acc{Lim<T>::lo(), 0xffffffffu};
     }
-    AFB_DI static Acc load(const Params &, In x, uint idx) {
+    AFB_DI static Acc load(const Params &p, In x, uint idx) {
         if (is_nan<T>(x)) {
-            // NaN candidates never win; only the seed (position 0) turns into the identity at index 0
-            if (idx == 0) return Acc{OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(), 1u};
+            // NaN candidates never win; only the seed (position 0 of the WHOLE array) turns into the identity at index 0
+            if (idx == 0 && p.seed) return Acc{OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(), 1u};
             return init();
         }
         return Acc{x, idx + 1u};
+    }
+    // sharded arrays: ranks become global by adding the shard's offset; "no candidate" stays what it is
+    AFB_DI static Acc globalize(Acc a, uint base) {
+        if (a.idx != (OP == OP_MIN ? 0u : 0xffffffffu)) a.idx += base;
+        return a;
     }
     AFB_DI static Acc join(Acc a, Acc b) {
         const double ka = order_key<T>(a.val), kb = order_key<T>(b.val);
@@ -184,6 +193,10 @@ template<int OP, typename T> struct FirstPolicy {
         if (OP == OP_MIN) take_b = (kb < ka) || (kb == ka && b.idx < a.idx);
         else take_b = (kb > ka) || (kb == ka && b.idx < a.idx);
         return take_b ? b : a;
+    }
+    AFB_DI static Acc globalize(Acc a, uint base) {
+        if (a.idx != 0u) a.idx += base;
+        return a;
     }
     AFB_DI static void store(const Out &o, size_t i, Acc a) { o.val[i] = a.val; }
     AFB_DI static Acc fold16(const Params &p, Acc acc, const Vec16 &v, uint idx0) {
@@ -317,7 +330,32 @@ struct SpanArgs {
     typename P::Out host_out;
     uint *host_flag;
     uint host_seq;
+    // "all" mode, optional (comm.world > 1): `in` is one shard of an array spread over several GPUs.  The thread that
+    // holds the shard's partial exchanges it with the other ranks over peer memory (peer_comm.cuh) and folds the world's
+    // partials in rank order BEFORE the stores above: every rank ends with the global result (comm_mode 0), or with the
+    // fold of the LOWER ranks only -- the carry-in of a sharded scan (comm_mode 1; rank 0 gets the identity).
+    PeerComm comm;
+    uint idx_base;      // global index of the shard's first element (index reductions)
+    int comm_mode;
 };
+
+// the cross-rank step of span_kernel (one thread)
+template<typename P>
+AFB_DI typename P::Acc span_exchange(const SpanArgs<P> &a, typename P::Acc mine) {
+    typedef typename P::Acc Acc;
+    PeerRecord rec;
+    rec.q[0] = rec.q[1] = rec.q[2] = rec.q[3] = make_uint4(0u, 0u, 0u, 0u);
+    rec_put(rec, P::globalize(mine, a.idx_base));
+    peer_publish(a.comm, rec);
+    peer_wait(a.comm, a.comm.world);
+    const int upto = a.comm_mode == 1 ? a.comm.rank : a.comm.world;
+    Acc g = P::init();
+    for (int r = 0; r < upto; r++) {
+        const Acc v = rec_get<Acc>(peer_read(a.comm, r));
+        g = (r == 0) ? v : P::join(g, v);
+    }
+    return g;
+}
 
 template<typename P>
 __global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
@@ -367,6 +405,7 @@ __global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
     // ---- level 3: one partial per (cluster of) CTA(s); the last arriver folds them in index order
     if (nparts == 1) {
         if (tid == 0) {
+            if (a.comm.world > 1) acc = span_exchange<P>(a, acc);
             P::store(a.out, (size_t)col, acc);
             if (a.host_flag) {
                 P::store(a.host_out, 0, acc);
@@ -390,6 +429,7 @@ __global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
     for (uint i = tid; i < nparts; i += kThreads) fin = P::join(fin, load_cg(slots + i));
     fin = block_reduce<P>(fin, sm);
     if (tid == 0) {
+        if (a.comm.world > 1) fin = span_exchange<P>(a, fin);
         P::store(a.out, (size_t)col, fin);
         *ticket = 0u;  // self-reset: the next launch on this stream finds it clean
         if (a.host_flag) {

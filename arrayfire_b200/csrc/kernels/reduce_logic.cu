@@ -2,12 +2,12 @@
 #include "reduce_dispatch.cuh"
 namespace afb {
 bool reduce_family_logic(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const View &in, int dim, bool all,
-                         bool cn, double nv, void *out, const HostRet *ret) {
+                         bool cn, double nv, void *out, const HostRet *ret, const ShardLink *link) {
     if (op == OP_NOTZERO) {
         if (to != u32) return false;
 #define X(code, T)                                                          \
     if (ti == code) {                                                       \
-        reduce_one<OP_NOTZERO, T, uint>(c, in, dim, all, cn, nv, out, ret);      \
+        reduce_one<OP_NOTZERO, T, uint>(c, in, dim, all, cn, nv, out, ret, link);      \
         return true;                                                        \
     }
         AFB_ALL_TYPES(X)
@@ -17,8 +17,8 @@ bool reduce_family_logic(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, co
     if (to != b8) return false;
 #define X(code, T)                                                                      \
     if (ti == code) {                                                                   \
-        if (op == OP_AND) reduce_one<OP_AND, T, b8_t>(c, in, dim, all, cn, nv, out, ret);    \
-        else reduce_one<OP_OR, T, b8_t>(c, in, dim, all, cn, nv, out, ret);                  \
+        if (op == OP_AND) reduce_one<OP_AND, T, b8_t>(c, in, dim, all, cn, nv, out, ret, link);    \
+        else reduce_one<OP_OR, T, b8_t>(c, in, dim, all, cn, nv, out, ret, link);                  \
         return true;                                                                    \
     }
     AFB_ALL_TYPES(X)

@@ -2,10 +2,10 @@
 #include "reduce_dispatch.cuh"
 namespace afb {
 bool reduce_family_prod(const LaunchCtx &c, Op, af_dtype ti, af_dtype to, const View &in, int dim, bool all, bool cn,
-                        double nv, void *out, const HostRet *ret) {
+                        double nv, void *out, const HostRet *ret, const ShardLink *link) {
 #define X(ci, Ti, co, To)                                                \
     if (ti == ci && to == co) {                                          \
-        reduce_one<OP_MUL, Ti, To>(c, in, dim, all, cn, nv, out, ret);        \
+        reduce_one<OP_MUL, Ti, To>(c, in, dim, all, cn, nv, out, ret, link);        \
         return true;                                                     \
     }
     AFB_SUM_PAIRS(X)

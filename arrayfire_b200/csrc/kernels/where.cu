@@ -8,6 +8,7 @@
 // straight to their final position.  Traffic = N*sizeof(T) read + 4*count written.
 // Semantics: /root/reference/src/backend/cpu/where.cpp:27-63 (x != 0, NaN counts, view-order linear index).
 #include "scan_host.cuh"
+#include "peer_comm.cuh"
 
 namespace afb {
 
@@ -28,13 +29,34 @@ struct WhereArgs {
     unsigned long long *host_total;   // optional pinned copy of the count + flag (common.hpp HostRet)
     uint *host_flag;
     uint host_seq;
+    PeerComm comm;                    // world > 1: `in` is one shard, the counts are exchanged in the kernel
 };
 
-// the total goes to device memory and, when asked for, to the pinned host record (one thread calls this)
+// the total goes to device memory and, when asked for, to the pinned host record (one thread calls this).  For a shard
+// of a multi-GPU array the thread first exchanges the count with the other ranks (peer_comm.cuh): the record then also
+// carries the offset of this shard's slice in the global output and the global count.
 template<typename A> AFB_DI void where_publish_total(const A &a, unsigned long long total) {
-    *a.total = total;
+    unsigned long long offset = 0, all = total;
+    if (a.comm.world > 1) {
+        PeerRecord rec;
+        rec.q[0] = rec.q[1] = rec.q[2] = rec.q[3] = make_uint4(0u, 0u, 0u, 0u);
+        rec_put(rec, total);
+        peer_publish(a.comm, rec);
+        peer_wait(a.comm, a.comm.world);
+        all = 0;
+        for (int r = 0; r < a.comm.world; r++) {
+            const unsigned long long c = rec_get<unsigned long long>(peer_read(a.comm, r));
+            if (r < a.comm.rank) offset += c;
+            all += c;
+        }
+    }
+    a.total[0] = total;
+    a.total[1] = offset;
+    a.total[2] = all;
     if (a.host_flag) {
-        *a.host_total = total;
+        a.host_total[0] = total;
+        a.host_total[1] = offset;
+        a.host_total[2] = all;
         host_ret_publish(a.host_flag, a.host_seq);
     }
 }
@@ -150,7 +172,7 @@ __global__ void __launch_bounds__(kScanThreads) where_kernel(const WhereArgs<T> 
 
 template<typename T>
 static void run_where_simple(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base,
-                             const HostRet *ret) {
+                             const HostRet *ret, const ShardLink *link) {
     WhereArgs<T> a;
     a.in = (const T *)in.ptr;
     a.n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
@@ -167,6 +189,7 @@ static void run_where_simple(const LaunchCtx &c, const View &in, uint *out, unsi
     a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
     a.host_flag = ret ? ret->flag : nullptr;
     a.host_seq = ret ? ret->seq : 0u;
+    a.comm = peer_comm_of(link);
     where_kernel<T><<<(unsigned)a.ntiles, kScanThreads, 0, c.stream>>>(a);
     note_launches(1);
     post_launch_check("where_kernel");
@@ -197,20 +220,23 @@ struct ChainWhereArgs {
     unsigned long long *host_total;   // optional pinned copy of the count + flag (common.hpp HostRet)
     uint *host_flag;
     uint host_seq;
+    PeerComm comm;                    // world > 1: `in` is one shard, the counts are exchanged in the kernel
 };
-
 
 // bit k of the result: element k of the 16-byte vector is non-zero
 template<typename T> AFB_DI uint nonzero_mask(const Vec16 &v) {
     constexpr int E = VecN<T>::value;
     if constexpr (sizeof(T) == 1) {
+        // 5 instructions per 4 bytes (r01: ~9): bit 7 of every byte <- (byte != 0) [and, add, or-and]; one multiply
+        // gathers the four flags into the product's top nibble (0x204081 = 2^21 + 2^14 + 2^7 + 1 moves bits 7 / 15 / 23 /
+        // 31 to 28 / 29 / 30 / 31, the cross terms land on distinct lower bits, so nothing carries); a funnel shift
+        // appends the nibble to the running mask
         uint m = 0;
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
+        for (int w = 3; w >= 0; w--) {
             const uint x = v.w[w];
-            // bit 7 of every byte <- (byte != 0), then gather the four bits into the top nibble
-            const uint nz = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) >> 7;
-            m |= ((nz * 0x10204080u) >> 28) << (4 * w);
+            const uint nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+            m = __funnelshift_l(nz * 0x00204081u, m, 4);
         }
         return m;
     } else {
@@ -636,59 +662,124 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
             cw[2] += clock64() - k1;
             k1 = clock64();
             const unsigned short *mkp = masks + (size_t)((i - 1) & 1) * (SUB * Lay::NVEC);
+            // flush `total` indices from the warp's strip (filled from index `shift` = gpos & 3 on, so that its 16-byte
+            // quads line up with `out`): whole quads with 16-byte stores, the ragged ends element by element
+            auto flush = [&](uint gpos, uint shift, uint total) {
+                if (total <= 32u) {                  // one coalesced scalar store
+                    if (lane < total) a.out[gpos + lane] = strip[shift + lane];
+                    return;
+                }
+                uint *out_al = a.out + (gpos - shift);
+                const uint lim = shift + total;
+                // a strip holds at most 32 * E + 4 indices = kQ quads per lane: all shared-memory loads are issued before
+                // the first store, so their latencies overlap (r01: a load -> store chain per iteration)
+                constexpr int kQ = (32 * E + 4 + 127) / 128;
+                uint4 v[kQ];
+#pragma unroll
+                for (int j = 0; j < kQ; j++) {
+                    const uint qd = lane + 32u * j;
+                    if (4u * qd < lim) v[j] = *reinterpret_cast<const uint4 *>(strip + 4u * qd);
+                }
+#pragma unroll
+                for (int j = 0; j < kQ; j++) {
+                    const uint qd = lane + 32u * j;
+                    if (4u * qd >= lim) continue;
+                    if (4u * qd >= shift && 4u * qd + 4u <= lim) {
+                        *reinterpret_cast<uint4 *>(out_al + 4u * qd) = v[j];
+                    } else {
+                        if (4u * qd + 0u >= shift && 4u * qd + 0u < lim) out_al[4u * qd + 0u] = v[j].x;
+                        if (4u * qd + 1u >= shift && 4u * qd + 1u < lim) out_al[4u * qd + 1u] = v[j].y;
+                        if (4u * qd + 2u >= shift && 4u * qd + 2u < lim) out_al[4u * qd + 2u] = v[j].z;
+                        if (4u * qd + 3u >= shift && 4u * qd + 3u < lim) out_al[4u * qd + 3u] = v[j].w;
+                    }
+                }
+            };
 #pragma unroll 1
             for (int sub = 0; sub < SUB; sub++) {
                 uint gpos = sm_wp[bp][sub * NW + warp];
+                const uint gtotal = sm_wtot[bp][sub * NW + warp];   // hits of this warp's U slots (pass 1)
+                if (gtotal == 0u) continue;                         // warp-uniform
                 const dim_t sub_lo = tile_prev * TILE + (dim_t)sub * SUBTILE;
-#pragma unroll 1
-                for (int u = 0; u < U; u++) {
-                    const int q = (warp * U + u) * 32 + lane;
-                    uint mm = mkp[sub * Lay::NVEC + q];
-                    const uint c = __popc(mm);
+                if (gtotal <= 32u * E) {
+                    // ---- sparse group (the warp's U x 512 input bytes hold at most one strip of hits): a lane owns U
+                    // CONSECUTIVE vectors (one 8-byte load of their masks), so its hits are contiguous in the output and
+                    // ONE warp scan + one flush serve all U slots (r01: one scan + flush per slot; 1 % mask 311 M -> ~110 M
+                    // warp instructions per 2^30 bytes)
+                    static_assert(U == 4, "the sparse path reads the masks of 4 vectors as one 8-byte word");
+                    const int q0 = warp * U * 32 + lane * U;
+                    const uint2 mw = *reinterpret_cast<const uint2 *>(mkp + sub * Lay::NVEC + q0);
+                    const uint c = __popc(mw.x) + __popc(mw.y);
                     uint inc = c;
 #pragma unroll
                     for (int dd = 1; dd < 32; dd <<= 1) {
                         const uint o = __shfl_up_sync(0xffffffffu, inc, dd);
                         if (lane >= dd) inc += o;
                     }
-                    const uint total = __shfl_sync(0xffffffffu, inc, 31);
-                    if (total == 0u) continue;        // warp-uniform
-                    // the strip is filled from index (gpos & 3) on, so that its 16-byte quads line up with `out`
                     const uint shift = gpos & 3u;
-                    uint o = shift + inc - c;
-                    const uint first = a.base + (uint)(sub_lo + (dim_t)q * E);
-                    if (total * 4u >= 32u * E) {
-                        // dense slot: branch-free, one predicated store per element (no per-lane trip counts)
-#pragma unroll
-                        for (int k = 0; k < E; k++) {
-                            if ((mm >> k) & 1u) strip[o] = first + k;
-                            o += (mm >> k) & 1u;
-                        }
-                    } else {
-                        while (mm) {
-                            const int k = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            strip[o++] = first + k;
-                        }
+                    uint *p = strip + (shift + inc - c);
+                    const uint first = a.base + (uint)(sub_lo + (dim_t)q0 * E);
+                    uint m = mw.x;
+                    while (m) {                      // vectors 0 (bits 0..15) and 1 (bits 16..31)
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        *p++ = first + (uint)((b >> 4) * E + (b & 15));
+                    }
+                    m = mw.y;
+                    while (m) {                      // vectors 2 and 3
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        *p++ = first + (uint)(2 * E + (b >> 4) * E + (b & 15));
                     }
                     __syncwarp();
-                    // flush: whole quads with 16-byte stores, the ragged ends element by element
-                    uint *out_al = a.out + (gpos - shift);
-                    const uint lim = shift + total;
-                    if (total <= 32u) {                // sparse slot: one coalesced scalar store
-                        if (lane < total) a.out[gpos + lane] = strip[shift + lane];
-                    } else
-                    for (uint qd = lane; 4u * qd < lim; qd += 32) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(strip + 4u * qd);
-                        if (4u * qd >= shift && 4u * qd + 4u <= lim) {
-                            *reinterpret_cast<uint4 *>(out_al + 4u * qd) = v;
-                        } else {
-                            if (4u * qd + 0u >= shift && 4u * qd + 0u < lim) out_al[4u * qd + 0u] = v.x;
-                            if (4u * qd + 1u >= shift && 4u * qd + 1u < lim) out_al[4u * qd + 1u] = v.y;
-                            if (4u * qd + 2u >= shift && 4u * qd + 2u < lim) out_al[4u * qd + 2u] = v.z;
-                            if (4u * qd + 3u >= shift && 4u * qd + 3u < lim) out_al[4u * qd + 3u] = v.w;
-                        }
+                    flush(gpos, shift, gtotal);
+                    __syncwarp();
+                    continue;
+                }
+                // ---- dense group: slot by slot, a lane owns ONE vector per slot.  The U masks are fetched and their U warp
+                // scans run interleaved up front (independent shuffle chains), so only expansion + flush stay serial per slot
+                uint mm[U], cc[U], inc[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    mm[u] = mkp[sub * Lay::NVEC + (warp * U + u) * 32 + lane];
+                    cc[u] = __popc(mm[u]);
+                    inc[u] = cc[u];
+                }
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const uint o = __shfl_up_sync(0xffffffffu, inc[u], dd);
+                        if (lane >= dd) inc[u] += o;
                     }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint total = __shfl_sync(0xffffffffu, inc[u], 31);
+                    if (total == 0u) continue;        // warp-uniform
+                    const int q = (warp * U + u) * 32 + lane;
+                    const uint shift = gpos & 3u;
+                    const uint first = a.base + (uint)(sub_lo + (dim_t)q * E);
+                    // branch-free expansion through running pointers (one per half vector: two short dependency chains):
+                    // per element one predicated store and one predicated pointer bump (r01 recomputed the strip address
+                    // from the offset for every element)
+                    const uint m = mm[u];
+                    uint *p0 = strip + (shift + inc[u] - cc[u]);
+                    constexpr int H = E >= 2 ? E / 2 : 1;
+                    uint *p1 = p0 + __popc(m & ((1u << H) - 1u));
+#pragma unroll
+                    for (int k = 0; k < H; k++) {
+                        const bool hit = (m >> k) & 1u;
+                        if (hit) *p0 = first + k;
+                        if (hit) p0++;
+                    }
+#pragma unroll
+                    for (int k = H; k < E; k++) {
+                        const bool hit = (m >> k) & 1u;
+                        if (hit) *p1 = first + k;
+                        if (hit) p1++;
+                    }
+                    __syncwarp();
+                    flush(gpos, shift, total);
                     __syncwarp();
                     gpos += total;
                 }
@@ -706,7 +797,7 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
 
 template<typename T>
 static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned long long *d_count, uint base,
-                      const HostRet *ret) {
+                      const HostRet *ret, const ShardLink *link) {
     const dim_t n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
     constexpr dim_t CT = (dim_t)kChainThreads * kCW_U * VecN<T>::value;
     if (aligned_to(in.ptr, 16) && aligned_to(out, 16) && n >= 2 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
@@ -731,6 +822,7 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
         a.host_flag = ret ? ret->flag : nullptr;
         a.host_seq = ret ? ret->seq : 0u;
+        a.comm = peer_comm_of(link);
         dim_t grid = (dim_t)c.sms;
         if (grid > a.ntiles) grid = a.ntiles;
         a.ticket = c.scratch->chain_ticket;
@@ -781,6 +873,7 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
         a.host_flag = ret ? ret->flag : nullptr;
         a.host_seq = ret ? ret->seq : 0u;
+        a.comm = peer_comm_of(link);
         int ctas = env_int("AFB200_CHAIN_CTAS_PER_SM", resident[dv]);
         if (ctas > resident[dv]) ctas = resident[dv];
         dim_t grid = (dim_t)c.sms * ctas;
@@ -793,25 +886,25 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         post_launch_check("chain_where_kernel");
         return;
     }
-    run_where_simple<T>(c, in, out, d_count, base, ret);
+    run_where_simple<T>(c, in, out, d_count, base, ret, link);
 }
 
 bool launch_where(const LaunchCtx &c, af_dtype t, const View &in, unsigned *out, unsigned long long *d_count,
-                  unsigned base, const HostRet *ret) {
+                  unsigned base, const HostRet *ret, const ShardLink *link) {
     switch (t) {
-        case f32: run_where<float>(c, in, out, d_count, base, ret); return true;
-        case f64: run_where<double>(c, in, out, d_count, base, ret); return true;
-        case c32: run_where<cfloat>(c, in, out, d_count, base, ret); return true;
-        case c64: run_where<cdouble>(c, in, out, d_count, base, ret); return true;
-        case s32: run_where<int>(c, in, out, d_count, base, ret); return true;
-        case u32: run_where<uint>(c, in, out, d_count, base, ret); return true;
-        case s64: run_where<intl>(c, in, out, d_count, base, ret); return true;
-        case u64: run_where<uintl>(c, in, out, d_count, base, ret); return true;
-        case s16: run_where<short>(c, in, out, d_count, base, ret); return true;
-        case u16: run_where<ushort>(c, in, out, d_count, base, ret); return true;
-        case s8: run_where<schar>(c, in, out, d_count, base, ret); return true;
-        case u8: run_where<uchar>(c, in, out, d_count, base, ret); return true;
-        case b8: run_where<b8_t>(c, in, out, d_count, base, ret); return true;
+        case f32: run_where<float>(c, in, out, d_count, base, ret, link); return true;
+        case f64: run_where<double>(c, in, out, d_count, base, ret, link); return true;
+        case c32: run_where<cfloat>(c, in, out, d_count, base, ret, link); return true;
+        case c64: run_where<cdouble>(c, in, out, d_count, base, ret, link); return true;
+        case s32: run_where<int>(c, in, out, d_count, base, ret, link); return true;
+        case u32: run_where<uint>(c, in, out, d_count, base, ret, link); return true;
+        case s64: run_where<intl>(c, in, out, d_count, base, ret, link); return true;
+        case u64: run_where<uintl>(c, in, out, d_count, base, ret, link); return true;
+        case s16: run_where<short>(c, in, out, d_count, base, ret, link); return true;
+        case u16: run_where<ushort>(c, in, out, d_count, base, ret, link); return true;
+        case s8: run_where<schar>(c, in, out, d_count, base, ret, link); return true;
+        case u8: run_where<uchar>(c, in, out, d_count, base, ret, link); return true;
+        case b8: run_where<b8_t>(c, in, out, d_count, base, ret, link); return true;
         default: return false;
     }
 }

@@ -171,6 +171,7 @@ class LocalGpu:
         rank (torch.distributed._symmetric_memory).  Returns False -- and the NCCL all-gather stays in use -- when the
         platform cannot map peer memory."""
         self._peer = None
+        self._comm = None
         try:
             import torch.distributed._symmetric_memory as symm
             world, rank = dist.get_world_size(), dist.get_rank()
@@ -184,12 +185,54 @@ class LocalGpu:
             ptrs = (self.ct.c_ulonglong * 8)(*([int(p) for p in hdl.buffer_ptrs] + [0] * (8 - world)))
             self._peer = {"tensor": t, "handle": hdl, "ptrs": ptrs, "rank": rank, "world": world, "epoch": 0,
                           "out": (self.ct.c_ubyte * (8 * PAYLOAD_BYTES))()}
+            # a second symmetric buffer for the FUSED ops (afx_sharded_*: the exchange happens inside the compute kernels,
+            # include/afb200.h); its epochs advance independently of the afx_peer_exchange buffer above
+            t2 = symm.empty(2048, dtype=self.torch.uint8, device=self.dev)
+            t2.zero_()
+            hdl2 = symm.rendezvous(t2, dist.group.WORLD)
+            self.torch.cuda.synchronize()
+            dist.barrier()
+            ptrs2 = (self.ct.c_ulonglong * 8)(*([int(p) for p in hdl2.buffer_ptrs] + [0] * (8 - world)))
+            comm = self.ct.c_void_p()
+            self.af._check(self.af.lib.afx_comm_create(self.ct.byref(comm), self.ct.c_int(rank), self.ct.c_int(world), ptrs2))
+            self._comm = comm
+            self._comm_keep = (t2, hdl2, ptrs2)
             return True
         except Exception as ex:  # noqa: BLE001 -- any failure here only means "keep using NCCL"
             import sys
             print("[afb200] peer exchange unavailable, using NCCL all-gather: %r" % (ex,), file=sys.stderr)
             self._peer = None
+            self._comm = None
             return False
+
+    # ---- fused ops: ONE C call per sharded op, the cross-GPU combine happens inside the kernels ----------------------
+    def fused_reduce_all(self, a, op):
+        af, ct = self.af, self.ct
+        re, im = ct.c_double(), ct.c_double()
+        af._check(af.lib.afx_sharded_reduce_all(ct.byref(re), ct.byref(im), self._comm, a.handle, ct.c_int(op), ct.c_bool(False),
+                                                ct.c_double(0.0)))
+        return complex(re.value, im.value) if a.dtype in (af.c32, af.c64) else re.value
+
+    def fused_ireduce_all(self, a, op, base):
+        af, ct = self.af, self.ct
+        re, im, idx = ct.c_double(), ct.c_double(), ct.c_uint()
+        af._check(af.lib.afx_sharded_ireduce_all(ct.byref(re), ct.byref(im), ct.byref(idx), self._comm, a.handle, ct.c_int(op),
+                                                 ct.c_uint(base)))
+        v = complex(re.value, im.value) if a.dtype in (af.c32, af.c64) else re.value
+        return v, idx.value
+
+    def fused_scan(self, key, a, binop, inclusive):
+        af, ct = self.af, self.ct
+        h = ct.c_void_p()
+        af._check(af.lib.afx_sharded_scan(ct.byref(h), self._comm, key.handle if key is not None else None, a.handle,
+                                          ct.c_int(binop), ct.c_bool(inclusive)))
+        return af.Array(h)
+
+    def fused_where(self, a, base):
+        af, ct = self.af, self.ct
+        h, off, tot = ct.c_void_p(), ct.c_longlong(), ct.c_longlong()
+        af._check(af.lib.afx_sharded_where(ct.byref(h), ct.byref(off), ct.byref(tot), self._comm, a.handle, ct.c_uint(base)))
+        return af.Array(h), off.value, tot.value
 
     def peer_gather(self, buf):
         """[world, PAYLOAD_BYTES] numpy array of every rank's 64-byte record, exchanged by ONE kernel over peer memory"""
@@ -204,8 +247,17 @@ class LocalGpu:
         """the per-op 64-byte partial record.  ONE persistent device buffer: every op overwrites the fields it
         reads back, and ops on the library's stream are ordered, so no per-op allocation / memset is needed."""
         if getattr(self, "_payload", None) is None:
-            self._payload = self.torch.zeros(PAYLOAD_BYTES, dtype=self.torch.uint8, device=self.dev)
+            with self.on_stream():     # every op that touches the payload runs on the LIBRARY's stream
+                self._payload = self.torch.zeros(PAYLOAD_BYTES, dtype=self.torch.uint8, device=self.dev)
         return self._payload
+
+    def put_base(self, buf, base):
+        """buf[48:56] <- this shard's global offset (so that no second exchange is needed to learn the other ranks' bases)"""
+        cache = self.__dict__.setdefault("_base_t", {})
+        if base not in cache:   # purely local: no collective hides behind this cache
+            cache[base] = self.torch.frombuffer(bytearray(np.uint64(base).tobytes()), dtype=self.torch.uint8).to(self.dev)
+        with self.on_stream():
+            buf[48:56] = cache[base]
 
     def to_host(self, gathered):
         """[world, PAYLOAD_BYTES] device tensor -> numpy, through a persistent pinned landing zone (one async copy +
@@ -297,8 +349,9 @@ class LocalGpu:
                                               ct.c_bool(inclusive)))
         kb = af._SIZE[key.dtype]
         kv = self.bytes_view(key)
-        buf[32:32 + kb] = kv[:kb]
-        buf[40:40 + kb] = kv[-kb:]
+        with self.on_stream():         # ordered after the scan kernel and before the gather, both on the library's stream
+            buf[32:32 + kb] = kv[:kb]
+            buf[40:40 + kb] = kv[-kb:]
         return af.Array(h)
 
     def scan_fixup(self, out, carry_bytes, count, binop):
@@ -369,6 +422,9 @@ class ShardedOps:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 self.local._peer = None
+                self.local._comm = None
+            if os.environ.get("AFB200_NO_FUSED", "0") == "1":   # A-B switch: round-1 path (separate exchange kernel + host fold)
+                self.local._comm = None
 
     # -- helpers -----------------------------------------------------------------------------------
     def _gather(self, buf):
@@ -381,22 +437,11 @@ class ShardedOps:
                 return self.local.to_host(g)
             return g.cpu().numpy()
 
-    def _shard_bases(self, base):
-        """global offsets of every rank's shard.  A sharding is fixed for the life of the arrays, so the offsets are
-        exchanged once per distinct `base` and cached (every rank calls with its own base, collectively)."""
-        cache = self.__dict__.setdefault("_bases", {})
-        if base not in cache:
-            import torch
-            t = torch.zeros(PAYLOAD_BYTES, dtype=torch.uint8)
-            t[:8] = torch.frombuffer(bytearray(np.uint64(base).tobytes()), dtype=torch.uint8)
-            dev = getattr(self.local, "dev", None)
-            g = self._gather(t.to(dev) if dev is not None else t)
-            cache[base] = [int(g[r, :8].view(np.uint64)[0]) for r in range(self.world)]
-        return cache[base]
-
     # -- reductions ----------------------------------------------------------------------------------
     def reduce_all(self, op, a):
         """af_<op>_all over the global array; the scalar comes back as the promoted numpy type"""
+        if getattr(self.local, "_comm", None) is not None:
+            return self.local.fused_reduce_all(a, _AFX_OP[op])
         buf = self.local.payload()
         code = self.local.reduce_partial(buf, a, _AFX_OP[op])
         g = self._gather(buf)
@@ -406,10 +451,13 @@ class ShardedOps:
 
     def ireduce_all(self, op, a, base):
         """(value, GLOBAL u32 index) of af_imin_all / af_imax_all; `base` is this shard's global offset"""
+        if getattr(self.local, "_comm", None) is not None:
+            return self.local.fused_ireduce_all(a, _AFX_OP[op], int(base))
         buf = self.local.payload()
         self.local.ireduce_partial(buf, a, _AFX_OP[op])
+        self.local.put_base(buf, int(base))      # every rank's base travels in its own record
         g = self._gather(buf)
-        bases = self._shard_bases(int(base))
+        bases = [int(g[r, 48:56].view(np.uint64)[0]) for r in range(self.world)]
         code = self.local.dtype(a)
         dt = np.dtype(_NP_OF[code])
         vals = [g[r, :dt.itemsize].view(dt)[0] for r in range(self.world)]
@@ -421,6 +469,8 @@ class ShardedOps:
     def scan(self, a, binop, inclusive):
         """af_scan along the flattened axis: shard totals are exchanged first, then every shard is scanned
         once with its carry-in (the second read of a shard that fits the 126 MB L2 is served from L2)."""
+        if getattr(self.local, "_comm", None) is not None and self.local.dtype(a) != _B8:
+            return self.local.fused_scan(None, a, binop, inclusive)
         buf = self.local.payload()
         red = _BINOP_TO_RED[binop]
         code = self.local.reduce_partial(buf, a, _AFX_OP[red])
@@ -440,6 +490,8 @@ class ShardedOps:
     def scan_by_key(self, key, a, binop, inclusive):
         """af_scan_by_key along the flattened axis: local carry-less scan, one all-gather of the shard
         summaries, fix-up of the first segment only."""
+        if getattr(self.local, "_comm", None) is not None:
+            return self.local.fused_scan(key, a, binop, inclusive)
         buf = self.local.payload()
         out = self.local.scan_by_key_local(buf, key, a, binop, inclusive)
         g = self._gather(buf)
@@ -460,6 +512,8 @@ class ShardedOps:
     def where(self, a, base):
         """af_where: returns (this shard's indices [global numbering], offset of the slice in the global
         output, global hit count).  The output stays sharded."""
+        if getattr(self.local, "_comm", None) is not None:
+            return self.local.fused_where(a, base)
         if hasattr(self.local, "where_launch"):
             # kernel, all-gather of the device-resident counts and ONE read-back / synchronisation
             h, slot = self.local.where_launch(a, base)

@@ -273,7 +273,8 @@ AFAPI af_err afx_scan_shard_fixup(af_array out, const void *carry, dim_t count, 
 AFAPI af_err afx_where_shard(af_array *idx, dim_t *count, const af_array in, unsigned base);
 /* The same in two asynchronous halves, so that a multi-GPU caller pays ONE host synchronisation for the kernel
  * and the exchange of the counts together: _launch enqueues the compaction into a worst-case sized u32 array and
- * leaves the hit count (u64) in device memory at *count_dev (valid until the next libafb200 call on this device);
+ * leaves the hit count (u64) in device memory at *count_dev (a per-launch slot of a 64-entry ring: valid until 63 further
+ * count-returning calls have been issued on this device);
  * _finish trims the array to `count` hits once the caller has read the count back. */
 AFAPI af_err afx_where_shard_launch(af_array *idx, void **count_dev, const af_array in, unsigned base);
 AFAPI af_err afx_where_shard_finish(af_array *idx, dim_t count);
@@ -284,6 +285,26 @@ AFAPI af_err afx_where_shard_finish(af_array *idx, dim_t count);
  * `epoch` must be 1, 2, 3, ... on successive calls, identically on every rank (world <= 8). */
 AFAPI af_err afx_peer_exchange(void *out, const void *payload, const unsigned long long *peer_bufs, int rank, int world,
                                unsigned epoch);
+/* ---- the same ops with the cross-GPU combine FUSED into the kernels (kernels/peer_comm.cuh): the thread that holds the
+ * shard's partial stores it into every rank's symmetric buffer over NVLink peer memory, waits for the others and folds the
+ * world's partials in rank order -- no second launch, no collective-library call, no host round trip before the combine.
+ * `peer_bufs[r]` = device address (in THIS process) of rank r's symmetric buffer: >= 1088 bytes, zero-initialised, mapped
+ * into every rank (torch.distributed._symmetric_memory, or cuMemCreate + IPC handles).  Every rank must issue the same
+ * afx_sharded_* calls in the same order (they are collectives); world <= 8. */
+AFAPI af_err afx_comm_create(void **comm, int rank, int world, const unsigned long long *peer_bufs);
+AFAPI af_err afx_comm_release(void *comm);
+/* af_<op>_all of the GLOBAL array (op codes of afx_reduce_all_partial); identical result on every rank */
+AFAPI af_err afx_sharded_reduce_all(double *real, double *imag, void *comm, const af_array shard, int op, bool change_nan,
+                                    double nanval);
+/* af_imin_all (op 2) / af_imax_all (op 3) of the global array; *idx is the GLOBAL index, shard_base this shard's offset */
+AFAPI af_err afx_sharded_ireduce_all(double *real, double *imag, unsigned *idx, void *comm, const af_array shard, int op,
+                                     unsigned shard_base);
+/* this rank's slice of af_scan (key == NULL) / af_scan_by_key of the global 1-D array; fully asynchronous (two launches) */
+AFAPI af_err afx_sharded_scan(af_array *out, void *comm, const af_array key, const af_array shard, af_binary_op op,
+                              bool inclusive_scan);
+/* this rank's slice of af_where of the global array (global indices): the slice starts at *offset of *total hits */
+AFAPI af_err afx_sharded_where(af_array *idx, dim_t *offset, dim_t *total, void *comm, const af_array shard,
+                               unsigned shard_base);
 /* number of CUDA kernels this library launched on the calling thread's device since the last reset */
 AFAPI af_err afx_launch_count(unsigned long long *count, bool reset);
 

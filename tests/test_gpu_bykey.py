@@ -52,8 +52,8 @@ def test_reduce_by_key(af, port_oracle, code):
             keys = make_keys(rng, n, kind, kdt)
             gk = af.Array.from_numpy(keys)
             for name in OPS:
-                if name == "product_by_key" and code in (po.F32, po.F64, po.C32, po.C64, po.F16) and kind in ("same", "long"):
-                    continue   # long float products are not exactly representable
+                if name == "product_by_key" and code in (po.F32, po.F64, po.C32, po.C64, po.F16):
+                    continue   # float products are not exactly representable: order-dependent rounding (see below)
                 tk, wk, tv, wv = getattr(orc, name)(keys, x, dim, dtype=code)
                 ko, vo = getattr(af, name)(gk, gx, dim)
                 assert ko.dtype == tk and vo.dtype == tv, (name, shape)
@@ -62,6 +62,12 @@ def test_reduce_by_key(af, port_oracle, code):
             tk, wk, tv, wv = orc.sum_by_key(keys, x, dim, dtype=code, nanval=2.0)
             ko, vo = af.sum_by_key(gk, gx, dim, nanval=2.0)
             same_bits(vo.to_numpy(), d4(wv), "sum_by_key_nan %s %s" % (shape, kind))
+            if code in (po.F32, po.F64, po.C32, po.C64, po.F16) and kind == "short":
+                # float products: runs of at most a few elements of +-1 / +-2 stay exact in any order
+                xs = np.where(x == x, np.sign(x.real) * np.minimum(np.abs(x.real), 2), x).astype(x.dtype)
+                tk, wk, tv, wv = orc.product_by_key(keys, xs, dim, dtype=code, nanval=1.0)
+                ko, vo = af.product_by_key(gk, af.Array.from_numpy(np.asfortranarray(xs), dtype=code), dim, nanval=1.0)
+                same_bits(vo.to_numpy(), d4(wv), "product_by_key_nan %s" % (shape,))
 
 
 def test_reduce_by_key_large_and_views(af, port_oracle):

@@ -52,6 +52,9 @@ class LocalOracle:
         self._put(buf, 0, np.asarray(v).reshape(-1)[:1].tobytes())
         return code
 
+    def put_base(self, buf, base):
+        self._put(buf, 48, np.uint64(base).tobytes())
+
     def ireduce_partial(self, buf, a, op):
         v, i = (self.orc.imin_all if op == 2 else self.orc.imax_all)(a)
         self._put(buf, 0, np.asarray(v, dtype=a.dtype).tobytes())

@@ -40,6 +40,33 @@ def main():
         if not ok:
             bad.append(name)
 
+    # other dtypes through the fused / exchanged reductions (f64, s64 wrap-free, u8 min / max, complex sum)
+    xd = rng.integers(-4, 5, n).astype(np.float64)
+    xl = rng.integers(-2 ** 40, 2 ** 40, n).astype(np.int64)
+    xc = (rng.integers(-4, 5, n) + 1j * rng.integers(-4, 5, n)).astype(np.complex64)
+    check("sum_f64", float(ops.reduce_all(sh.OP_SUM, A(xd[lo:hi]))) == float(orc.sum_all(xd)[1][0]))
+    check("sum_s64", int(ops.reduce_all(sh.OP_SUM, A(xl[lo:hi]))) == int(float(orc.sum_all(xl)[1][0])))
+    check("min_u8", int(ops.reduce_all(sh.OP_MIN, A(u8[lo:hi]))) == int(u8.min()) and int(ops.reduce_all(sh.OP_MAX, A(u8[lo:hi]))) == int(u8.max()))
+    check("sum_c32", complex(ops.reduce_all(sh.OP_SUM, A(xc[lo:hi]))) == complex(orc.sum_all(xc, scalar_api=False)[1][0]))
+    check("any_all", int(ops.reduce_all(sh.OP_ANY, A(u8[lo:hi]))) == 1 and int(ops.reduce_all(sh.OP_ALL, A(u8[lo:hi]))) == 0)
+    # NaN seeds at shard starts must not become candidates (only global element 0 is the seed)
+    tn = ties.copy()
+    for r in range(world):
+        tn[sh.shard_bounds(n, world, r)[0]] = np.nan
+    for op, fn in ((sh.OP_MAX, orc.imax_all), (sh.OP_MIN, orc.imin_all)):
+        v, i = ops.ireduce_all(op, A(tn[lo:hi]), lo)
+        wv, wi = fn(tn)
+        check("ireduce_nan%d" % op, (float(v), int(i)) == (float(wv), int(wi)))
+    # scans: min / max by key, f32 plain max
+    for binop in (2, 3):
+        got = ops.scan_by_key(A(keys[lo:hi]), A(iv[lo:hi]), binop, True).to_numpy().reshape(-1)
+        check("sbk_op%d" % binop, got.tobytes() == orc.scan_by_key(keys, iv, 0, binop, True)[1].reshape(-1)[lo:hi].tobytes())
+    got = ops.scan(A(x[lo:hi]), 3, True).to_numpy().reshape(-1)
+    check("scan_max", got.tobytes() == orc.scan(x, 0, 3, True)[1].reshape(-1)[lo:hi].tobytes())
+    k1 = np.zeros(n, np.int32)                 # ONE run over all shards: the carry chains through every rank
+    got = ops.scan_by_key(A(k1[lo:hi]), A(iv[lo:hi]), 0, True).to_numpy().reshape(-1)
+    check("sbk_one_run", got.tobytes() == np.cumsum(iv, dtype=np.int64).astype(np.int32)[lo:hi].tobytes())
+
     for rep in range(3):   # repeated: epochs / persistent buffers must stay consistent
         check("sum", np.float32(ops.reduce_all(sh.OP_SUM, A(x[lo:hi]))).tobytes() == orc.sum_all(x, scalar_api=False)[1][:1].tobytes())
         check("count", int(ops.reduce_all(sh.OP_COUNT, A(u8[lo:hi]))) == int(orc.count_all(u8)[1][0]))
@@ -59,8 +86,12 @@ def main():
     t = torch.tensor([len(bad)], device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print("check_sharded world=%d peer=%s: %s" % (world, getattr(ops.local, "_peer", None) is not None,
-                                                      "OK" if int(t.item()) == 0 else "FAILED %s" % bad), flush=True)
+        print("check_sharded world=%d peer=%s fused=%s: %s" % (world, getattr(ops.local, "_peer", None) is not None,
+                                                               getattr(ops.local, "_comm", None) is not None,
+                                                               "OK (every sharded op bit-exact against the oracle on the global array)"
+                                                               if int(t.item()) == 0 else "FAILED"), flush=True)
+    if bad:
+        print("  rank %d failures: %s" % (rank, bad), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     return 0 if int(t.item()) == 0 else 1
