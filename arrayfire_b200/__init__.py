@@ -503,6 +503,57 @@ def where(a):
     return Array(h)
 
 
+# ---- issue / collect (include/afb200.h afx_*_async): enqueue many ops, collect their O(1) host results afterwards --------
+OP_ADD, OP_MUL, OP_MIN, OP_MAX, OP_COUNT, OP_ALL, OP_ANY = range(7)
+
+
+class Pending:
+    """an enqueued whole-array op whose scalar / index / hit count has not been collected yet; result() waits on the
+    pinned host record the kernel's last thread writes (no cudaMemcpy, no stream synchronisation)"""
+
+    def __init__(self, handle, kind, cplx):
+        self.handle, self.kind, self.cplx = handle, kind, cplx
+
+    def result(self):
+        h, self.handle = self.handle, None
+        if h is None:
+            raise AfError(202, "this pending op was already collected")   # AF_ERR_ARG
+        if self.kind == "where":
+            out, off, tot = _vp(), ctypes.c_longlong(), ctypes.c_longlong()
+            _check(lib.afx_pending_where(h, ctypes.byref(out), ctypes.byref(off), ctypes.byref(tot)))
+            return Array(out), off.value, tot.value
+        re, im, idx = ctypes.c_double(), ctypes.c_double(), ctypes.c_uint()
+        _check(lib.afx_pending_scalar(h, ctypes.byref(re), ctypes.byref(im), ctypes.byref(idx)))
+        v = complex(re.value, im.value) if self.cplx else re.value
+        return (v, idx.value) if self.kind == "indexed" else v
+
+    def __del__(self):
+        if getattr(self, "handle", None) is not None and lib is not None:
+            lib.afx_pending_release(self.handle)
+            self.handle = None
+
+
+def reduce_all_async(a, op, comm=None, nanval=None):
+    """af_<op>_all (op: OP_ADD .. OP_ANY) enqueued; with `comm` (afx_comm_create) `a` is this rank's shard of a global array"""
+    h = _vp()
+    _check(lib.afx_reduce_all_async(ctypes.byref(h), comm, a.handle, ctypes.c_int(op), ctypes.c_bool(nanval is not None),
+                                    ctypes.c_double(0.0 if nanval is None else nanval)))
+    return Pending(h, "scalar", a.dtype in (c32, c64) and op in (OP_ADD, OP_MUL, OP_MIN, OP_MAX))
+
+
+def ireduce_all_async(a, op, comm=None, base=0):
+    h = _vp()
+    _check(lib.afx_ireduce_all_async(ctypes.byref(h), comm, a.handle, ctypes.c_int(op), ctypes.c_uint(base)))
+    return Pending(h, "indexed", a.dtype in (c32, c64))
+
+
+def where_async(a, comm=None, base=0):
+    """af_where enqueued; result() -> (indices [+ base], offset of the slice in the global output, global hit count)"""
+    h = _vp()
+    _check(lib.afx_where_async(ctypes.byref(h), comm, a.handle, ctypes.c_uint(base)))
+    return Pending(h, "where", False)
+
+
 # ---- device ------------------------------------------------------------------------------------------
 def sync(device=-1):
     _check(lib.af_sync(ctypes.c_int(device)))

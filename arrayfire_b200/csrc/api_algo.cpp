@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include <atomic>
+#include <memory>
 
 #include "common.hpp"
 
@@ -396,8 +397,9 @@ Array *where_finish(Array *big_raw, dim_t h_count) {
     return big.release();
 }
 
-Array *where_impl(const Array &in, unsigned base, dim_t *count_out, const ShardLink *link = nullptr, dim_t *offset_out = nullptr,
-                  dim_t *total_out = nullptr) {
+// enqueue the compaction into a worst-case sized output (straight from the pool: the kernel writes indices to their final
+// position); the kernel's last tile publishes {count, offset of the shard's slice, global count} through `ret`
+Array *where_begin(const Array &in, unsigned base, const ShardLink *link, HostRet *ret) {
     const af_dtype t = in.info.type;
     if (t == f16) AFB_TYPE_ERROR(1, t);
     const dim_t n = in.elements();
@@ -408,45 +410,31 @@ Array *where_impl(const Array &in, unsigned base, dim_t *count_out, const ShardL
         tmp.a = make_dense_copy(in);
         src = tmp.a;
     }
-    // worst-case sized output straight from the pool: the kernel writes indices to their final position
-    // and the count comes back once, at the end (the reference syncs mid-pipeline to size the output)
     Holder big;
     dim_t cap[4] = {n, 1, 1, 1};
     big.a = new_array(u32, cap);
-    unsigned long long h_count = 0;
-    {
-        HostRet ret;
-        LaunchCtx c;
-        {
-            OpLock lk(in.device());
-            c = ctx_for_active_device();
-            ret = c.scratch->next_host_ret();
-            if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), (unsigned long long *)ret.dev, base, &ret, link))
-                AFB_TYPE_ERROR(1, t);
-        }
-        wait_host_ret(c, ret);   // the kernel's last tile wrote {count, offset, global count} into the pinned record
-        const unsigned long long *rec = (const unsigned long long *)ret.host;
-        h_count = rec[0];
-        if (offset_out) *offset_out = (dim_t)rec[1];
-        if (total_out) *total_out = (dim_t)rec[2];
-    }
-    if (count_out) *count_out = (dim_t)h_count;
-    const char *e = getenv("AFB200_WHERE_SHRINK_DIV");
-    const dim_t div = e ? atoll(e) : 8;
-    if (h_count == 0 || (div > 0 && (dim_t)h_count < n / div)) {
-        // few hits: hand back an exact-size buffer instead of pinning the worst-case allocation
-        dim_t d[4] = {(dim_t)h_count, 1, 1, 1};
-        Holder exact;
-        exact.a = new_array(u32, d);
-        if (h_count) {
-            cudaStream_t s = stream_of(in.device());
-            AFB_CUDA(cudaMemcpyAsync(exact.a->data(), big.a->data(), (size_t)h_count * 4, cudaMemcpyDeviceToDevice, s));
-        }
-        return exact.release();
-    }
-    big.a->info.dims[0] = (dim_t)h_count;  // keep the over-sized buffer, expose only the hits
-    dense_strides(big.a->info.dims, big.a->info.strides);
+    OpLock lk(in.device());
+    LaunchCtx c = ctx_for_active_device();
+    *ret = c.scratch->next_host_ret();
+    if (!launch_where(c, t, view_of(*src), (unsigned *)big.a->data(), (unsigned long long *)ret->dev, base, ret, link))
+        AFB_TYPE_ERROR(1, t);
     return big.release();
+}
+
+// the count comes back once, at the end (the reference syncs mid-pipeline to size the output)
+Array *where_impl(const Array &in, unsigned base, dim_t *count_out, const ShardLink *link = nullptr, dim_t *offset_out = nullptr,
+                  dim_t *total_out = nullptr) {
+    HostRet ret;
+    Holder big;
+    big.a = where_begin(in, base, link, &ret);
+    LaunchCtx c = ctx_for_active_device();
+    wait_host_ret(c, ret);
+    const unsigned long long *rec = (const unsigned long long *)ret.host;
+    const dim_t h_count = (dim_t)rec[0];
+    if (offset_out) *offset_out = (dim_t)rec[1];
+    if (total_out) *total_out = (dim_t)rec[2];
+    if (count_out) *count_out = h_count;
+    return where_finish(big.release(), h_count);   // few hits: an exact-size buffer instead of the worst-case allocation
 }
 
 }  // namespace
@@ -698,11 +686,34 @@ Comm *comm_of(void *h) {
 // the link of the next collective op of this communicator (epochs advance in lockstep on every rank)
 ShardLink next_link(Comm *c, unsigned idx_base, int mode) {
     std::lock_guard<std::mutex> lk(c->mu);
-    if (++c->link.epoch == 0) ++c->link.epoch;
+    if (++c->link.epoch == 0) c->link.epoch = 2;   // never 0, and the parity keeps alternating across the wrap
     ShardLink l = c->link;
     l.idx_base = idx_base;
     l.mode = mode;
     return l;
+}
+
+// an op that has been enqueued and whose O(1) host result has not been collected yet (afx_*_async)
+constexpr unsigned kPendingMagic = 0xAFB2F07Eu;
+enum PendingKind { PEND_SCALAR = 0, PEND_INDEXED = 1, PEND_WHERE = 2 };
+struct Pending {
+    unsigned magic = kPendingMagic;
+    int kind = PEND_SCALAR;
+    int device = 0;
+    af_dtype type = f32;     // dtype of the value in the record
+    HostRet ret{};
+    unsigned idx_add = 0;
+    Array *big = nullptr;    // where: the worst-case sized output
+    ~Pending() {
+        magic = 0;
+        delete big;
+    }
+};
+LaunchCtx ctx_for_device(int d) { return LaunchCtx{d, stream_of(d), sm_count(d), &scratch_of(d)}; }
+Pending *pending_of(void *h) {
+    Pending *p = reinterpret_cast<Pending *>(h);
+    if (!p || p->magic != kPendingMagic) fail(AF_ERR_ARG, "invalid afx_pending handle");
+    return p;
 }
 }  // namespace
 
@@ -734,29 +745,118 @@ af_err afx_comm_release(void *comm) {
     AFB_API_END
 }
 
-af_err afx_sharded_reduce_all(double *real, double *imag, void *comm, const af_array in_h, int op, bool change_nan,
-                              double nanval) {
+af_err afx_reduce_all_async(afx_pending *pending, void *comm, const af_array in_h, int op, bool change_nan, double nanval) {
     AFB_API_BEGIN
-    AFB_ARG(0, real != nullptr);
-    AFB_ARG(4, op >= 0 && op <= 6);
-    Comm *cm = comm_of(comm);
+    AFB_ARG(0, pending != nullptr);
+    AFB_ARG(3, op >= 0 && op <= 6);
+    Comm *cm = comm ? comm_of(comm) : nullptr;
     Array *in = from_handle(in_h);
-    AFB_ARG(3, in->elements() > 0);
+    AFB_ARG(2, in->elements() > 0);
     check_same_device(*in);
     const Family fam = (op == OP_ADD || op == OP_MUL) ? FAM_PROMOTE : (op == OP_MIN || op == OP_MAX) ? FAM_COMMON : FAM_TYPE;
     Op eff;
     af_dtype to;
     resolve(fam, (Op)op, in->info.type, &eff, &to);
-    const bool cplx = (in->info.type == c32 || in->info.type == c64);
-    if (cplx && fam != FAM_TYPE) AFB_ARG(1, imag != nullptr);
+    std::unique_ptr<Pending> p(new Pending());
+    p->kind = PEND_SCALAR;
+    p->device = in->device();
+    p->type = to;
+    ShardLink link;
+    if (cm) link = next_link(cm, 0u, 0);
+    reduce_all_into(*in, eff, to, change_nan, nanval, nullptr, &p->ret, cm ? &link : nullptr);
+    *pending = p.release();
+    AFB_API_END
+}
+
+af_err afx_ireduce_all_async(afx_pending *pending, void *comm, const af_array in_h, int op, unsigned shard_base) {
+    AFB_API_BEGIN
+    AFB_ARG(0, pending != nullptr);
+    AFB_ARG(3, op == OP_MIN || op == OP_MAX);
+    Comm *cm = comm ? comm_of(comm) : nullptr;
+    Array *in = from_handle(in_h);
+    AFB_ARG(2, in->ndims() > 0);
+    const af_dtype t = in->info.type;
+    if (t == f16) AFB_TYPE_ERROR(2, t);
+    check_same_device(*in);
+    std::unique_ptr<Pending> p(new Pending());
+    p->kind = PEND_INDEXED;
+    p->device = in->device();
+    p->type = t;
+    ShardLink link;
+    if (cm) link = next_link(cm, shard_base, 0);
+    ireduce_all_into(*in, (Op)op, nullptr, nullptr, &p->ret, cm ? &link : nullptr);
+    p->idx_add = cm ? 0u : shard_base;   // a lone shard: the kernel did not add the base
+    *pending = p.release();
+    AFB_API_END
+}
+
+af_err afx_where_async(afx_pending *pending, void *comm, const af_array in_h, unsigned shard_base) {
+    AFB_API_BEGIN
+    AFB_ARG(0, pending != nullptr);
+    Comm *cm = comm ? comm_of(comm) : nullptr;
+    Array *in = from_handle(in_h);
+    AFB_ARG(2, in->elements() > 0);
+    check_same_device(*in);
+    std::unique_ptr<Pending> p(new Pending());
+    p->kind = PEND_WHERE;
+    p->device = in->device();
+    p->type = u32;
+    ShardLink link;
+    if (cm) link = next_link(cm, 0u, 0);
+    p->big = where_begin(*in, shard_base, cm ? &link : nullptr, &p->ret);
+    *pending = p.release();
+    AFB_API_END
+}
+
+af_err afx_pending_scalar(afx_pending pending, double *real, double *imag, unsigned *idx) {
+    AFB_API_BEGIN
+    AFB_ARG(1, real != nullptr);
+    std::unique_ptr<Pending> p(pending_of(pending));   // consumed whatever happens below
+    if (p->kind == PEND_WHERE) fail(AF_ERR_ARG, "afx_pending_scalar: the pending op is a where (use afx_pending_where)");
+    if (p->kind == PEND_INDEXED) AFB_ARG(3, idx != nullptr);
+    if ((p->type == c32 || p->type == c64)) AFB_ARG(2, imag != nullptr);
     *real = 0;
     if (imag) *imag = 0;
-    const ShardLink link = next_link(cm, 0u, 0);
-    HostRet ret;
-    reduce_all_into(*in, eff, to, change_nan, nanval, nullptr, &ret, &link);
-    LaunchCtx c = ctx_for_active_device();
-    wait_host_ret(c, ret);
-    decode_scalar(to, ret.host, real, imag);
+    LaunchCtx c = ctx_for_device(p->device);
+    wait_host_ret(c, p->ret);
+    decode_scalar(p->type, p->ret.host, real, imag);
+    if (idx) *idx = p->kind == PEND_INDEXED ? *(const unsigned *)((const char *)p->ret.host + 32) + p->idx_add : 0u;
+    AFB_API_END
+}
+
+af_err afx_pending_where(afx_pending pending, af_array *idx, dim_t *offset, dim_t *total) {
+    AFB_API_BEGIN
+    AFB_ARG(1, idx != nullptr);
+    std::unique_ptr<Pending> p(pending_of(pending));
+    if (p->kind != PEND_WHERE) fail(AF_ERR_ARG, "afx_pending_where: the pending op is not a where");
+    LaunchCtx c = ctx_for_device(p->device);
+    wait_host_ret(c, p->ret);
+    const unsigned long long *rec = (const unsigned long long *)p->ret.host;
+    if (offset) *offset = (dim_t)rec[1];
+    if (total) *total = (dim_t)rec[2];
+    Array *big = p->big;
+    p->big = nullptr;
+    *idx = where_finish(big, (dim_t)rec[0]);
+    AFB_API_END
+}
+
+af_err afx_pending_release(afx_pending pending) {
+    AFB_API_BEGIN
+    if (!pending) return AF_SUCCESS;
+    delete pending_of(pending);   // the kernel may still be running: its output buffer goes back to the stream-ordered pool
+    AFB_API_END
+}
+
+// the blocking forms: issue + collect
+af_err afx_sharded_reduce_all(double *real, double *imag, void *comm, const af_array in_h, int op, bool change_nan,
+                              double nanval) {
+    AFB_API_BEGIN
+    AFB_ARG(0, real != nullptr);
+    comm_of(comm);
+    afx_pending p = nullptr;
+    af_err e = afx_reduce_all_async(&p, comm, in_h, op, change_nan, nanval);
+    if (e != AF_SUCCESS) return e;
+    return afx_pending_scalar(p, real, imag, nullptr);
     AFB_API_END
 }
 
@@ -765,23 +865,11 @@ af_err afx_sharded_ireduce_all(double *real, double *imag, unsigned *idx, void *
     AFB_API_BEGIN
     AFB_ARG(0, real != nullptr);
     AFB_ARG(2, idx != nullptr);
-    AFB_ARG(5, op == OP_MIN || op == OP_MAX);
-    Comm *cm = comm_of(comm);
-    Array *in = from_handle(in_h);
-    AFB_ARG(4, in->ndims() > 0);
-    const af_dtype t = in->info.type;
-    if (t == f16) AFB_TYPE_ERROR(4, t);
-    if (t == c32 || t == c64) AFB_ARG(1, imag != nullptr);
-    check_same_device(*in);
-    *real = 0;
-    if (imag) *imag = 0;
-    const ShardLink link = next_link(cm, shard_base, 0);
-    HostRet ret;
-    ireduce_all_into(*in, (Op)op, nullptr, nullptr, &ret, &link);
-    LaunchCtx c = ctx_for_active_device();
-    wait_host_ret(c, ret);
-    decode_scalar(t, ret.host, real, imag);
-    *idx = *(const unsigned *)((const char *)ret.host + 32);
+    comm_of(comm);
+    afx_pending p = nullptr;
+    af_err e = afx_ireduce_all_async(&p, comm, in_h, op, shard_base);
+    if (e != AF_SUCCESS) return e;
+    return afx_pending_scalar(p, real, imag, idx);
     AFB_API_END
 }
 
@@ -845,12 +933,11 @@ af_err afx_sharded_scan(af_array *out, void *comm, const af_array key_h, const a
 af_err afx_sharded_where(af_array *idx, dim_t *offset, dim_t *total, void *comm, const af_array in_h, unsigned shard_base) {
     AFB_API_BEGIN
     AFB_ARG(0, idx != nullptr);
-    Comm *cm = comm_of(comm);
-    Array *in = from_handle(in_h);
-    AFB_ARG(4, in->elements() > 0);
-    check_same_device(*in);
-    const ShardLink link = next_link(cm, 0u, 0);
-    *idx = where_impl(*in, shard_base, nullptr, &link, offset, total);
+    comm_of(comm);
+    afx_pending p = nullptr;
+    af_err e = afx_where_async(&p, comm, in_h, shard_base);
+    if (e != AF_SUCCESS) return e;
+    return afx_pending_where(p, idx, offset, total);
     AFB_API_END
 }
 

@@ -164,14 +164,17 @@ struct LaunchCtx {
 };
 LaunchCtx ctx_for_active_device();
 
-// A scalar coming back from a kernel WITHOUT cudaMemcpyAsync + cudaStreamSynchronize: the kernel's last thread stores the
-// payload (<= 48 bytes) into a pinned, device-mapped 64-byte record, fences to system scope and raises the record's flag
-// to `seq`; the host spins on the flag (wait_host_ret).  `dev` is a 64-byte device slot paired with the record for
-// kernels that also keep the value on the device (the hit count of af_where).  Records come from a small ring
-// (Scratch::next_host_ret, under the device's op mutex); `seq` is monotone per device and never 0.
+// A scalar coming back from a kernel WITHOUT cudaMemcpyAsync + cudaStreamSynchronize: the kernel's last thread writes the
+// payload (<= 40 bytes) into a pinned, device-mapped wire record as five 16-byte lines {data, seq, data, seq} -- flag in
+// line, so the device needs NO system-scope fence (two MEMBAR.SYS cost 4.3 us per op, measured) -- and the host polls the
+// lines until both flag words of each carry `seq`, then unpacks the payload into `host` (wait_host_ret).  `dev` is a
+// 64-byte device slot paired with the record for kernels that also keep the value on the device (the hit count of
+// af_where).  Records come from a small ring (Scratch::next_host_ret, under the device's op mutex); `seq` is monotone per
+// device and never 0.
+constexpr int kHostRetLines = 5;   // 10 payload words: value at +0 (<= 16 bytes), index at +32
 struct HostRet {
-    void *host;        // pinned payload, as seen by host AND device (UVA)
-    unsigned *flag;    // pinned
+    void *host;        // the unpacked payload (plain host memory; valid after wait_host_ret)
+    void *wire;        // pinned wire record, as seen by host AND device (UVA): kHostRetLines x 16 bytes
     unsigned seq;
     void *dev;         // device slot
 };
@@ -180,7 +183,7 @@ void wait_host_ret(const LaunchCtx &c, const HostRet &r);   // spins; surfaces k
 // One shard of an array spread over several GPUs (one process per GPU): what a kernel needs to exchange its O(1) partial
 // with the other ranks over peer-mapped symmetric buffers and fold the world's partials itself (kernels/peer_comm.cuh).
 struct ShardLink {
-    unsigned long long bufs[8];   // device address of every rank's symmetric buffer (>= 1088 bytes, zeroed once)
+    unsigned long long bufs[8];   // device address of every rank's symmetric buffer (>= 2048 bytes, zeroed once)
     int rank, world;
     unsigned epoch;               // 1, 2, 3, ... identical on every rank for the same op
     unsigned idx_base;            // global index of the shard's first element
@@ -248,9 +251,10 @@ struct Scratch {
     unsigned long long *chain_ticket = nullptr;                 // monotone 64-bit ticket of the persistent chained kernels
     unsigned long long chain_base = 0;                          // host mirror: its value once all enqueued launches are done
     unsigned epoch = 0, wepoch = 0;                             // generation tags of the two descriptor arrays
-    void *host_pinned = nullptr;   size_t host_pinned_bytes = 0;  // pinned: [0,4096) peer exchange, [4096,8192) HostRet ring
+    void *host_pinned = nullptr;   size_t host_pinned_bytes = 0;  // pinned: [0,4096) peer exchange, [4096,12288) HostRet wire ring
     void *dev_scalar = nullptr;                                 // 64 device slots of 64 bytes (paired with the HostRet ring)
     unsigned ret_seq = 0;                                       // last HostRet sequence number handed out
+    unsigned char ret_plain[64][64] = {};                       // unpacked payloads of the HostRet ring
     HostRet next_host_ret();                                    // call under the device's op mutex
 
     void *need_partials(size_t bytes);

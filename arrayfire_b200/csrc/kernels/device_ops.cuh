@@ -279,10 +279,14 @@ AFB_DI unsigned ld_acquire_sys(const unsigned *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// raise the flag of a pinned host record after its payload has been stored by THIS thread (common.hpp: HostRet)
-AFB_DI void host_ret_publish(unsigned *flag, unsigned seq) {
-    __threadfence_system();
-    st_release_sys(flag, seq);
+// ONE thread: the 10 payload words of a host result -> the pinned wire record (common.hpp: HostRet), flag in line: five
+// 16-byte stores, no fence
+AFB_DI void host_ret_send(void *wire, unsigned seq, const unsigned *w) {
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"((char *)wire + 16 * j), "r"(w[2 * j]), "r"(seq),
+                     "r"(w[2 * j + 1]), "r"(seq)
+                     : "memory");
 }
 AFB_DI unsigned long long ld_relaxed64(const unsigned long long *p) {
     unsigned long long v;

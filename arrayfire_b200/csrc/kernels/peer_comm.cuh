@@ -5,13 +5,18 @@
 // ~50 us per op, more than the kernels themselves once 2^30 elements are split over 8 GPUs (3.65x at 8 GPUs).  Now the
 // LAST thread of the producing kernel (the last-arriver CTA of span_kernel, the walker of the last tile of the pipelined
 // scan / compaction kernels) does the exchange itself over NVLink / NVSwitch peer memory:
-//   1. stores its 64-byte record into slot [rank] of EVERY rank's symmetric buffer (four 16-byte peer stores),
-//   2. raises flag [rank] = epoch there (release, system scope -- orders the record before the flag),
-//   3. waits until the `world` flags in its OWN buffer carry the epoch (acquire, system scope),
-//   4. folds the records in RANK ORDER (deterministic, identical on every rank, equal to the serial answer) and hands the
-//      result to the device output and / or the pinned host record of the call.
-// One launch, no collective-library call, no host round trip between partial and combine.  Slots and flags are
-// double-buffered by epoch parity: a rank reaches epoch e+2 only after every peer has published e+1, i.e. consumed e.
+//   1. sends its record (<= 64 bytes) into slot [rank] of EVERY rank's symmetric buffer,
+//   2. collects the records of the other ranks from its OWN buffer as they arrive,
+//   3. folds them in RANK ORDER (deterministic, identical on every rank, equal to the serial answer) and hands the result
+//      to the device output and / or the pinned host record of the call.
+// One launch, no collective-library call, no host round trip between partial and combine.
+//
+// Wire format ("LL": flag in line, no fences): a record travels as 16-byte lines {data, epoch, data, epoch}, each written
+// with ONE 16-byte store.  The receiver polls a line until both flag words carry the epoch of the op -- the data words of a
+// line that shows the right flags are valid (8-byte store atomicity is all that is assumed, as in NCCL's LL protocol), so
+// neither side needs a system-scope fence (round 2, first cut: st.release.sys per peer = one MEMBAR.SYS per peer, 16 us at
+// 2 GPUs and 35 us at 8 per op).  Slots are double-buffered by epoch parity: a rank reaches epoch e+2 only after every peer
+// has published e+1, i.e. after the kernel that consumed e has finished.  The buffers start zeroed and epochs are never 0.
 // The buffers are peer-mapped once by the host layer (torch.distributed._symmetric_memory or cuMem + IPC handles).
 #pragma once
 
@@ -20,9 +25,9 @@
 namespace afb {
 
 constexpr int kPeerMax = 8;
-constexpr int kPeerRecord = 64;                                  // bytes per rank and parity
-constexpr int kPeerFlagOff = 2 * kPeerMax * kPeerRecord;         // flags follow the 2 x 8 records
-constexpr int kPeerBufBytes = kPeerFlagOff + 2 * kPeerMax * 4;   // 1088
+constexpr int kPeerRecord = 64;                                    // payload bytes per rank and parity
+constexpr int kPeerSlotBytes = 2 * kPeerRecord;                    // on the wire: every 8 payload bytes ride with 8 flag bytes
+constexpr int kPeerBufBytes = 2 * kPeerMax * kPeerSlotBytes;       // 2048
 
 struct PeerComm {
     unsigned long long bufs[kPeerMax];   // device addresses of every rank's symmetric buffer (index = rank)
@@ -47,69 +52,84 @@ inline PeerComm peer_comm_of(const ShardLink *link) {
 }
 
 struct alignas(16) PeerRecord {
-    uint4 q[4];
+    uint w[16];
 };
 
-AFB_DI void st_peer16(void *dst, const uint4 &v) {
-    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-AFB_DI uint4 ld_peer16(const void *src) {
-    uint4 v;
-    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
-    return v;
+AFB_DI char *peer_slot(const PeerComm &c, int owner, int writer) {
+    const int par = (int)(c.epoch & 1u);
+    return reinterpret_cast<char *>(c.bufs[owner]) + (size_t)((par * kPeerMax + writer) * kPeerSlotBytes);
 }
 
-// ONE thread: publish this rank's record to every rank (itself included) and raise the flags
-AFB_DI void peer_publish(const PeerComm &c, const PeerRecord &rec) {
-    const int par = (int)(c.epoch & 1u);
-    for (int p = 0; p < c.world; p++) {
-        char *slot = reinterpret_cast<char *>(c.bufs[p]) + (size_t)((par * kPeerMax + c.rank) * kPeerRecord);
+// ONE thread: the first NW words of this rank's record -> rank `dst`'s buffer (fire and forget)
+template<int NW> AFB_DI void peer_send(const PeerComm &c, int dst, const PeerRecord &rec) {
+    static_assert(NW >= 1 && NW <= 16, "a peer record carries at most 64 bytes");
+    char *slot = peer_slot(c, dst, c.rank);
 #pragma unroll
-        for (int j = 0; j < 4; j++) st_peer16(slot + 16 * j, rec.q[j]);
-    }
-    for (int p = 0; p < c.world; p++) {
-        unsigned *f = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(c.bufs[p]) + kPeerFlagOff) + par * kPeerMax + c.rank;
-        st_release_sys(f, c.epoch);   // release: this thread's record stores above are visible before the flag
-    }
-}
-
-// ONE thread: wait until ranks [0, upto) have published this epoch into OUR buffer.  Ranks may legitimately arrive
-// seconds apart (host-side skew); never arriving is a protocol error -> trap instead of hanging the device.
-AFB_DI void peer_wait(const PeerComm &c, int upto) {
-    const int par = (int)(c.epoch & 1u);
-    const unsigned *flags = reinterpret_cast<const unsigned *>(reinterpret_cast<const char *>(c.bufs[c.rank]) + kPeerFlagOff) + par * kPeerMax;
-    for (int r = 0; r < upto; r++) {
-        unsigned long long spins = 0;
-        while (ld_acquire_sys(flags + r) != c.epoch) {
-            if (++spins > (1ull << 31)) __trap();
-        }
+    for (int j = 0; j < (NW + 1) / 2; j++) {
+        const uint d0 = rec.w[2 * j], d1 = (2 * j + 1 < 16) ? rec.w[2 * j + 1] : 0u;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(slot + 16 * j), "r"(d0), "r"(c.epoch), "r"(d1), "r"(c.epoch)
+                     : "memory");
     }
 }
 
-// record of rank r in OUR buffer (valid after peer_wait covered r)
-AFB_DI PeerRecord peer_read(const PeerComm &c, int r) {
-    const int par = (int)(c.epoch & 1u);
-    const char *slot = reinterpret_cast<const char *>(c.bufs[c.rank]) + (size_t)((par * kPeerMax + r) * kPeerRecord);
+// ONE thread: wait for rank `src`'s record of this epoch in OUR buffer.  Ranks may legitimately arrive seconds apart
+// (host-side skew); never arriving is a protocol error -> trap instead of hanging the device.
+template<int NW> AFB_DI PeerRecord peer_recv(const PeerComm &c, int src) {
+    const char *slot = peer_slot(c, c.rank, src);
     PeerRecord rec;
 #pragma unroll
-    for (int j = 0; j < 4; j++) rec.q[j] = ld_peer16(slot + 16 * j);
+    for (int j = 0; j < 8; j++) rec.w[2 * j] = rec.w[2 * j + 1] = 0u;
+#pragma unroll
+    for (int j = 0; j < (NW + 1) / 2; j++) {
+        uint d0, f0, d1, f1;
+        unsigned long long spins = 0;
+        while (true) {
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(slot + 16 * j) : "memory");
+            if (f0 == c.epoch && f1 == c.epoch) break;
+            if (++spins > (1ull << 31)) __trap();
+        }
+        rec.w[2 * j] = d0;
+        rec.w[2 * j + 1] = d1;
+    }
     return rec;
+}
+
+// ONE thread does the whole exchange: sends to every rank (itself included), then collects ranks [0, upto) into out[]
+template<int NW> AFB_DI void peer_exchange_serial(const PeerComm &c, const PeerRecord &mine, PeerRecord *out, int upto) {
+    for (int p = 0; p < c.world; p++) peer_send<NW>(c, p, mine);
+    for (int r = 0; r < upto; r++) out[r] = peer_recv<NW>(c, r);
+}
+
+// The first WARP of a CTA does the exchange (all 32 lanes call; `mine` is read from lane 0): lane r sends to rank r and
+// collects rank r's record -- the stores and the polls of all ranks overlap.  The records land in `sm` (shared memory,
+// kPeerMax entries); valid for the whole warp on return.
+template<int NW> AFB_DI void peer_exchange_warp(const PeerComm &c, const PeerRecord &mine, PeerRecord *sm) {
+    const int lane = (int)(threadIdx.x & 31u);
+    PeerRecord rec;
+#pragma unroll
+    for (int j = 0; j < 16; j++) rec.w[j] = j < NW ? __shfl_sync(0xffffffffu, mine.w[j], 0) : 0u;
+    if (lane < c.world) {
+        peer_send<NW>(c, lane, rec);
+        sm[lane] = peer_recv<NW>(c, lane);
+    }
+    __syncwarp();
 }
 
 // typed views of a record: a POD of at most 48 bytes at offset 0, 16 more bytes of op-specific extras at offset 48
 template<typename T> AFB_DI void rec_put(PeerRecord &rec, const T &v, int byte_off = 0) {
-    static_assert(sizeof(T) <= 48, "a peer record carries at most 48 bytes of payload");
-    union U { PeerRecord r; char b[kPeerRecord]; AFB_DI U() {} } u;
-    u.r = rec;
-    const char *s = reinterpret_cast<const char *>(&v);
-    for (int i = 0; i < (int)sizeof(T); i++) u.b[byte_off + i] = s[i];
-    rec = u.r;
+    static_assert(sizeof(T) <= 48, "a peer record carries at most 48 bytes of payload (+ 16 of op-specific extras)");
+    static_assert(sizeof(T) % 4 == 0 || sizeof(T) < 4, "record fields are whole words (or one sub-word scalar)");
+    union V { T t; uint w[(sizeof(T) + 3) / 4]; AFB_DI V() {} } u;
+#pragma unroll
+    for (int i = 0; i < (int)((sizeof(T) + 3) / 4); i++) u.w[i] = 0u;
+    u.t = v;
+#pragma unroll
+    for (int i = 0; i < (int)((sizeof(T) + 3) / 4); i++) rec.w[byte_off / 4 + i] = u.w[i];
 }
 template<typename T> AFB_DI T rec_get(const PeerRecord &rec, int byte_off = 0) {
-    union U { PeerRecord r; char b[kPeerRecord]; AFB_DI U() {} } u;
-    u.r = rec;
-    union V { T t; char b[sizeof(T)]; AFB_DI V() {} } v;
-    for (int i = 0; i < (int)sizeof(T); i++) v.b[i] = u.b[byte_off + i];
+    union V { T t; uint w[(sizeof(T) + 3) / 4]; AFB_DI V() {} } v;
+#pragma unroll
+    for (int i = 0; i < (int)((sizeof(T) + 3) / 4); i++) v.w[i] = rec.w[byte_off / 4 + i];
     return v.t;
 }
 

@@ -36,8 +36,7 @@ struct RbkCountArgs {
     dim_t n, ntiles;
     uint *tile_base;                 // [ntiles + 1]
     uint *ticket;                    // self-resetting arrival counter
-    unsigned long long *host_total;  // pinned record (common.hpp HostRet)
-    uint *host_flag;
+    void *host_wire;                 // pinned wire record (common.hpp HostRet)
     uint host_seq;
 };
 
@@ -117,8 +116,11 @@ static __global__ void __launch_bounds__(kRbkThreads) rbk_count_kernel(const Rbk
     if (tid == kRbkThreads - 1) {
         a.tile_base[a.ntiles] = run;   // per >= 1 element for the low threads; the last thread's `run` is the total
         *a.ticket = 0u;
-        *a.host_total = (unsigned long long)run;
-        host_ret_publish(a.host_flag, a.host_seq);
+        uint w[10];
+#pragma unroll
+        for (int j = 0; j < 10; j++) w[j] = 0u;
+        w[0] = (uint)(unsigned long long)run, w[1] = (uint)((unsigned long long)run >> 32);
+        host_ret_send(a.host_wire, a.host_seq, w);
     }
 }
 

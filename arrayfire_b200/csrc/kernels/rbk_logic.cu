@@ -37,8 +37,7 @@ void launch_rbk_count(const LaunchCtx &c, const void *keys, dim_t n, unsigned *t
     a.ntiles = (n + kRbkTile - 1) / kRbkTile;
     a.tile_base = tile_base;
     a.ticket = c.scratch->need_tickets(2) + 1;   // ticket 0 belongs to the whole-array reductions
-    a.host_total = (unsigned long long *)ret.host;
-    a.host_flag = ret.flag;
+    a.host_wire = ret.wire;
     a.host_seq = ret.seq;
     dim_t grid = a.ntiles;
     const dim_t cap = (dim_t)c.sms * 8;

@@ -85,7 +85,17 @@ void run_cols(const LaunchCtx &c, const View &in, const typename P::Params &prm,
     a.in = (const In *)in.ptr;
     a.g = g;
     a.all = 0;
-    const int ctas_per_sm = env_int("AFB200_REDUCE_CTAS_PER_SM", 8);
+    // ONE wave: the grid never exceeds what is resident at once (a 48-register instantiation holds 5 CTAs per SM, not 8:
+    // asking for 8 left a thin second wave that cannot saturate HBM -- measured -12 % on the 2^30 f32 sum)
+    static int resident[64] = {0};
+    const int dv = c.device & 63;
+    if (!resident[dv]) {
+        int occ = 0;
+        AFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, span_kernel<P>, kThreads, 0));
+        resident[dv] = occ < 1 ? 1 : occ;
+    }
+    int ctas_per_sm = env_int("AFB200_REDUCE_CTAS_PER_SM", 8);
+    if (ctas_per_sm > resident[dv]) ctas_per_sm = resident[dv];
     const dim_t target = (dim_t)c.sms * ctas_per_sm;
     dim_t bpc = 1;
     if (g.ncols < target) {
@@ -110,9 +120,8 @@ void run_cols(const LaunchCtx &c, const View &in, const typename P::Params &prm,
     a.out = out;
     a.partials = nullptr;
     a.tickets = nullptr;
-    a.host_flag = nullptr;
+    a.host_wire = nullptr;
     a.host_seq = 0;
-    a.host_out = out;
     a.comm = peer_comm_of(nullptr);
     a.idx_base = 0;
     a.comm_mode = 0;
@@ -151,7 +160,17 @@ void run_all(const LaunchCtx &c, const View &in, const typename P::Params &prm, 
     a.in = (const In *)in.ptr;
     a.g = g;
     a.all = 1;
-    const int ctas_per_sm = env_int("AFB200_REDUCE_CTAS_PER_SM", 8);
+    // ONE wave: the grid never exceeds what is resident at once (a 48-register instantiation holds 5 CTAs per SM, not 8:
+    // asking for 8 left a thin second wave that cannot saturate HBM -- measured -12 % on the 2^30 f32 sum)
+    static int resident[64] = {0};
+    const int dv = c.device & 63;
+    if (!resident[dv]) {
+        int occ = 0;
+        AFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, span_kernel<P>, kThreads, 0));
+        resident[dv] = occ < 1 ? 1 : occ;
+    }
+    int ctas_per_sm = env_int("AFB200_REDUCE_CTAS_PER_SM", 8);
+    if (ctas_per_sm > resident[dv]) ctas_per_sm = resident[dv];
     const dim_t target = (dim_t)c.sms * ctas_per_sm;
     const dim_t quantum = (dim_t)VecN<In>::value * 32;
     const dim_t min_chunk = 16384;
@@ -176,9 +195,8 @@ void run_all(const LaunchCtx &c, const View &in, const typename P::Params &prm, 
     a.out = out;
     a.partials = (Slot<Acc> *)c.scratch->need_partials((size_t)(grid / csize) * sizeof(Slot<Acc>));
     a.tickets = c.scratch->need_tickets(1);
-    a.host_flag = ret ? ret->flag : nullptr;
+    a.host_wire = ret ? ret->wire : nullptr;
     a.host_seq = ret ? ret->seq : 0u;
-    a.host_out = P::host_out(ret ? ret->host : nullptr);
     a.comm = peer_comm_of(link);
     a.idx_base = link ? link->idx_base : 0u;
     a.comm_mode = link ? link->mode : 0;
@@ -191,6 +209,18 @@ void run_all(const LaunchCtx &c, const View &in, const typename P::Params &prm, 
 }
 
 // ---- reduce along dim > 0 ---------------------------------------------------------------------------
+// CTAs of dim_kernel<P, VEC> resident per SM (cached per device)
+template<typename P, int VEC> int dim_resident(int device) {
+    static int resident[64] = {0};
+    const int dv = device & 63;
+    if (!resident[dv]) {
+        int occ = 0;
+        AFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dim_kernel<P, VEC>, 32 * kDimRows, 0));
+        resident[dv] = occ < 1 ? 1 : occ;
+    }
+    return resident[dv];
+}
+
 template<typename P>
 void run_dim(const LaunchCtx &c, const View &in, int dim, const typename P::Params &prm, const typename P::Out &out) {
     typedef typename P::In In;
@@ -230,7 +260,13 @@ void run_dim(const LaunchCtx &c, const View &in, int dim, const typename P::Para
     // (tools/dim_sweep.py on B200, 8192 columns: 8192 rows 4349 GB/s with 16-byte vs 3526 with 8-byte vectors;
     //  4096 rows 2473 vs 2901; 1024 rows 641 vs 1024; scalar lanes never win)
     const dim_t want_ctas = (dim_t)c.sms * 3;
-    if (vec_ok && VH > 1 && ((g.d0 + 32 * V - 1) / (32 * V)) * gz * 8 < want_ctas) vec = VH;
+    // two-stage split below (keeps the full vectors): ONE full wave of CTAs -- 1.5 waves measured 30 % slower than 1
+    int gsplit_per_sm = env_int("AFB200_DIM_GSPLIT_CTAS", 4);
+    if (gsplit_per_sm > 0) {
+        const int occ = (vec == V && V > 1) ? dim_resident<P, V>(c.device) : dim_resident<P, 1>(c.device);
+        if (gsplit_per_sm > occ) gsplit_per_sm = occ;
+    }
+    if (gsplit_per_sm <= 0 && vec_ok && VH > 1 && ((g.d0 + 32 * V - 1) / (32 * V)) * gz * 8 < want_ctas) vec = VH;
     { const int f = env_int("AFB200_DIM_VEC", 0); if (f == 1 || (f == VH && vec_ok) || (f == V && vec_ok)) vec = f; }
     const dim_t gx = (g.d0 + 32 * vec - 1) / (32 * vec);
     // split the reduced axis across a cluster when the grid would not fill the machine
@@ -238,17 +274,40 @@ void run_dim(const LaunchCtx &c, const View &in, int dim, const typename P::Para
     const dim_t want = (dim_t)c.sms * 4;
     while (splits < 8 && gx * gz * splits < want && g.len / (splits * 2) >= 4 * kDimRows) splits *= 2;
     if (env_int("AFB200_CLUSTER", 2) <= 1) splits = 1;
+    // ... and when even 8 cluster splits leave SMs idle (1024 rows x 8192 columns: 64 CTAs, 1.75 TB/s): as many splits as it
+    // takes to give every SM `per_sm` CTAs, combined through global partials by the last arriver of each tile
+    a.gsplits = 1;
+    a.partials = nullptr;
+    a.tickets = nullptr;
+    {
+        typedef typename P::Acc Acc;
+        const int per_sm = gsplit_per_sm;
+        const dim_t ntiles = gx * g.na * g.nb;
+        if (per_sm > 0 && gx * gz * 8 < (dim_t)c.sms * 4 && g.na * g.nb <= 65535 && g.len >= 16 * kDimRows) {
+            dim_t gs = ((dim_t)c.sms * per_sm + ntiles - 1) / ntiles;
+            const dim_t max_gs = g.len / (2 * kDimRows);          // at least two rows per warp
+            if (gs > max_gs) gs = max_gs;
+            if (gs > 1024) gs = 1024;
+            if (gs > 8) {
+                splits = (int)gs;
+                a.gsplits = (int)gs;
+                a.partials = (Slot<Acc> *)c.scratch->need_partials((size_t)ntiles * gs * 32 * vec * sizeof(Slot<Acc>));
+                a.tickets = c.scratch->need_tickets((size_t)ntiles);
+            }
+        }
+    }
     a.splits = splits;
+    const bool clustered = splits > 1 && a.gsplits == 1;
     dim3 grid((unsigned)gx, (unsigned)splits, (unsigned)gz), block(32, kDimRows, 1);
     if (gx > 0x7fffffffLL) fail(AF_ERR_SIZE, "reduce: dim 0 too large");
     if (vec == V && V > 1) {
-        if (splits > 1) launch_with_cluster(dim_kernel<P, V>, grid, block, dim3(1, splits, 1), c.stream, a);
+        if (clustered) launch_with_cluster(dim_kernel<P, V>, grid, block, dim3(1, splits, 1), c.stream, a);
         else dim_kernel<P, V><<<grid, block, 0, c.stream>>>(a);
     } else if (vec == VH && VH > 1) {
-        if (splits > 1) launch_with_cluster(dim_kernel<P, VH>, grid, block, dim3(1, splits, 1), c.stream, a);
+        if (clustered) launch_with_cluster(dim_kernel<P, VH>, grid, block, dim3(1, splits, 1), c.stream, a);
         else dim_kernel<P, VH><<<grid, block, 0, c.stream>>>(a);
     } else {
-        if (splits > 1) launch_with_cluster(dim_kernel<P, 1>, grid, block, dim3(1, splits, 1), c.stream, a);
+        if (clustered) launch_with_cluster(dim_kernel<P, 1>, grid, block, dim3(1, splits, 1), c.stream, a);
         else dim_kernel<P, 1><<<grid, block, 0, c.stream>>>(a);
     }
     note_launches(1);

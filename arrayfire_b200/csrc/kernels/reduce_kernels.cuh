@@ -46,7 +46,7 @@ template<int OP, typename Ti, typename To> struct ValPolicy {
     typedef Rule<OP, Ti, Acc> R;
     typedef ValParams Params;
     struct Out { To *val; };
-    static Out host_out(void *rec) { return Out{(To *)rec}; }
+    __host__ __device__ static Out host_out(void *rec) { return Out{(To *)rec}; }
     AFB_DI static Acc init() { return R::init(); }
     AFB_DI static Acc load(const Params &p, In x, uint) {
         Acc v = R::pre(x);
@@ -102,7 +102,7 @@ template<int OP, typename T> struct ArgPolicy {
     typedef Arg<T> Acc;
     typedef ArgParams Params;
     struct Out { T *val; uint *loc; };
-    static Out host_out(void *rec) { return Out{(T *)rec, (uint *)((char *)rec + 32)}; }   // value at +0, index at +32
+    __host__ __device__ static Out host_out(void *rec) { return Out{(T *)rec, (uint *)((char *)rec + 32)}; }   // value at +0, index at +32
     // Internally element i carries rank i+1, so that "no candidate yet" (rank 0 for min, UINT_MAX for max)
     // loses every tie against a real element -- distinct values can share an ordering key (b8 compares
     // `v > 0`, 64-bit integers compare as double, complex compares magnitudes).
@@ -183,7 +183,7 @@ template<int OP, typename T> struct FirstPolicy {
     typedef Arg<T> Acc;
     typedef ValParams Params;
     struct Out { T *val; };
-    static Out host_out(void *rec) { return Out{(T *)rec}; }
+    __host__ __device__ static Out host_out(void *rec) { return Out{(T *)rec}; }
     AFB_DI static T ident() { return OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(); }
     AFB_DI static Acc init() { return Acc{ident(), 0u}; }
     AFB_DI static Acc load(const Params &, In x, uint idx) { return Acc{is_nan<T>(x) ? ident() : x, idx + 1u}; }
@@ -327,8 +327,7 @@ struct SpanArgs {
     uint *tickets;               // [ncols] or [1]
     // "all" mode, optional: the final value also goes to a pinned host record and its flag is raised (no D2H copy, no
     // stream synchronisation on the host side: common.hpp HostRet)
-    typename P::Out host_out;
-    uint *host_flag;
+    void *host_wire;
     uint host_seq;
     // "all" mode, optional (comm.world > 1): `in` is one shard of an array spread over several GPUs.  The thread that
     // holds the shard's partial exchanges it with the other ranks over peer memory (peer_comm.cuh) and folds the world's
@@ -339,30 +338,49 @@ struct SpanArgs {
     int comm_mode;
 };
 
-// the cross-rank step of span_kernel (one thread)
+// ONE thread: the result as the output type (value at +0, index at +32) -> the pinned wire record of the call
 template<typename P>
-AFB_DI typename P::Acc span_exchange(const SpanArgs<P> &a, typename P::Acc mine) {
+AFB_DI void span_host_send(const SpanArgs<P> &a, typename P::Acc v) {
+    alignas(16) uint w[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) w[j] = 0u;
+    P::store(P::host_out(w), 0, v);
+    host_ret_send(a.host_wire, a.host_seq, w);
+}
+
+// the cross-rank step of span_kernel: called by the whole first warp, `mine` is lane 0's; the result is valid in lane 0
+template<typename P>
+AFB_DI typename P::Acc span_exchange(const SpanArgs<P> &a, typename P::Acc mine, PeerRecord *sm) {
     typedef typename P::Acc Acc;
+    constexpr int NW = (int)((sizeof(Acc) + 3) / 4);
     PeerRecord rec;
-    rec.q[0] = rec.q[1] = rec.q[2] = rec.q[3] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int j = 0; j < 16; j++) rec.w[j] = 0u;
     rec_put(rec, P::globalize(mine, a.idx_base));
-    peer_publish(a.comm, rec);
-    peer_wait(a.comm, a.comm.world);
+    peer_exchange_warp<NW>(a.comm, rec, sm);
     const int upto = a.comm_mode == 1 ? a.comm.rank : a.comm.world;
     Acc g = P::init();
     for (int r = 0; r < upto; r++) {
-        const Acc v = rec_get<Acc>(peer_read(a.comm, r));
+        const Acc v = rec_get<Acc>(sm[r]);
         g = (r == 0) ? v : P::join(g, v);
     }
     return g;
 }
 
+// 4-byte accumulators (the f32 / s32 / u32 sums, counts): 8 CTAs of 256 threads per SM = 32 registers per thread, full
+// occupancy for the streaming loop; wider accumulators and the index reductions keep the registers they need
+// (5 CTAs = 51 registers, 4 CTAs = 64: about what ptxas chose unprompted -- an explicit "1" makes it spend up to 92)
+template<typename P> struct SpanMinCtas {
+    static constexpr int value = sizeof(typename P::Acc) <= 4 ? 8 : sizeof(typename P::Acc) <= 8 ? 5 : 4;
+};
+
 template<typename P>
-__global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
+__global__ void __launch_bounds__(kThreads, SpanMinCtas<P>::value) span_kernel(const SpanArgs<P> a) {
     typedef typename P::Acc Acc;
     __shared__ Acc sm[32];
     __shared__ Acc sm_cluster[8];
     __shared__ int sm_last;
+    __shared__ PeerRecord sm_peer[kPeerMax];   // sharded arrays: the world's records (peer_comm.cuh)
     const int tid = threadIdx.x;
 
     Acc acc = P::init();
@@ -404,13 +422,10 @@ __global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
 
     // ---- level 3: one partial per (cluster of) CTA(s); the last arriver folds them in index order
     if (nparts == 1) {
+        if (a.comm.world > 1 && tid < 32) acc = span_exchange<P>(a, acc, sm_peer);
         if (tid == 0) {
-            if (a.comm.world > 1) acc = span_exchange<P>(a, acc);
             P::store(a.out, (size_t)col, acc);
-            if (a.host_flag) {
-                P::store(a.host_out, 0, acc);
-                host_ret_publish(a.host_flag, a.host_seq);
-            }
+            if (a.host_wire) span_host_send<P>(a, acc);
         }
         return;
     }
@@ -428,14 +443,11 @@ __global__ void __launch_bounds__(kThreads) span_kernel(const SpanArgs<P> a) {
     Acc fin = P::init();
     for (uint i = tid; i < nparts; i += kThreads) fin = P::join(fin, load_cg(slots + i));
     fin = block_reduce<P>(fin, sm);
+    if (a.comm.world > 1 && tid < 32) fin = span_exchange<P>(a, fin, sm_peer);
     if (tid == 0) {
-        if (a.comm.world > 1) fin = span_exchange<P>(a, fin);
         P::store(a.out, (size_t)col, fin);
         *ticket = 0u;  // self-reset: the next launch on this stream finds it clean
-        if (a.host_flag) {
-            P::store(a.host_out, 0, fin);
-            host_ret_publish(a.host_flag, a.host_seq);
-        }
+        if (a.host_wire) span_host_send<P>(a, fin);
     }
 }
 
@@ -527,6 +539,11 @@ struct DimArgs {
     int splits;         // CTAs along the reduced axis (= cluster size in y)
     typename P::Params prm;
     typename P::Out out;
+    // two-stage split (gsplits > 1, then splits == gridDim.y == gsplits and there is no cluster): every CTA leaves its
+    // 32 x VEC partial in `partials`, the last arriver of a tile (ticket) folds the gsplits partials in split order
+    int gsplits;
+    Slot<typename P::Acc> *partials;
+    uint *tickets;
 };
 
 constexpr int kDimRows = 8;  // warps per CTA; each warp owns every kDimRows-th row of the CTA's slice
@@ -537,6 +554,7 @@ __global__ void __launch_bounds__(32 * kDimRows) dim_kernel(const DimArgs<P> a) 
     typedef typename P::In In;
     __shared__ Acc sm[kDimRows][32 * VEC + 1];
     __shared__ Acc sm_cluster[8][32 * VEC];
+    __shared__ int sm_last;
     const int lane = threadIdx.x, wy = threadIdx.y;
     const dim_t x0 = ((dim_t)blockIdx.x * 32 + lane) * VEC;  // first dim-0 element of this thread
     const int split = blockIdx.y;
@@ -580,6 +598,39 @@ __global__ void __launch_bounds__(32 * kDimRows) dim_kernel(const DimArgs<P> a) 
                 acc[k] = v;
             }
         }
+        // narrow dim 0 (few x blocks): many splits of the reduced axis, combined through global partials
+        if (a.gsplits > 1) {
+            const size_t tile = (size_t)batch * gridDim.x + blockIdx.x;
+            Slot<Acc> *part = a.partials + tile * (size_t)a.gsplits * (32 * VEC);
+            if (wy == 0) {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) part[(size_t)split * (32 * VEC) + lane * VEC + k].v = acc[k];
+                __threadfence();
+            }
+            __syncthreads();
+            if (wy == 0 && lane == 0) sm_last = (atomicAdd(a.tickets + tile, 1u) == (uint)a.gsplits - 1u);
+            __syncthreads();
+            if (!sm_last) continue;            // CTA-uniform
+            __threadfence();
+#pragma unroll
+            for (int k = 0; k < VEC; k++) acc[k] = P::init();
+            for (int s = wy; s < a.gsplits; s += kDimRows)
+#pragma unroll
+                for (int k = 0; k < VEC; k++) acc[k] = P::join(acc[k], load_cg(part + (size_t)s * (32 * VEC) + lane * VEC + k));
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < VEC; k++) sm[wy][lane * VEC + k] = acc[k];
+            __syncthreads();
+            if (wy == 0) {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    Acc v = sm[0][lane * VEC + k];
+                    for (int y = 1; y < kDimRows; y++) v = P::join(v, sm[y][lane * VEC + k]);
+                    acc[k] = v;
+                }
+                if (lane == 0) a.tickets[tile] = 0u;   // self-reset: the next launch finds it clean
+            }
+        } else
         // combine the CTAs of the cluster (splits of the reduced axis)
         if (a.splits > 1) {
             cg::cluster_group cluster = cg::this_cluster();

@@ -67,22 +67,22 @@ __global__ void __launch_bounds__(256) sbk_exchange_fixup_kernel(T *out, dim_t n
     __shared__ unsigned long long sm_count;
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
-            PeerRecord rec;
-            rec.q[0] = rec.q[1] = rec.q[2] = rec.q[3] = make_uint4(0u, 0u, 0u, 0u);
+            PeerRecord rec, all_recs[kPeerMax];
+#pragma unroll
+            for (int j = 0; j < 16; j++) rec.w[j] = 0u;
             const T tail = reinterpret_cast<const Slot<T> *>(summary)->v;
             const uint has_head = *reinterpret_cast<const uint *>(summary + 16);
             rec_put(rec, tail, 0);
             rec_put(rec, has_head, 16);
             rec_put(rec, (unsigned long long)keys[0], 32);
             rec_put(rec, (unsigned long long)keys[n - 1], 40);
-            peer_publish(comm, rec);
-            peer_wait(comm, comm.world);
+            peer_exchange_serial<12>(comm, rec, all_recs, comm.rank + 1);   // only the LOWER ranks' records are needed
             // carry-in of this rank: the tail of rank-1 when the key continues across the boundary, extended by that
             // shard's own carry while it is a single run of the same key (a run spanning several shards)
             bool have = false;
             T carry = R::init();
             for (int r = 1; r <= comm.rank; r++) {
-                const PeerRecord prev = peer_read(comm, r - 1), cur = peer_read(comm, r);
+                const PeerRecord &prev = all_recs[r - 1], &cur = all_recs[r];
                 if (rec_get<unsigned long long>(prev, 40) != rec_get<unsigned long long>(cur, 32)) {
                     have = false;     // the key changes at this boundary: nothing is carried across it
                     continue;

@@ -26,8 +26,7 @@ struct WhereArgs {
     uint epoch;
     uint base;                     // added to every index (sharded where)
     int vec_ok;
-    unsigned long long *host_total;   // optional pinned copy of the count + flag (common.hpp HostRet)
-    uint *host_flag;
+    void *host_wire;                  // optional pinned wire record of the count (common.hpp HostRet)
     uint host_seq;
     PeerComm comm;                    // world > 1: `in` is one shard, the counts are exchanged in the kernel
 };
@@ -38,14 +37,14 @@ struct WhereArgs {
 template<typename A> AFB_DI void where_publish_total(const A &a, unsigned long long total) {
     unsigned long long offset = 0, all = total;
     if (a.comm.world > 1) {
-        PeerRecord rec;
-        rec.q[0] = rec.q[1] = rec.q[2] = rec.q[3] = make_uint4(0u, 0u, 0u, 0u);
+        PeerRecord rec, all_recs[kPeerMax];
+#pragma unroll
+        for (int j = 0; j < 16; j++) rec.w[j] = 0u;
         rec_put(rec, total);
-        peer_publish(a.comm, rec);
-        peer_wait(a.comm, a.comm.world);
+        peer_exchange_serial<2>(a.comm, rec, all_recs, a.comm.world);
         all = 0;
         for (int r = 0; r < a.comm.world; r++) {
-            const unsigned long long c = rec_get<unsigned long long>(peer_read(a.comm, r));
+            const unsigned long long c = rec_get<unsigned long long>(all_recs[r]);
             if (r < a.comm.rank) offset += c;
             all += c;
         }
@@ -53,11 +52,13 @@ template<typename A> AFB_DI void where_publish_total(const A &a, unsigned long l
     a.total[0] = total;
     a.total[1] = offset;
     a.total[2] = all;
-    if (a.host_flag) {
-        a.host_total[0] = total;
-        a.host_total[1] = offset;
-        a.host_total[2] = all;
-        host_ret_publish(a.host_flag, a.host_seq);
+    if (a.host_wire) {
+        uint w[10];
+        w[0] = (uint)total, w[1] = (uint)(total >> 32);
+        w[2] = (uint)offset, w[3] = (uint)(offset >> 32);
+        w[4] = (uint)all, w[5] = (uint)(all >> 32);
+        w[6] = w[7] = w[8] = w[9] = 0u;
+        host_ret_send(a.host_wire, a.host_seq, w);
     }
 }
 
@@ -186,8 +187,7 @@ static void run_where_simple(const LaunchCtx &c, const View &in, uint *out, unsi
     a.tile_counter = c.scratch->tile_counter;
     a.base = base;
     a.vec_ok = aligned_to(in.ptr, 16) ? 1 : 0;
-    a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
-    a.host_flag = ret ? ret->flag : nullptr;
+    a.host_wire = ret ? ret->wire : nullptr;
     a.host_seq = ret ? ret->seq : 0u;
     a.comm = peer_comm_of(link);
     where_kernel<T><<<(unsigned)a.ntiles, kScanThreads, 0, c.stream>>>(a);
@@ -217,8 +217,7 @@ struct ChainWhereArgs {
     unsigned long long *ticket;
     unsigned long long ticket_base;
     unsigned long long *debug;     // optional per-CTA cycle counters of pipe_where_kernel (AFB200_PIPE_DEBUG=1)
-    unsigned long long *host_total;   // optional pinned copy of the count + flag (common.hpp HostRet)
-    uint *host_flag;
+    void *host_wire;                  // optional pinned wire record of the count (common.hpp HostRet)
     uint host_seq;
     PeerComm comm;                    // world > 1: `in` is one shard, the counts are exchanged in the kernel
 };
@@ -819,8 +818,7 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
         a.gen = c.scratch->next_wepoch(c.stream);
         a.base = base;
-        a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
-        a.host_flag = ret ? ret->flag : nullptr;
+        a.host_wire = ret ? ret->wire : nullptr;
         a.host_seq = ret ? ret->seq : 0u;
         a.comm = peer_comm_of(link);
         dim_t grid = (dim_t)c.sms;
@@ -870,8 +868,7 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
         a.gen = c.scratch->next_wepoch(c.stream);
         a.base = base;
-        a.host_total = ret ? (unsigned long long *)ret->host : nullptr;
-        a.host_flag = ret ? ret->flag : nullptr;
+        a.host_wire = ret ? ret->wire : nullptr;
         a.host_seq = ret ? ret->seq : 0u;
         a.comm = peer_comm_of(link);
         int ctas = env_int("AFB200_CHAIN_CTAS_PER_SM", resident[dv]);

@@ -367,9 +367,9 @@ void Scratch::ensure_basics() {
     chain_base = 0;
     AFB_CUDA(cudaMalloc(&dev_scalar, 4096));
     AFB_CUDA(cudaMemsetAsync(dev_scalar, 0, 4096, s));
-    AFB_CUDA(cudaMallocHost(&host_pinned, 8192));
-    memset(host_pinned, 0, 8192);
-    host_pinned_bytes = 8192;
+    AFB_CUDA(cudaMallocHost(&host_pinned, 12288));
+    memset(host_pinned, 0, 12288);
+    host_pinned_bytes = 12288;
 }
 
 constexpr unsigned kRetSlots = 64;
@@ -377,25 +377,32 @@ constexpr unsigned kRetSlots = 64;
 HostRet Scratch::next_host_ret() {
     if (++ret_seq == 0) ++ret_seq;
     const unsigned slot = ret_seq % kRetSlots;
-    unsigned char *rec = (unsigned char *)host_pinned + 4096 + (size_t)slot * 64;
     HostRet r;
-    r.host = rec;
-    r.flag = (unsigned *)(rec + 60);
+    r.host = ret_plain[slot];
+    r.wire = (unsigned char *)host_pinned + 4096 + (size_t)slot * 128;
     r.seq = ret_seq;
     r.dev = (unsigned char *)dev_scalar + (size_t)slot * 64;
     return r;
 }
 
 void wait_host_ret(const LaunchCtx &c, const HostRet &r) {
-    volatile unsigned *flag = r.flag;
+    // every line is one 16-byte device store {data, seq, data, seq}; a 64-bit half that shows the right flag carries valid
+    // data (8-byte reads of aligned pinned memory are atomic), so the two halves are polled one after the other
+    const volatile unsigned long long *wire = (const volatile unsigned long long *)r.wire;
+    unsigned *out = (unsigned *)r.host;
     unsigned long long spins = 0;
-    while (*flag != r.seq) {
-        if ((++spins & 0x3ffff) == 0) {
-            cudaError_t e = cudaStreamQuery(c.stream);
-            if (e != cudaSuccess && e != cudaErrorNotReady) AFB_CUDA(e);
-            if (e == cudaSuccess && *flag != r.seq)
-                fail(AF_ERR_INTERNAL, "a kernel finished without publishing its host result (seq %u, flag %u)", r.seq, *flag);
+    for (int h = 0; h < 2 * kHostRetLines; h++) {
+        unsigned long long v;
+        while ((unsigned)((v = wire[h]) >> 32) != r.seq) {
+            if ((++spins & 0x3ffff) == 0) {
+                cudaError_t e = cudaStreamQuery(c.stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady) AFB_CUDA(e);
+                if (e == cudaSuccess && (unsigned)(wire[h] >> 32) != r.seq)
+                    fail(AF_ERR_INTERNAL, "a kernel finished without publishing its host result (seq %u, flag %u)", r.seq,
+                         (unsigned)(wire[h] >> 32));
+            }
         }
+        out[h] = (unsigned)v;
     }
     std::atomic_thread_fence(std::memory_order_acquire);
 }

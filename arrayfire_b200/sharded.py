@@ -187,7 +187,7 @@ class LocalGpu:
                           "out": (self.ct.c_ubyte * (8 * PAYLOAD_BYTES))()}
             # a second symmetric buffer for the FUSED ops (afx_sharded_*: the exchange happens inside the compute kernels,
             # include/afb200.h); its epochs advance independently of the afx_peer_exchange buffer above
-            t2 = symm.empty(2048, dtype=self.torch.uint8, device=self.dev)
+            t2 = symm.empty(4096, dtype=self.torch.uint8, device=self.dev)
             t2.zero_()
             hdl2 = symm.rendezvous(t2, dist.group.WORLD)
             self.torch.cuda.synchronize()
@@ -464,6 +464,35 @@ class ShardedOps:
         gidx = [int(g[r, 16:20].view(np.uint32)[0]) + bases[r] for r in range(self.world)]
         v, i = fold_arg(op, vals, gidx, is_b8=(code == _B8))
         return v, i & 0xffffffff
+
+    # -- issue / collect -----------------------------------------------------------------------------------
+    # The *_async forms enqueue the op (kernel + in-kernel exchange) and return at once; .result() collects the O(1) host
+    # result later.  A step that issues all its ops first and collects afterwards keeps every GPU busy: no host round trip
+    # between two ops, and the skew between ranks is absorbed by queued work instead of idling the early rank.
+    class _Done:
+        def __init__(self, value):
+            self.value = value
+
+        def result(self):
+            return self.value
+
+    def reduce_all_async(self, op, a):
+        comm = getattr(self.local, "_comm", None)
+        if comm is None:
+            return self._Done(self.reduce_all(op, a))
+        return self.local.af.reduce_all_async(a, _AFX_OP[op], comm)
+
+    def ireduce_all_async(self, op, a, base):
+        comm = getattr(self.local, "_comm", None)
+        if comm is None:
+            return self._Done(self.ireduce_all(op, a, base))
+        return self.local.af.ireduce_all_async(a, _AFX_OP[op], comm, int(base))
+
+    def where_async(self, a, base):
+        comm = getattr(self.local, "_comm", None)
+        if comm is None:
+            return self._Done(self.where(a, base))
+        return self.local.af.where_async(a, comm, int(base))
 
     # -- scans -----------------------------------------------------------------------------------------
     def scan(self, a, binop, inclusive):

@@ -273,6 +273,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sync-ops", action="store_true", help="device-resident arm through the blocking calls (one host round trip per op)")
+    ap.add_argument("--no-sync-compare", action="store_true", help="skip the extra timed pass through the blocking calls")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity check of the warm-up step")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -97,7 +97,10 @@ def make_inputs(torch, w, rank, world, dev):
 # ------------------------------------------------------------------------------------------------
 # the suite: name -> callable returning (result object or None); device-resident inputs
 # ------------------------------------------------------------------------------------------------
-def build_suite(af, torch, d, rank, world, group):
+def build_suite(af, torch, d, rank, world, group, pipelined=True, ops=None):
+    """name -> callable that ENQUEUES the op and returns its result: an af.Array (device result, as in the reference API),
+    or -- pipelined -- an af.Pending whose .result() collects the scalar / index / hit count later.  pipelined=False uses
+    the blocking reference calls (af_sum_all ... af_where: one host round trip per op)."""
     A = af.Array
     x1 = A.from_torch(d["x1"])
     m2c = A.from_device_ptr(d["m2_cols"].data_ptr(), d["m2_cols_dims"], af.f32, keepalive=d["m2_cols"])
@@ -107,41 +110,158 @@ def build_suite(af, torch, d, rank, world, group):
     m50, m01 = A.from_torch(d["m50"]), A.from_torch(d["m01"])
     keep = [x1, m2c, m2r, x3, i3, u3, k4, v4, m50, m01]
     if world == 1:
-        suite = {
-            "C1.sum_f32": lambda: af.sum_all(x1),
-            "C1.scan_f32": lambda: af.accum(x1, 0),
-            "C2.sum_dim0": lambda: af.sum(m2c, 0),
-            "C2.sum_dim1": lambda: af.sum(m2r, 1),
-            "C2.max_dim0": lambda: af.max(m2c, 0),
-            "C2.max_dim1": lambda: af.max(m2r, 1),
-            "C3.sum_f32": lambda: af.sum_all(x3),
-            "C3.sum_s32": lambda: af.sum_all(i3),
-            "C3.imax_f32": lambda: af.imax_all(u3),
-            "C4.scan_by_key_s32": lambda: af.scan_by_key(k4, v4, 0, af.AF_BINARY_ADD, False),
-            "C5.where_50": lambda: af.where(m50),
-            "C5.where_01": lambda: af.where(m01),
-            "C5.count": lambda: af.count_all(m50),
-        }
+        if pipelined:
+            red = lambda op, a: af.reduce_all_async(a, op)                      # noqa: E731
+            ired = lambda a, base: af.ireduce_all_async(a, af.OP_MAX, None, 0)  # noqa: E731
+            whr = lambda a, base: af.where_async(a, None, 0)                    # noqa: E731
+        else:
+            fn = {af.OP_ADD: af.sum_all, af.OP_COUNT: af.count_all}
+            red = lambda op, a: fn[op](a)                                       # noqa: E731
+            ired = lambda a, base: af.imax_all(a)                               # noqa: E731
+            whr = lambda a, base: af.where(a)                                   # noqa: E731
+        scn = lambda a: af.accum(a, 0)                                          # noqa: E731
+        sbk = lambda k, v: af.scan_by_key(k, v, 0, af.AF_BINARY_ADD, False)     # noqa: E731
+        OP_SUM, OP_COUNT = af.OP_ADD, af.OP_COUNT
     else:
         from arrayfire_b200 import sharded as sh
-        ops = sh.ShardedOps(group)
-        suite = {
-            "C1.sum_f32": lambda: ops.reduce_all(sh.OP_SUM, x1),
-            "C1.scan_f32": lambda: ops.scan(x1, af.AF_BINARY_ADD, True),
-            "C2.sum_dim0": lambda: af.sum(m2c, 0),       # partitioned along the non-reduced axis: no communication
-            "C2.sum_dim1": lambda: af.sum(m2r, 1),
-            "C2.max_dim0": lambda: af.max(m2c, 0),
-            "C2.max_dim1": lambda: af.max(m2r, 1),
-            "C3.sum_f32": lambda: ops.reduce_all(sh.OP_SUM, x3),
-            "C3.sum_s32": lambda: ops.reduce_all(sh.OP_SUM, i3),
-            "C3.imax_f32": lambda: ops.ireduce_all(sh.OP_MAX, u3, d["x3_base"]),
-            "C4.scan_by_key_s32": lambda: ops.scan_by_key(k4, v4, af.AF_BINARY_ADD, False),
-            "C5.where_50": lambda: ops.where(m50, d["c5_base"]),
-            "C5.where_01": lambda: ops.where(m01, d["c5_base"]),
-            "C5.count": lambda: ops.reduce_all(sh.OP_COUNT, m50),
-        }
+        if ops is None:
+            ops = sh.ShardedOps(group)
+        if pipelined:
+            red = lambda op, a: ops.reduce_all_async(op, a)                     # noqa: E731
+            ired = lambda a, base: ops.ireduce_all_async(sh.OP_MAX, a, base)    # noqa: E731
+            whr = lambda a, base: ops.where_async(a, base)                      # noqa: E731
+        else:
+            red = lambda op, a: ops.reduce_all(op, a)                           # noqa: E731
+            ired = lambda a, base: ops.ireduce_all(sh.OP_MAX, a, base)          # noqa: E731
+            whr = lambda a, base: ops.where(a, base)                            # noqa: E731
+        scn = lambda a: ops.scan(a, af.AF_BINARY_ADD, True)                     # noqa: E731
+        sbk = lambda k, v: ops.scan_by_key(k, v, af.AF_BINARY_ADD, False)       # noqa: E731
+        OP_SUM, OP_COUNT = sh.OP_SUM, sh.OP_COUNT
         keep.append(ops)
-    return suite, keep
+    suite = {
+        "C1.sum_f32": lambda: red(OP_SUM, x1),
+        "C1.scan_f32": lambda: scn(x1),
+        "C2.sum_dim0": lambda: af.sum(m2c, 0),       # N > 1: partitioned along the non-reduced axis, no communication
+        "C2.sum_dim1": lambda: af.sum(m2r, 1),
+        "C2.max_dim0": lambda: af.max(m2c, 0),
+        "C2.max_dim1": lambda: af.max(m2r, 1),
+        "C3.sum_f32": lambda: red(OP_SUM, x3),
+        "C3.sum_s32": lambda: red(OP_SUM, i3),
+        "C3.imax_f32": lambda: ired(u3, d["x3_base"]),
+        "C4.scan_by_key_s32": lambda: sbk(k4, v4),
+        "C5.where_50": lambda: whr(m50, d["c5_base"]),
+        "C5.where_01": lambda: whr(m01, d["c5_base"]),
+        "C5.count": lambda: red(OP_COUNT, m50),
+    }
+    return suite, keep, ops
+
+
+def as_torch(torch, arr, dtype, dev):
+    """zero-copy torch view of a dense af.Array"""
+    n = int(arr.elements)
+    if n == 0:
+        return torch.empty(0, dtype=dtype, device=dev)
+    item = torch.empty(0, dtype=dtype).element_size()
+    ptr = arr.device_ptr()
+    arr.unlock()
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (n * item,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(_Holder(), device=dev).view(dtype)
+
+
+def check_results(af, torch, dist, d, last, rank, world, dev):
+    """Every op of the step against an INDEPENDENT value computed by torch from the same device-resident inputs (all-reduced /
+    all-gathered over the ranks for the sharded ops).  All inputs are integer valued, so every comparison is exact.
+    Returns the list of failed op names (empty = parity holds on this rank)."""
+    bad = []
+
+    def allsum(v):
+        t = torch.tensor([v], dtype=torch.float64 if isinstance(v, float) else torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        return t.item()
+
+    def gather(v, dtype=torch.int64):
+        t = torch.tensor([v], dtype=dtype, device=dev)
+        if world == 1:
+            return [t.item()]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.item() for o in out]
+
+    def chk(name, ok):
+        if not bool(ok):
+            bad.append(name)
+
+    torch.cuda.synchronize()
+    # whole-array reductions
+    chk("C1.sum_f32", float(last["C1.sum_f32"]) == allsum(float(d["x1"].sum(dtype=torch.float64).item())))
+    chk("C3.sum_f32", float(last["C3.sum_f32"]) == allsum(float(d["x3"].sum(dtype=torch.float64).item())))
+    tot = allsum(int(d["i3"].sum(dtype=torch.int64).item()))
+    tot = ((tot + (1 << 31)) % (1 << 32)) - (1 << 31)          # s32 accumulator: wraps like the reference's
+    chk("C3.sum_s32", int(last["C3.sum_s32"]) == tot)
+    chk("C5.count", int(last["C5.count"]) == allsum(int(torch.count_nonzero(d["m50"]).item())))
+    # imax: first index of the global maximum
+    mx = d["u3"].max()
+    first = int((d["u3"] == mx).nonzero()[0].item()) + int(d["x3_base"])
+    vals, idxs = gather(float(mx.item()), torch.float64), gather(first)
+    gmax = max(vals)
+    gidx = min(i for v, i in zip(vals, idxs) if v == gmax)
+    v, i = last["C3.imax_f32"]
+    chk("C3.imax_f32", float(v) == gmax and int(i) == gidx)
+    # C2: column-major blocks; flat buffer viewed row-major as [cols, rows]
+    rows_c, cols_c = d["m2_cols_dims"]
+    mc = d["m2_cols"].view(cols_c, rows_c)
+    chk("C2.sum_dim0", torch.equal(as_torch(torch, last["C2.sum_dim0"], torch.float32, dev), mc.sum(dim=1, dtype=torch.float64).float()))
+    chk("C2.max_dim0", torch.equal(as_torch(torch, last["C2.max_dim0"], torch.float32, dev), mc.max(dim=1).values))
+    rows_r, cols_r = d["m2_rows_dims"]
+    mr = d["m2_rows"].view(cols_r, rows_r)
+    chk("C2.sum_dim1", torch.equal(as_torch(torch, last["C2.sum_dim1"], torch.float32, dev), mr.sum(dim=0, dtype=torch.float64).float()))
+    chk("C2.max_dim1", torch.equal(as_torch(torch, last["C2.max_dim1"], torch.float32, dev), mr.max(dim=0).values))
+    # C1 inclusive scan: local cumsum (exact: |partial sums| << 2^24) + the totals of the lower ranks
+    tots = gather(float(d["x1"].sum(dtype=torch.float64).item()), torch.float64)
+    want = torch.cumsum(d["x1"].double(), 0) + sum(tots[:rank])
+    chk("C1.scan_f32", torch.equal(as_torch(torch, last["C1.scan_f32"], torch.float32, dev), want.float()))
+    del want
+    # C4 exclusive scan by key: segmented from the plain cumsum; the first run of rank r continues rank r-1's last key
+    k, v4 = d["k4"], d["v4"].long()
+    n4 = k.numel()
+    head = torch.ones(n4, dtype=torch.bool, device=dev)
+    head[1:] = k[1:] != k[:-1]
+    ex = torch.cumsum(v4, 0) - v4                                 # exclusive prefix of the whole shard
+    start = torch.cummax(torch.where(head, torch.arange(n4, device=dev), torch.zeros((), dtype=torch.long, device=dev)), 0).values
+    want = ex - ex[start]
+    firsts, lasts = gather(int(k[0].item())), gather(int(k[-1].item()))
+    last_head = int(start[-1].item())
+    tails = gather(int(v4[last_head:].sum().item()))
+    nheads = gather(int(head.sum().item()))
+    carry, r = 0, rank
+    while r > 0 and lasts[r - 1] == firsts[r]:                    # chain through shards that are ONE run of the same key
+        carry += tails[r - 1]
+        if nheads[r - 1] > 1:
+            break
+        r -= 1
+    if carry:
+        first_len = int(head[1:].nonzero()[0].item()) + 1 if nheads[rank] > 1 else n4
+        want[:first_len] += carry
+    chk("C4.scan_by_key_s32", torch.equal(as_torch(torch, last["C4.scan_by_key_s32"], torch.int32, dev), want.int()))
+    del want, ex, start, head
+    # where: this rank's slice = local nonzero positions + base; offsets / totals from the counts of all ranks
+    for name, key in (("C5.where_50", "m50"), ("C5.where_01", "m01")):
+        want = d[key].nonzero().flatten() + int(d["c5_base"])
+        cnts = gather(int(want.numel()))
+        r = last[name]
+        if isinstance(r, tuple):
+            arr, off, total = r
+            ok = int(off) == sum(cnts[:rank]) and int(total) == sum(cnts)
+        else:
+            arr, ok = r, True
+        ok = ok and int(arr.elements) == int(want.numel()) and torch.equal(as_torch(torch, arr, torch.int32, dev).long() & 0xffffffff, want)
+        chk(name, ok)
+        del want
+    torch.cuda.synchronize()
+    return bad
 
 
 def where_count(res):
@@ -274,8 +394,9 @@ def gpu_arm(args):
     t0 = time.time()
     d = make_inputs(torch, w, rank, world, dev)
     log("[rank %d] inputs ready in %.1f s" % (rank, time.time() - t0))
-    suite, keep = build_suite(af, torch, d, rank, world, group)
-    e2e_ops = keep[-1] if world > 1 else None   # build_suite appends its ShardedOps instance
+    pipelined = not args.sync_ops
+    suite, keep, sh_ops = build_suite(af, torch, d, rank, world, group, pipelined)
+    e2e_ops = sh_ops
 
     def barrier():
         torch.cuda.synchronize()
@@ -284,39 +405,67 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident arm -------------------------------------------------------------------
+    # One step = ENQUEUE the 13 ops back to back, then COLLECT the host-side results (scalars, index, hit counts; the
+    # where outputs are trimmed to their count).  Array results stay on the device, as in the reference API.
     counts = {}
     last = {}
 
-    def step(events=None):
-        for name in OP_ORDER:
-            if events is not None:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e0.record(lib_stream)
-            r = suite[name]()
-            if events is not None:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record(lib_stream)
-                events.append((name, e0, e1))
+    host_issue = [0.0, 0]   # host seconds spent enqueueing, steps
+
+    def run_step(st, ev=None):
+        pend = []
+        t_issue = time.perf_counter()
+        for i, name in enumerate(OP_ORDER):
+            if ev is not None:
+                ev[i][0].record(lib_stream)
+            pend.append(st[name]())
+            if ev is not None:
+                ev[i][1].record(lib_stream)
+        host_issue[0] += time.perf_counter() - t_issue
+        host_issue[1] += 1
+        for name, r in zip(OP_ORDER, pend):
+            if hasattr(r, "result"):
+                r = r.result()
             if name.startswith("C5.where"):
                 counts[name] = where_count(r)
             last[name] = r
 
+    def step(ev=None):
+        run_step(suite, ev)
+
     for _ in range(args.warmup):
         step()
+    barrier()
+    # ---- parity: the results of the last warm-up step against torch on the same inputs, on every rank ----
+    parity_failed = None
+    if not args.no_check:
+        bad = check_results(af, torch, dist, d, last, rank, world, dev)
+        if world > 1:
+            obj = [None] * world
+            dist.all_gather_object(obj, bad)
+            bad = sorted(set(sum(obj, [])))
+        parity_failed = bad
+        if bad:
+            log("[rank %d] PARITY FAILED: %s" % (rank, bad))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     af.launch_count(reset=True)
-    events = []
+    # events are created up front: nothing but the two records per op is added to the timed region
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in OP_ORDER]
+           for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    host_issue[0], host_issue[1] = 0.0, 0
     start.record(lib_stream)
-    for _ in range(args.steps):
-        step(events)
+    for k in range(args.steps):
+        step(evs[k])
     end.record(lib_stream)
     barrier()
     launches = af.launch_count()
+    host_issue_ms = host_issue[0] / max(1, host_issue[1]) * 1e3
+    events = [(name, e0, e1) for ev in evs for name, (e0, e1) in zip(OP_ORDER, ev)]
     if rank == 0 and world == 1 and len(sampler.rows) < 8:
         # the timed region (~150 ms) can be too short for the sampling thread: keep the same load running, untimed,
         # until the clock / throttle-reason record has a few samples taken UNDER LOAD
@@ -369,6 +518,30 @@ def gpu_arm(args):
         except Exception:
             pass
 
+    # ---- the same suite through the BLOCKING reference calls (af_sum_all ... af_where: one host round trip per op) -------
+    sync_api = None
+    if pipelined and not args.no_sync_compare:
+        suite_s, keep_s, _ = build_suite(af, torch, d, rank, world, group, False, ops=sh_ops)
+        for _ in range(2):
+            run_step(suite_s)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record(lib_stream)
+        for _ in range(args.steps):
+            run_step(suite_s)
+        s1.record(lib_stream)
+        barrier()
+        s_ms = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([s_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            s_ms = float(t[0])
+        sync_api = {"value": round(total_bytes * args.steps / (s_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+                    "ms_per_step": round(s_ms / args.steps, 4),
+                    "how": "same suite, same inputs, every whole-array op through the blocking call (the host waits for each "
+                           "scalar / hit count before it enqueues the next op)"}
+        del suite_s, keep_s
+
     # ---- end-to-end arm (host buffers) ------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -417,11 +590,19 @@ def gpu_arm(args):
             "config": {"workload": WORKLOAD,
                        "scale": args.scale, "l2": "every input (>=256 MiB) exceeds the 126 MB L2 and ops are interleaved so "
                                                   "no input is re-read while resident",
+                       "issue": ("pipelined: the 13 ops of a step are enqueued back to back (afx_*_async for the ops with a host "
+                                 "result), the scalars / index / hit counts are collected from pinned host records at the end "
+                                 "of the step") if pipelined else "blocking reference calls, one host round trip per op",
                        "sharding": "none" if world == 1 else "whole-array ops sharded along the flattened axis (global sizes "
-                                   "fixed), 64-byte per-shard partials exchanged over NVLink peer memory by the library's own "
-                                   "kernels (NCCL only carries the rendezvous / barrier / timing all-reduce, and the "
-                                   "all-gather fallback when peer mapping is unavailable); C2 partitioned along the "
-                                   "non-reduced axis, no communication"},
+                                   "fixed); the 64-byte per-shard partials are exchanged INSIDE the compute kernels over NVLink "
+                                   "peer memory (symmetric buffers, kernels/peer_comm.cuh) and folded in rank order on every "
+                                   "GPU -- no collective-library call on the data path (NCCL only carries the rendezvous, the "
+                                   "barrier and the timing all-reduce); C2 partitioned along the non-reduced axis, no "
+                                   "communication"},
+            "parity_checked": parity_failed is not None and not parity_failed,
+            "parity_failed_ops": parity_failed,
+            "sync_api": sync_api,
+            "host_issue_ms_per_step": round(host_issue_ms, 4),
             "bytes_per_step": int(total_bytes), "ops": ops, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "where_counts": counts,
         }

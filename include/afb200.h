@@ -288,7 +288,7 @@ AFAPI af_err afx_peer_exchange(void *out, const void *payload, const unsigned lo
 /* ---- the same ops with the cross-GPU combine FUSED into the kernels (kernels/peer_comm.cuh): the thread that holds the
  * shard's partial stores it into every rank's symmetric buffer over NVLink peer memory, waits for the others and folds the
  * world's partials in rank order -- no second launch, no collective-library call, no host round trip before the combine.
- * `peer_bufs[r]` = device address (in THIS process) of rank r's symmetric buffer: >= 1088 bytes, zero-initialised, mapped
+ * `peer_bufs[r]` = device address (in THIS process) of rank r's symmetric buffer: >= 2048 bytes, zero-initialised, mapped
  * into every rank (torch.distributed._symmetric_memory, or cuMemCreate + IPC handles).  Every rank must issue the same
  * afx_sharded_* calls in the same order (they are collectives); world <= 8. */
 AFAPI af_err afx_comm_create(void **comm, int rank, int world, const unsigned long long *peer_bufs);
@@ -305,6 +305,23 @@ AFAPI af_err afx_sharded_scan(af_array *out, void *comm, const af_array key, con
 /* this rank's slice of af_where of the global array (global indices): the slice starts at *offset of *total hits */
 AFAPI af_err afx_sharded_where(af_array *idx, dim_t *offset, dim_t *total, void *comm, const af_array shard,
                                unsigned shard_base);
+/* ---- issue / collect: the whole-array ops whose result is O(1) host data (a scalar, an index, a hit count), split in
+ * two so that a caller can enqueue MANY ops back to back and collect the results afterwards -- the GPU never idles through
+ * a host round trip between two ops, and (sharded) ranks that arrive at different times overlap their skew with work.
+ * `comm` may be NULL: the op then runs on the calling device alone (af_<op>_all / af_imin_all / af_where semantics, with
+ * `shard_base` added to the indices).  The kernel's last thread publishes the result into a pinned host record
+ * (csrc/common.hpp HostRet); afx_pending_* spins on that record's flag -- no cudaMemcpy, no stream synchronisation.
+ * At most 63 ops may be pending per device.  Every pending handle must be consumed by exactly one afx_pending_* call. */
+typedef void *afx_pending;
+AFAPI af_err afx_reduce_all_async(afx_pending *pending, void *comm, const af_array shard, int op, bool change_nan, double nanval);
+AFAPI af_err afx_ireduce_all_async(afx_pending *pending, void *comm, const af_array shard, int op, unsigned shard_base);
+AFAPI af_err afx_where_async(afx_pending *pending, void *comm, const af_array shard, unsigned shard_base);
+/* wait for and decode a reduction (idx may be NULL unless the op was an index reduction); consumes the handle */
+AFAPI af_err afx_pending_scalar(afx_pending pending, double *real, double *imag, unsigned *idx);
+/* wait for a where: the indices trimmed to the hit count (exact-size copy when sparse), slice offset, global count */
+AFAPI af_err afx_pending_where(afx_pending pending, af_array *idx, dim_t *offset, dim_t *total);
+/* drop a pending op without collecting its result */
+AFAPI af_err afx_pending_release(afx_pending pending);
 /* number of CUDA kernels this library launched on the calling thread's device since the last reset */
 AFAPI af_err afx_launch_count(unsigned long long *count, bool reset);
 
