@@ -503,6 +503,66 @@ def where(a):
     return Array(h)
 
 
+# ---- statistics on the reduction path (af::mean / var / stdev / norm / cov / corrcoef, src/api/cpp/{mean,var,stdev}.cpp) ------
+AF_VARIANCE_DEFAULT, AF_VARIANCE_SAMPLE, AF_VARIANCE_POPULATION = 0, 1, 2
+(AF_NORM_VECTOR_1, AF_NORM_VECTOR_INF, AF_NORM_VECTOR_2, AF_NORM_VECTOR_P, AF_NORM_MATRIX_1, AF_NORM_MATRIX_INF,
+ AF_NORM_MATRIX_2, AF_NORM_MATRIX_L_PQ) = range(8)
+
+
+def _stat_dim(fn, a, dim, *extra):
+    h = _vp()
+    _check(fn(ctypes.byref(h), a.handle, *extra, ctypes.c_longlong(_fnsd(a, dim))))
+    return Array(h)
+
+
+def mean(a, dim=-1):
+    return _stat_dim(lib.af_mean, a, dim)
+
+
+def mean_all(a):
+    return _all(lib.af_mean_all, a)
+
+
+def var(a, dim=-1, bias=AF_VARIANCE_POPULATION):
+    return _stat_dim(lib.af_var_v2, a, dim, ctypes.c_int(bias))
+
+
+def var_all(a, bias=AF_VARIANCE_POPULATION):
+    return _all(lib.af_var_all_v2, a, ctypes.c_int(bias))
+
+
+def stdev(a, dim=-1, bias=AF_VARIANCE_POPULATION):
+    return _stat_dim(lib.af_stdev_v2, a, dim, ctypes.c_int(bias))
+
+
+def stdev_all(a, bias=AF_VARIANCE_POPULATION):
+    return _all(lib.af_stdev_all_v2, a, ctypes.c_int(bias))
+
+
+def meanvar(a, dim=-1, bias=AF_VARIANCE_POPULATION):
+    m, v = _vp(), _vp()
+    _check(lib.af_meanvar(ctypes.byref(m), ctypes.byref(v), a.handle, None, ctypes.c_int(bias), ctypes.c_longlong(_fnsd(a, dim))))
+    return Array(m), Array(v)
+
+
+def norm(a, kind=AF_NORM_VECTOR_2, p=1.0, q=1.0):
+    out = ctypes.c_double()
+    _check(lib.af_norm(ctypes.byref(out), a.handle, ctypes.c_int(kind), ctypes.c_double(p), ctypes.c_double(q)))
+    return out.value
+
+
+def corrcoef(x, y):
+    re, im = ctypes.c_double(), ctypes.c_double()
+    _check(lib.af_corrcoef(ctypes.byref(re), ctypes.byref(im), x.handle, y.handle))
+    return re.value
+
+
+def cov(x, y, bias=AF_VARIANCE_POPULATION):
+    h = _vp()
+    _check(lib.af_cov_v2(ctypes.byref(h), x.handle, y.handle, ctypes.c_int(bias)))
+    return Array(h)
+
+
 # ---- issue / collect (include/afb200.h afx_*_async): enqueue many ops, collect their O(1) host results afterwards --------
 OP_ADD, OP_MUL, OP_MIN, OP_MAX, OP_COUNT, OP_ALL, OP_ANY = range(7)
 

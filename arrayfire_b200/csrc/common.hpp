@@ -221,6 +221,24 @@ bool launch_where(const LaunchCtx &c, af_dtype t, const View &in, unsigned *out,
 // key, last key) with the other ranks, derives this shard's carry and repairs its first segment in place
 bool launch_sbk_exchange_fixup(const LaunchCtx &c, Op op, af_dtype t, af_dtype tk, void *out, dim_t n, const void *keys,
                                const void *summary, const ShardLink &link);
+// ---- statistics on the reduction path (kernels/stats_*.cu).  Output dtypes follow stat_out_type() (api_stats.cpp).
+bool launch_mean(const LaunchCtx &c, af_dtype ti, const View &in, int dim, void *out);
+// out: ONE element of the compute type (f32 / f64 / c32 / c64; f16 computes in f32), also published through `ret`
+bool launch_mean_all(const LaunchCtx &c, af_dtype ti, const View &in, void *out, const HostRet *ret);
+// variance (take_sqrt: standard deviation) = norm * sum (x - mean)^2 in one pass; out_mean (optional): the means
+bool launch_var(const LaunchCtx &c, af_dtype ti, const View &in, int dim, void *out_var, void *out_mean, double norm,
+                bool take_sqrt);
+bool launch_var_all(const LaunchCtx &c, af_dtype ti, const View &in, void *out, double norm, bool take_sqrt,
+                    const HostRet *ret);
+// sum (OP_ADD) or max (OP_MAX) of |x| (pre 0), |x|^2 (pre 1) or |x|^p (pre 2); dim < 0: whole array.  Result type: f32 for
+// f32 / c32 / f16 inputs, f64 for f64 / c64
+bool launch_norm_reduce(const LaunchCtx &c, Op op, af_dtype ti, const View &in, int dim, int pre, double p, void *out,
+                        const HostRet *ret);
+// x, y: dense arrays of n elements; out: {sum x, sum y, sum x^2, sum y^2, sum xy} in f32 (f64 for f64 / s64 / u64)
+bool launch_corr_sums(const LaunchCtx &c, af_dtype t, const void *x, const void *y, dim_t n, void *out);
+// out[j] = scale * sum_i (x[i,j] - *mx)(y[i,j] - *my) over dense [n x ncols] arrays; mx / my device scalars
+bool launch_cov_cols(const LaunchCtx &c, af_dtype t, const void *x, const void *y, dim_t n, dim_t ncols, const void *mx,
+                     const void *my, double scale, void *out);
 // ---- reductions by key (kernels/rbk_*.cu): keys = n dense 32-bit keys, runs of equal consecutive keys are segments
 // pass 1: number of runs -> published through `ret` (u64); tile_base[t] (device, ntiles + 1 words) = runs starting before tile t
 dim_t rbk_tile_elems();

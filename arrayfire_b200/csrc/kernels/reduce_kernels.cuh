@@ -46,7 +46,7 @@ template<int OP, typename Ti, typename To> struct ValPolicy {
     typedef Rule<OP, Ti, Acc> R;
     typedef ValParams Params;
     struct Out { To *val; };
-    __host__ __device__ static Out host_out(void *rec) { return Out{(To *)rec}; }
+    __host__ __device__ static Out host_out(const Out &, void *rec) { return Out{(To *)rec}; }   // `out`, re-pointed at a host record
     AFB_DI static Acc init() { return R::init(); }
     AFB_DI static Acc load(const Params &p, In x, uint) {
         Acc v = R::pre(x);
@@ -102,7 +102,7 @@ template<int OP, typename T> struct ArgPolicy {
     typedef Arg<T> Acc;
     typedef ArgParams Params;
     struct Out { T *val; uint *loc; };
-    __host__ __device__ static Out host_out(void *rec) { return Out{(T *)rec, (uint *)((char *)rec + 32)}; }   // value at +0, index at +32
+    __host__ __device__ static Out host_out(const Out &, void *rec) { return Out{(T *)rec, (uint *)((char *)rec + 32)}; }   // value at +0, index at +32
     // Internally element i carries rank i+1, so that "no candidate yet" (rank 0 for min, UINT_MAX for max)
     // loses every tie against a real element -- distinct values can share an ordering key (b8 compares
     // `v > 0`, 64-bit integers compare as double, complex compares magnitudes).
@@ -183,7 +183,7 @@ template<int OP, typename T> struct FirstPolicy {
     typedef Arg<T> Acc;
     typedef ValParams Params;
     struct Out { T *val; };
-    __host__ __device__ static Out host_out(void *rec) { return Out{(T *)rec}; }
+    __host__ __device__ static Out host_out(const Out &, void *rec) { return Out{(T *)rec}; }
     AFB_DI static T ident() { return OP == OP_MIN ? Lim<T>::hi() : Lim<T>::lo(); }
     AFB_DI static Acc init() { return Acc{ident(), 0u}; }
     AFB_DI static Acc load(const Params &, In x, uint idx) { return Acc{is_nan<T>(x) ? ident() : x, idx + 1u}; }
@@ -344,7 +344,7 @@ AFB_DI void span_host_send(const SpanArgs<P> &a, typename P::Acc v) {
     alignas(16) uint w[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) w[j] = 0u;
-    P::store(P::host_out(w), 0, v);
+    P::store(P::host_out(a.out, w), 0, v);
     host_ret_send(a.host_wire, a.host_seq, w);
 }
 

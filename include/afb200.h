@@ -61,6 +61,13 @@ typedef enum {
     AF_BACKEND_DEFAULT = 0, AF_BACKEND_CPU = 1, AF_BACKEND_CUDA = 2, AF_BACKEND_OPENCL = 4, AF_BACKEND_ONEAPI = 8
 } af_backend;
 typedef enum { AF_BINARY_ADD = 0, AF_BINARY_MUL = 1, AF_BINARY_MIN = 2, AF_BINARY_MAX = 3 } af_binary_op;
+/* include/af/defines.h:525-529 */
+typedef enum { AF_VARIANCE_DEFAULT = 0, AF_VARIANCE_SAMPLE = 1, AF_VARIANCE_POPULATION = 2 } af_var_bias;
+/* include/af/defines.h:366-377 */
+typedef enum {
+    AF_NORM_VECTOR_1, AF_NORM_VECTOR_INF, AF_NORM_VECTOR_2, AF_NORM_VECTOR_P, AF_NORM_MATRIX_1, AF_NORM_MATRIX_INF,
+    AF_NORM_MATRIX_2, AF_NORM_MATRIX_L_PQ, AF_NORM_EUCLID = AF_NORM_VECTOR_2
+} af_norm_type;
 typedef struct af_seq { double begin, end, step; } af_seq;
 /* include/af/index.h:19-31 */
 typedef struct af_index_t {
@@ -242,6 +249,31 @@ AFAPI af_err af_set_backend(const af_backend bknd);
 AFAPI af_err afcu_get_stream(void **stream /* cudaStream_t* */, int id);                     /* cuda.h:50 */
 AFAPI af_err afcu_get_native_id(int *nativeid, int id);                                      /* cuda.h:63 */
 AFAPI af_err afcu_set_native_id(int nativeid);                                               /* cuda.h:75 */
+
+/* ===================== statistics on the reduction path =====================
+ * include/af/statistics.h:348-659, include/af/lapack.h:568.  One fused streaming pass per input (kernels/stats_*.cu);
+ * floating-point results agree with the reference within 1e-5 (f32) / 1e-12 (f64) relative, not bit for bit.
+ * The weighted forms return AF_ERR_NOT_SUPPORTED. */
+AFAPI af_err af_mean(af_array *out, const af_array in, const dim_t dim);                                  /* mean.cpp:65 */
+AFAPI af_err af_mean_all(double *real, double *imag, const af_array in);                                  /* mean.cpp:151 */
+AFAPI af_err af_mean_weighted(af_array *out, const af_array in, const af_array weights, const dim_t dim);
+AFAPI af_err af_mean_all_weighted(double *real, double *imag, const af_array in, const af_array weights);
+AFAPI af_err af_var(af_array *out, const af_array in, const bool isbiased, const dim_t dim);              /* var.cpp:187 */
+AFAPI af_err af_var_v2(af_array *out, const af_array in, const af_var_bias bias, const dim_t dim);        /* var.cpp:194 */
+AFAPI af_err af_var_weighted(af_array *out, const af_array in, const af_array weights, const dim_t dim);
+AFAPI af_err af_var_all(double *realVal, double *imagVal, const af_array in, const bool isbiased);        /* var.cpp:336 */
+AFAPI af_err af_var_all_v2(double *realVal, double *imagVal, const af_array in, const af_var_bias bias);  /* var.cpp:343 */
+AFAPI af_err af_var_all_weighted(double *realVal, double *imagVal, const af_array in, const af_array weights);
+AFAPI af_err af_meanvar(af_array *mean, af_array *var, const af_array in, const af_array weights, const af_var_bias bias,
+                        const dim_t dim);                                                                 /* var.cpp:418 */
+AFAPI af_err af_stdev(af_array *out, const af_array in, const dim_t dim);                                 /* stdev.cpp:130 */
+AFAPI af_err af_stdev_v2(af_array *out, const af_array in, const af_var_bias bias, const dim_t dim);      /* stdev.cpp:134 */
+AFAPI af_err af_stdev_all(double *real, double *imag, const af_array in);                                 /* stdev.cpp:97 */
+AFAPI af_err af_stdev_all_v2(double *real, double *imag, const af_array in, const af_var_bias bias);      /* stdev.cpp:101 */
+AFAPI af_err af_cov(af_array *out, const af_array X, const af_array Y, const bool isbiased);              /* covariance.cpp:65 */
+AFAPI af_err af_cov_v2(af_array *out, const af_array X, const af_array Y, const af_var_bias bias);        /* covariance.cpp:72 */
+AFAPI af_err af_corrcoef(double *realVal, double *imagVal, const af_array X, const af_array Y);           /* corrcoef.cpp:63 */
+AFAPI af_err af_norm(double *out, const af_array in, const af_norm_type type, const double p, const double q); /* norm.cpp:119 */
 
 /* ===================== afx_*: sharded whole-array extension ============================
  * New functionality (the reference has no multi-GPU path).  One process

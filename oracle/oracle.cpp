@@ -657,3 +657,171 @@ int orc_ireduce_ragged(int op, int t, const void *in, const orc_dim_t dims[4], c
 }
 
 }  // extern "C"
+
+// ==== statistics =======================================================================
+namespace {
+
+// mean: src/backend/cpu/kernel/mean.hpp:18-127 -- MeanOp keeps a running mean and a running count; one serial loop per line
+template<typename Tc, typename Tw> struct RunningMean {
+    Tc mean;
+    Tw count;
+    RunningMean() : mean(Tc(0)), count(Tw(0)) {}
+    void push(Tc x, Tw w) {                       // mean.hpp:28-38
+        if (w != Tw(0) || count != Tw(0)) {
+            Tw rs = count, ns = w;
+            count += w;
+            rs = rs / count;
+            ns = ns / count;
+            mean = (rs * mean) + (ns * x);
+        }
+    }
+};
+template<typename T> struct base_of { using type = T; };
+template<> struct base_of<cfloat> { using type = float; };
+template<> struct base_of<cdouble> { using type = double; };
+
+// float -> half as the CPU backend stores it: common/half.hpp:258-420 (table-driven conversion, round to nearest with TIES
+// AWAY from zero -- HALF_ROUND_TIES_TO_EVEN is off), not the IEEE ties-to-even of a plain cast
+inline half_t half_ties_away(float v) {
+    half_t h = (half_t)v;
+    const float hf = (float)h;
+    if (!(v == v) || hf == v || std::isinf(hf)) return h;
+    uint16_t bits;
+    std::memcpy(&bits, &h, 2);
+    const bool toward_larger = std::fabs(v) > std::fabs(hf);
+    uint16_t nb = (uint16_t)(toward_larger ? bits + 1 : bits - 1);
+    half_t n;
+    std::memcpy(&n, &nb, 2);
+    const float nf = (float)n;
+    if (std::fabs(v - hf) == std::fabs(nf - v) && std::fabs(nf) > std::fabs(hf)) return n;   // exact tie: the larger magnitude
+    return h;
+}
+template<typename To, typename Tc> inline To stat_store(Tc v) { return (To)v; }
+template<> inline half_t stat_store<half_t, float>(float v) { return half_ties_away(v); }
+
+// Ti: stored input type, Tc: compute type (float / double / complex), To: stored output type
+template<typename Ti, typename Tc, typename To>
+void mean_lines(const void *vin, const dim_t *dims, const dim_t *strides, int dim, void *vout) {
+    using Tw = typename base_of<Tc>::type;
+    const Ti *in = (const Ti *)vin;
+    To *out = (To *)vout;
+    if (empty(dims)) return;
+    Shape sh = mk(dims, strides);
+    dim_t od[4] = {dims[0], dims[1], dims[2], dims[3]}, os[4];
+    od[dim] = 1;
+    dense_strides(od, os);
+    const dim_t len = dims[dim], step = strides[dim];
+    for_each_line(sh, os, dim, [&](dim_t ib, dim_t ob) {
+        RunningMean<Tc, Tw> op;
+        for (dim_t i = 0; i < len; i++) op.push(Tc(in[ib + i * step]), Tw(1));
+        out[ob] = stat_store<To, Tc>(op.mean);
+    });
+}
+template<typename Ti, typename Tc>
+Tc mean_everything(const void *vin, const dim_t *dims, const dim_t *strides) {     // cpu/mean.cpp:113-141
+    using Tw = typename base_of<Tc>::type;
+    const Ti *in = (const Ti *)vin;
+    RunningMean<Tc, Tw> op;
+    for (dim_t l = 0; l < dims[3]; l++)
+        for (dim_t k = 0; k < dims[2]; k++)
+            for (dim_t j = 0; j < dims[1]; j++) {
+                const Ti *p = in + j * strides[1] + k * strides[2] + l * strides[3];
+                for (dim_t i = 0; i < dims[0]; i++) op.push(Tc(p[i]), Tw(1));
+            }
+    return op.mean;
+}
+// var / stdev along a dimension: api/c/var.cpp:104-136 (meanvar) and stdev.cpp:61-96: cast, mean along dim, (x - mean)^2
+// summed serially (reduce<af_add_t>), times 1 / denom [, sqrt].  `denom` is computed by the caller (the two entry points
+// treat the DEFAULT bias differently).
+template<typename Ti, typename Tc, typename To>
+void var_lines(const void *vin, const dim_t *dims, const dim_t *strides, int dim, double denom, int take_sqrt, void *vout,
+               void *vmean) {
+    using Tw = typename base_of<Tc>::type;
+    const Ti *in = (const Ti *)vin;
+    To *out = (To *)vout, *mout = (To *)vmean;
+    if (empty(dims)) return;
+    Shape sh = mk(dims, strides);
+    dim_t od[4] = {dims[0], dims[1], dims[2], dims[3]}, os[4];
+    od[dim] = 1;
+    dense_strides(od, os);
+    const dim_t len = dims[dim], step = strides[dim];
+    for_each_line(sh, os, dim, [&](dim_t ib, dim_t ob) {
+        RunningMean<Tc, Tw> op;
+        for (dim_t i = 0; i < len; i++) op.push(Tc((To)in[ib + i * step]), Tw(1));   // cast<outType>(in) first
+        const Tc m = (Tc)stat_store<To, Tc>(op.mean);
+        Tc acc = Tc(0);
+        for (dim_t i = 0; i < len; i++) {
+            const Tc d = Tc((To)in[ib + i * step]) - m;
+            acc = d * d + acc;
+        }
+        Tc v = acc * Tc((Tw)(1.0 / denom));
+        if (take_sqrt) v = std::sqrt(v);
+        out[ob] = stat_store<To, Tc>(v);
+        if (mout) mout[ob] = stat_store<To, Tc>(op.mean);
+    });
+}
+template<typename Ti, typename Tc>
+Tc var_everything(const void *vin, const dim_t *dims, const dim_t *strides, double denom, int take_sqrt) {   // var.cpp:52-75
+    const Ti *in = (const Ti *)vin;
+    const Tc m = mean_everything<Ti, Tc>(vin, dims, strides);
+    Tc acc = Tc(0);
+    for (dim_t l = 0; l < dims[3]; l++)
+        for (dim_t k = 0; k < dims[2]; k++)
+            for (dim_t j = 0; j < dims[1]; j++) {
+                const Ti *p = in + j * strides[1] + k * strides[2] + l * strides[3];
+                for (dim_t i = 0; i < dims[0]; i++) {
+                    const Tc d = Tc(p[i]) - m;
+                    acc = d * d + acc;
+                }
+            }
+    using Tw = typename base_of<Tc>::type;
+    Tc v = acc / Tc((Tw)denom);
+    if (take_sqrt) v = std::sqrt(v);
+    return v;
+}
+
+#define FOR_STAT_TYPES(X)                                                                                           \
+    X(ORC_F32, float, float, float) X(ORC_F64, double, double, double) X(ORC_C32, cfloat, cfloat, cfloat)           \
+    X(ORC_C64, cdouble, cdouble, cdouble) X(ORC_S32, int, float, float) X(ORC_U32, unsigned, float, float)          \
+    X(ORC_S64, long long, double, double) X(ORC_U64, unsigned long long, double, double)                            \
+    X(ORC_S16, short, float, float) X(ORC_U16, unsigned short, float, float) X(ORC_S8, signed char, float, float)   \
+    X(ORC_U8, unsigned char, float, float) X(ORC_B8, b8_t, float, float) X(ORC_F16, half_t, float, half_t)
+
+}  // namespace
+
+extern "C" {
+
+/* af_mean along dim (api/c/mean.cpp:65-93): out dtype f32 / f64 / c32 / c64 / f16 per the table above */
+int ORC_FN(mean)(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], int dim, void *out) {
+#define X(code, Ti, Tc, To) if (ti == code) { mean_lines<Ti, Tc, To>(in, dims, strides, dim, out); return 0; }
+    FOR_STAT_TYPES(X)
+#undef X
+    return -1;
+}
+/* af_mean_all (mean.cpp:151-187): out = 2 doubles (real, imag) */
+int ORC_FN(mean_all)(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], double *out) {
+    out[0] = out[1] = 0;
+#define X(code, Ti, Tc, To) if (ti == code) { const std::complex<double> v(mean_everything<Ti, Tc>(in, dims, strides)); out[0] = v.real(); out[1] = v.imag(); return 0; }
+    FOR_STAT_TYPES(X)
+#undef X
+    return -1;
+}
+/* af_var_v2 / af_stdev_v2 / af_meanvar along dim; mean_out may be NULL */
+int ORC_FN(var)(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], int dim, double denom,
+                int take_sqrt, void *out, void *mean_out) {
+#define X(code, Ti, Tc, To) if (ti == code) { var_lines<Ti, Tc, To>(in, dims, strides, dim, denom, take_sqrt, out, mean_out); return 0; }
+    FOR_STAT_TYPES(X)
+#undef X
+    return -1;
+}
+/* af_var_all_v2 / af_stdev_all_v2: out = 2 doubles */
+int ORC_FN(var_all)(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], double denom, int take_sqrt,
+                    double *out) {
+    out[0] = out[1] = 0;
+#define X(code, Ti, Tc, To) if (ti == code) { const std::complex<double> v(var_everything<Ti, Tc>(in, dims, strides, denom, take_sqrt)); out[0] = v.real(); out[1] = v.imag(); return 0; }
+    FOR_STAT_TYPES(X)
+#undef X
+    return -1;
+}
+
+}  // extern "C"

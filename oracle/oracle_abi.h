@@ -103,6 +103,17 @@ long long ORC_FN(reduce_by_key)(int op, int ti, int to, int tk, const void *keys
 int ORC_FN(ireduce_ragged)(int op, int t, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4],
                            int dim, const uint32_t *rlen, void *out_val, uint32_t *out_loc);
 
+/* ---- statistics.  mean: cpu/kernel/mean.hpp (running mean) -- exported by BOTH libraries;
+ * var / var_all are composed at the reference's C-API level (api/c/var.cpp, stdev.cpp) and exist in the restatement only.
+ * Output dtype of the dim-wise forms: f32 for integers <= 32 bits and b8, f64 for f64 / s64 / u64, c32, c64, f16 -> f16.
+ * The *_all forms write 2 doubles (real, imag). */
+int ORC_FN(mean)(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], int dim, void *out);
+int ORC_FN(mean_all)(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], double *out);
+int ORC_FN(var)(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], int dim, double denom,
+                int take_sqrt, void *out, void *mean_out);
+int ORC_FN(var_all)(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], double denom, int take_sqrt,
+                    double *out);
+
 /* 1 if this library was built from the reference's own headers, 0 for the restatement */
 int ORC_FN(is_reference)(void);
 

@@ -262,6 +262,64 @@ _SBK_TO = {F32: F32, F64: F64, C32: C32, C64: C64, S16: S32, S32: S32, S8: S32, 
 _BINOP = {AF_BINARY_ADD: OP_ADD, AF_BINARY_MUL: OP_MUL, AF_BINARY_MIN: OP_MIN, AF_BINARY_MAX: OP_MAX}
 
 
+# output dtype of mean / var / stdev along a dimension (api/c/mean.cpp:71-86)
+STAT_TO = {F32: F32, S32: F32, U32: F32, S16: F32, U16: F32, S8: F32, U8: F32, B8: F32, F64: F64, S64: F64, U64: F64,
+           C32: C32, C64: C64, F16: F16}
+
+
+def _stat_methods():
+    def mean(self, x, dim, ti=None):
+        ptr, d, st, keep = as_view(x)
+        ti = code_of(np.asarray(x), ti)
+        od = list(d)
+        od[dim] = 1
+        out = np.zeros(od, dtype=NP_OF[STAT_TO[ti]], order="F")
+        rc = self._fn("mean")(ti, ctypes.c_void_p(ptr), _dim_arr(d), _dim_arr(st), dim, ctypes.c_void_p(out.ctypes.data))
+        if rc != 0:
+            raise TypeError("mean: no instantiation for %s" % DTYPE_NAMES[ti])
+        return out
+
+    def mean_all(self, x, ti=None):
+        ptr, d, st, keep = as_view(x)
+        ti = code_of(np.asarray(x), ti)
+        out = (ctypes.c_double * 2)()
+        rc = self._fn("mean_all")(ti, ctypes.c_void_p(ptr), _dim_arr(d), _dim_arr(st), out)
+        if rc != 0:
+            raise TypeError("mean_all: no instantiation for %s" % DTYPE_NAMES[ti])
+        return complex(out[0], out[1]) if ti in (C32, C64) else out[0]
+
+    def var(self, x, dim, denom, take_sqrt=False, want_mean=False, ti=None):
+        ptr, d, st, keep = as_view(x)
+        ti = code_of(np.asarray(x), ti)
+        od = list(d)
+        od[dim] = 1
+        out = np.zeros(od, dtype=NP_OF[STAT_TO[ti]], order="F")
+        mo = np.zeros(od, dtype=NP_OF[STAT_TO[ti]], order="F") if want_mean else None
+        rc = self._fn("var")(ti, ctypes.c_void_p(ptr), _dim_arr(d), _dim_arr(st), dim, ctypes.c_double(denom), int(take_sqrt),
+                             ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(mo.ctypes.data if want_mean else None))
+        if rc != 0:
+            raise TypeError("var: no instantiation for %s" % DTYPE_NAMES[ti])
+        return (mo, out) if want_mean else out
+
+    def var_all(self, x, denom, take_sqrt=False, ti=None):
+        ptr, d, st, keep = as_view(x)
+        ti = code_of(np.asarray(x), ti)
+        out = (ctypes.c_double * 2)()
+        rc = self._fn("var_all")(ti, ctypes.c_void_p(ptr), _dim_arr(d), _dim_arr(st), ctypes.c_double(denom), int(take_sqrt), out)
+        if rc != 0:
+            raise TypeError("var_all: no instantiation for %s" % DTYPE_NAMES[ti])
+        return complex(out[0], out[1]) if ti in (C32, C64) else out[0]
+
+    Oracle.mean, Oracle.mean_all, Oracle.var, Oracle.var_all = mean, mean_all, var, var_all
+
+
+_stat_methods()
+
+AF_VARIANCE_DEFAULT, AF_VARIANCE_SAMPLE, AF_VARIANCE_POPULATION = 0, 1, 2
+(AF_NORM_VECTOR_1, AF_NORM_VECTOR_INF, AF_NORM_VECTOR_2, AF_NORM_VECTOR_P, AF_NORM_MATRIX_1, AF_NORM_MATRIX_INF,
+ AF_NORM_MATRIX_2, AF_NORM_MATRIX_L_PQ) = range(8)
+
+
 class AfArgError(Exception):
     """AF_ERR_ARG (202)"""
 
@@ -522,3 +580,123 @@ class AfOracle:
         if ti == F16:
             raise AfTypeError
         return self.o.where(x, ti)
+
+
+    # ---- statistics ---------------------------------------------------------------
+    def mean(self, x, dim, dtype=None):
+        """af_mean (api/c/mean.cpp:65-93)"""
+        if not (0 <= dim <= 3):
+            raise AfArgError("dim")
+        ti = code_of(np.asarray(x), dtype)
+        return STAT_TO[ti], self.o.mean(x, dim, ti)
+
+    def mean_all(self, x, dtype=None):
+        return self.o.mean_all(x, code_of(np.asarray(x), dtype))
+
+    def var(self, x, dim, bias=AF_VARIANCE_POPULATION, dtype=None, want_mean=False):
+        """af_var_v2 / af_meanvar: 1 / (population ? N : N - 1) -- DEFAULT divides by N - 1 here (api/c/var.cpp:118-121)"""
+        if not (0 <= dim <= 3):
+            raise AfArgError("dim")
+        ti = code_of(np.asarray(x), dtype)
+        n = dims4(np.asarray(x).shape)[dim]
+        denom = n if bias == AF_VARIANCE_POPULATION else n - 1
+        return STAT_TO[ti], self.o.var(x, dim, denom, False, want_mean, ti)
+
+    def var_all(self, x, bias=AF_VARIANCE_POPULATION, dtype=None):
+        """af_var_all_v2: N - (bias == SAMPLE) (api/c/var.cpp:71-73)"""
+        return self.o.var_all(x, np.asarray(x).size - (1 if bias == AF_VARIANCE_SAMPLE else 0), False, code_of(np.asarray(x), dtype))
+
+    def stdev(self, x, dim, bias=AF_VARIANCE_POPULATION, dtype=None):
+        """af_stdev_v2: N - (bias == SAMPLE) (api/c/stdev.cpp:80-81); no complex / f16 case"""
+        ti = code_of(np.asarray(x), dtype)
+        if ti in (C32, C64, F16):
+            raise AfTypeError
+        n = dims4(np.asarray(x).shape)[dim]
+        return STAT_TO[ti], self.o.var(x, dim, n - (1 if bias == AF_VARIANCE_SAMPLE else 0), True, False, ti)
+
+    def stdev_all(self, x, bias=AF_VARIANCE_POPULATION, dtype=None):
+        ti = code_of(np.asarray(x), dtype)
+        if ti in (C32, C64, F16):
+            raise AfTypeError
+        return self.o.var_all(x, np.asarray(x).size - (1 if bias == AF_VARIANCE_SAMPLE else 0), True, ti)
+
+    @staticmethod
+    def norm(x, kind=AF_NORM_VECTOR_2, p=1.0, q=1.0):
+        """af_norm (api/c/norm.cpp:45-151): |x| first, every reduction serial in the result type (f32 for f32 / c32 / f16)"""
+        a = np.asarray(x)
+        rt = np.float64 if a.dtype in (np.float64, np.complex128) else np.float32
+        A = np.abs(a).astype(rt).reshape(dims4(a.shape)[:2], order="F") if a.ndim <= 2 else None
+        if A is None:
+            raise AfArgError("batch")
+        if a.size == 0:
+            return 0.0
+
+        def total(v):   # reduce_all<af_add_t>: serial, in rt
+            acc = rt(0)
+            for e in v.reshape(-1, order="F"):
+                acc = rt(e + acc)
+            return acc
+
+        def vec(pp):
+            if pp == 1:
+                return float(total(A))
+            if np.isinf(pp):
+                return float(A.max())
+            if pp == 2:
+                return float(np.sqrt(total((A * A).astype(rt))))
+            return float(total(np.power(A, rt(pp)).astype(rt)) ** (1.0 / pp))
+
+        if kind == AF_NORM_VECTOR_2:
+            return vec(2)
+        if kind == AF_NORM_VECTOR_1:
+            return vec(1)
+        if kind == AF_NORM_VECTOR_INF:
+            return vec(np.inf)
+        if kind == AF_NORM_VECTOR_P:
+            return vec(p)
+        if kind == AF_NORM_MATRIX_1:
+            return float(max(total(A[:, j]) for j in range(A.shape[1])))
+        if kind == AF_NORM_MATRIX_INF:
+            return float(max(total(A[i, :]) for i in range(A.shape[0])))
+        if kind == AF_NORM_MATRIX_L_PQ:
+            if p == 1:
+                cols = np.array([total(A[:, j]) for j in range(A.shape[1])], dtype=rt)
+            else:
+                cols = np.array([total(np.power(A[:, j], rt(p)).astype(rt)) for j in range(A.shape[1])], dtype=rt)
+                cols = np.power(cols, rt(1.0 / p)).astype(rt)
+            if q == 1:
+                return float(total(cols))
+            return float(total(np.power(cols, rt(q)).astype(rt)) ** (1.0 / q))
+        raise AfTypeError
+
+    @staticmethod
+    def corrcoef(x, y):
+        """af_corrcoef (api/c/corrcoef.cpp:39-60): five serial sums in the compute type, then the closed formula"""
+        a, b = np.asarray(x), np.asarray(y)
+        rt = np.float64 if a.dtype in (np.float64, np.int64, np.uint64) else np.float32
+        xa, ya = a.astype(rt).reshape(-1, order="F"), b.astype(rt).reshape(-1, order="F")
+
+        def total(v):
+            acc = rt(0)
+            for e in v:
+                acc = rt(e + acc)
+            return acc
+        n = rt(xa.size)
+        xs, ys, xx, yy, xy = total(xa), total(ya), total(xa * xa), total(ya * ya), total(xa * ya)
+        return float((n * xy - xs * ys) / (np.sqrt(n * xx - xs * xs) * np.sqrt(n * yy - ys * ys)))
+
+    def cov(self, x, y, bias=AF_VARIANCE_POPULATION):
+        """af_cov_v2 (api/c/covariance.cpp:41-63): the means are those of the WHOLE arrays; sums along dim 0"""
+        a, b = np.asarray(x), np.asarray(y)
+        rt = np.float64 if a.dtype in (np.float64, np.int64, np.uint64) else np.float32
+        d = dims4(a.shape)
+        n = d[0] - 1 if bias == AF_VARIANCE_SAMPLE else d[0]
+        mx, my = rt(self.o.mean_all(a)), rt(self.o.mean_all(b))
+        prod = ((a.astype(rt) - mx) * (b.astype(rt) - my)).astype(rt).reshape(d[:2], order="F")
+        out = np.zeros((1, d[1]), dtype=rt, order="F")
+        for j in range(d[1]):
+            acc = rt(0)
+            for e in prod[:, j]:
+                acc = rt(e + acc)
+            out[0, j] = acc / rt(n)
+        return (F64 if rt is np.float64 else F32), out

@@ -9,6 +9,7 @@
 //   kernel::ireduce_dim / MinMaxOp       src/backend/cpu/kernel/ireduce.hpp:29-104
 //   kernel::scan_dim                     src/backend/cpu/kernel/scan.hpp:19-72
 //   kernel::scan_dim_by_key              src/backend/cpu/kernel/scan_by_key.hpp:19-86
+//   kernel::mean_dim / MeanOp            src/backend/cpu/kernel/mean.hpp:18-127
 // for the (op, Ti, To) triples the reference's cpu/*.cpp files instantiate.
 // The host-side wrappers that pick the recursion depth (cpu/reduce.cpp:48-66:
 // reduce_funcs[in.ndims()-1], cpu/scan.cpp:24-70) and the whole-array ireduce
@@ -18,6 +19,7 @@
 
 #include <Param.hpp>
 #include <kernel/ireduce.hpp>
+#include <kernel/mean.hpp>
 #include <kernel/reduce.hpp>
 #include <kernel/scan.hpp>
 #include <kernel/scan_by_key.hpp>
@@ -394,4 +396,66 @@ int ref_ireduce_ragged(int op, int t, const void *in, const orc_dim_t dims[4], c
     return -1;
 }
 
+}  // extern "C"
+
+// ==== statistics: the reference's own running-mean kernel (kernel/mean.hpp); var / stdev are composed at the C-API level
+// from JIT element-wise nodes there and are pinned through the restatement's use of this mean ===============================
+namespace {
+template<typename Ti, typename Tw, typename To>
+int do_mean(const void *in, const orc_dim_t *dims, const orc_dim_t *strides, int dim, void *out) {
+    dim4 idims = D(dims), odims = D(dims);
+    if (idims.elements() == 0) return 0;
+    odims[dim] = 1;
+    Param<To> o((To *)out, odims, dense(odims));
+    CParam<Ti> i((const Ti *)in, idims, D(strides));
+    switch (ndims_of(idims)) {   // cpu/mean.cpp:40-45: mean_funcs[in.ndims() - 1]
+        case 1: kernel::mean_dim<Ti, Tw, To, 1>()(o, 0, i, 0, dim); break;
+        case 2: kernel::mean_dim<Ti, Tw, To, 2>()(o, 0, i, 0, dim); break;
+        case 3: kernel::mean_dim<Ti, Tw, To, 3>()(o, 0, i, 0, dim); break;
+        default: kernel::mean_dim<Ti, Tw, To, 4>()(o, 0, i, 0, dim); break;
+    }
+    return 0;
+}
+// cpu/mean.cpp:113-141 (needs Array<T>): the same MeanOp over the whole view
+template<typename Ti, typename Tw, typename To>
+To do_mean_all(const void *vin, const orc_dim_t *dims, const orc_dim_t *strides) {
+    const Ti *in = (const Ti *)vin;
+    kernel::MeanOp<compute_t<Ti>, compute_t<To>, compute_t<Tw>> Op(0, 0);
+    for (orc_dim_t l = 0; l < dims[3]; l++)
+        for (orc_dim_t k = 0; k < dims[2]; k++)
+            for (orc_dim_t j = 0; j < dims[1]; j++)
+                for (orc_dim_t i = 0; i < dims[0]; i++)
+                    Op(compute_t<Ti>(in[i + j * strides[1] + k * strides[2] + l * strides[3]]), 1);
+    return To(Op.runningMean);
+}
+}  // namespace
+
+// the instantiation list of cpu/mean.cpp:143-158
+#define FOR_MEAN_TYPES(X)                                                                               \
+    X(ORC_F32, float, float, float) X(ORC_F64, double, double, double) X(ORC_C32, cfloat, float, cfloat)   \
+    X(ORC_C64, cdouble, double, cdouble) X(ORC_S32, int, float, float) X(ORC_U32, uint, float, float)      \
+    X(ORC_S64, intl, double, double) X(ORC_U64, uintl, double, double) X(ORC_S16, short, float, float)     \
+    X(ORC_U16, ushort, float, float) X(ORC_S8, schar, float, float) X(ORC_U8, uchar, float, float)         \
+    X(ORC_B8, char, float, float) X(ORC_F16, half, float, half)
+
+extern "C" {
+int ref_mean(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], int dim, void *out) {
+#define X(code, Ti, Tw, To) if (ti == code) return do_mean<Ti, Tw, To>(in, dims, strides, dim, out);
+    FOR_MEAN_TYPES(X)
+#undef X
+    return -1;
+}
+int ref_mean_all(int ti, const void *in, const orc_dim_t dims[4], const orc_dim_t strides[4], double *out) {
+    out[0] = out[1] = 0;
+    if (ti == ORC_C32) { cfloat v = do_mean_all<cfloat, float, cfloat>(in, dims, strides); out[0] = v.real(); out[1] = v.imag(); return 0; }
+    if (ti == ORC_C64) { cdouble v = do_mean_all<cdouble, double, cdouble>(in, dims, strides); out[0] = v.real(); out[1] = v.imag(); return 0; }
+    if (ti == ORC_F16) { out[0] = (double)do_mean_all<half, float, float>(in, dims, strides); return 0; }
+#define X(code, Ti, Tw, To) if (ti == code) { out[0] = (double)do_mean_all<Ti, Tw, To>(in, dims, strides); return 0; }
+    X(ORC_F32, float, float, float) X(ORC_F64, double, double, double) X(ORC_S32, int, float, float)
+    X(ORC_U32, uint, float, float) X(ORC_S64, intl, double, double) X(ORC_U64, uintl, double, double)
+    X(ORC_S16, short, float, float) X(ORC_U16, ushort, float, float) X(ORC_S8, schar, float, float)
+    X(ORC_U8, uchar, float, float) X(ORC_B8, char, float, float)
+#undef X
+    return -1;
+}
 }  // extern "C"

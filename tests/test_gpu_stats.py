@@ -1,0 +1,232 @@
+"""`-m gpu`: the statistics built on the reduction path -- af_mean / af_var / af_stdev / af_meanvar /
+af_norm / af_corrcoef / af_cov through the C-ABI against the oracle (the reference's running-mean kernel and the C-API level
+compositions restated in oracle/).  Floating point: within 1e-5 (f32) / 1e-12 (f64) of the oracle AND of float64 truth,
+relative to the data scale -- the tolerance BASELINE.json's north_star states; the association order of a parallel sum
+differs from the serial loop, so these results are not bit-identical (the reference's own tests use ASSERT_NEAR too)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.gpu_util import gpu_available, random_subview, to_gpu
+
+pytestmark = pytest.mark.gpu
+
+ALL = [po.F32, po.F64, po.C32, po.C64, po.S32, po.U32, po.S64, po.U64, po.S16, po.U16, po.S8, po.U8, po.B8, po.F16]
+SHAPES = [(1,), (7,), (1000,), (5, 3), (1, 9), (33, 1, 4), (4, 5, 3, 2), (257, 70), (40, 300), (70001,), (3000, 100),
+          (130, 1000), (4, 50001), (1 << 20,)]
+
+
+@pytest.fixture(scope="module")
+def af():
+    if not gpu_available():
+        pytest.skip("no CUDA device")
+    import arrayfire_b200
+    return arrayfire_b200
+
+
+def rand(rng, code, shape):
+    n = int(np.prod(shape))
+    dt = po.NP_OF[code]
+    if code in (po.F32, po.F64, po.F16):
+        a = (rng.standard_normal(n) * 4 + 3).astype(dt)
+    elif code in (po.C32, po.C64):
+        a = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(dt)
+    elif code == po.B8:
+        a = rng.integers(0, 2, n).astype(dt)
+    else:
+        info = np.iinfo(dt)
+        a = rng.integers(max(info.min, -100), min(info.max, 100), n, endpoint=True).astype(dt)
+    return np.asfortranarray(a.reshape(shape, order="F"))
+
+
+def tol_of(code):
+    return 1e-12 if code in (po.F64, po.C64, po.S64, po.U64) else (2e-3 if code == po.F16 else 1e-5)
+
+
+def close(got, want, tol, scale, what):
+    got = np.asarray(got).reshape(-1)
+    want = np.asarray(want).reshape(-1)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    if got.size:
+        err = np.abs(got.astype(np.complex128) - want.astype(np.complex128)).max()
+        assert err <= tol * scale, (what, err, tol * scale)
+
+
+@pytest.mark.parametrize("code", ALL)
+def test_mean_var_stdev_dimwise(af, port_oracle, code):
+    orc = port_oracle
+    rng = np.random.default_rng(7000 + code)
+    cplx = code in (po.C32, po.C64)
+    for shape in SHAPES:
+        base = rand(rng, code, shape)
+        views = [(base, None)]
+        if base.size > 1:
+            sl = random_subview(rng, base.shape)
+            if base[sl].size:
+                views.append((base[sl], sl))
+        for x, sl in views:
+            g = to_gpu(af, base, sl, dtype=code)
+            x64 = x.astype(np.complex128 if cplx else np.float64)
+            scale = float(np.abs(x64).max()) + 1.0
+            nd = len(x.shape)
+            for dim in range(nd):
+                n = x.shape[dim]
+                tc, wm = orc.mean(x, dim, code)
+                gm = af.mean(g, dim)
+                assert gm.dtype == tc
+                # the serial running mean of the reference drifts on long f32 lines (-50 % at 2^26); the
+                # oracle is the judge up to 4096 elements per line, float64 truth always
+                short = n <= 4096
+                if short:
+                    close(gm.to_numpy(), wm, tol_of(code) * 4, scale, ("mean", shape, dim))
+                close(gm.to_numpy(), x64.mean(axis=dim), tol_of(code) * 4, scale, ("mean-truth", shape, dim))
+                if n < 2:
+                    continue
+                dd = x64 - x64.mean(axis=dim, keepdims=True)
+                ssq = (dd * dd).sum(axis=dim)
+                for bias, ddof in ((po.AF_VARIANCE_POPULATION, 0), (po.AF_VARIANCE_SAMPLE, 1), (po.AF_VARIANCE_DEFAULT, 1)):
+                    tc, wv = orc.var(x, dim, bias, code)
+                    gv = af.var(g, dim, bias)
+                    assert gv.dtype == tc
+                    if short:
+                        close(gv.to_numpy(), wv, tol_of(code) * 16, scale * scale, ("var", shape, dim, bias))
+                    close(gv.to_numpy(), ssq / (n - ddof), tol_of(code) * 16, scale * scale, ("var-truth", shape, dim, bias))
+                mm, vv = af.meanvar(g, dim, po.AF_VARIANCE_SAMPLE)
+                close(vv.to_numpy(), ssq / (n - 1), tol_of(code) * 16, scale * scale, ("meanvar.var", shape, dim))
+                close(mm.to_numpy(), x64.mean(axis=dim), tol_of(code) * 4, scale, ("meanvar.mean", shape, dim))
+                if not cplx and code != po.F16:
+                    for bias, ddof in ((po.AF_VARIANCE_POPULATION, 0), (po.AF_VARIANCE_SAMPLE, 1)):
+                        tc, ws = orc.stdev(x, dim, bias, code)
+                        gs = af.stdev(g, dim, bias)
+                        assert gs.dtype == tc
+                        if short:
+                            close(gs.to_numpy(), ws, tol_of(code) * 16, scale, ("stdev", shape, dim, bias))
+                        close(gs.to_numpy(), np.sqrt(ssq / (n - ddof)), tol_of(code) * 16, scale, ("stdev-truth", shape, dim, bias))
+
+
+@pytest.mark.parametrize("code", ALL)
+def test_mean_var_stdev_all(af, port_oracle, code):
+    orc = port_oracle
+    rng = np.random.default_rng(7100 + code)
+    cplx = code in (po.C32, po.C64)
+    for shape in SHAPES + [(3, 1 << 18), (2500, 480)]:
+        base = rand(rng, code, shape)
+        views = [(base, None)]
+        if base.size > 1:
+            sl = random_subview(rng, base.shape)
+            if base[sl].size > 1:
+                views.append((base[sl], sl))
+        for x, sl in views:
+            g = to_gpu(af, base, sl, dtype=code)
+            x64 = x.astype(np.complex128 if cplx else np.float64)
+            scale = float(np.abs(x64).max()) + 1.0
+            t = tol_of(code) if code != po.F16 else 1e-5     # the scalar form of f16 stays in f32
+            close(af.mean_all(g), x64.mean(), t * 4, scale, ("mean_all", shape))
+            if x.size <= 4096:      # the serial oracle itself drifts on long f32 inputs; truth is the judge there
+                close(af.mean_all(g), orc.mean_all(x, code), t * 8, scale, ("mean_all-oracle", shape))
+            if x.size < 2:
+                continue
+            d = x64 - x64.mean()
+            for bias, ddof in ((po.AF_VARIANCE_POPULATION, 0), (po.AF_VARIANCE_SAMPLE, 1), (po.AF_VARIANCE_DEFAULT, 0)):
+                want = (d * d).sum() / (x.size - ddof)
+                close(af.var_all(g, bias), want, t * 16, scale * scale, ("var_all", shape, bias))
+                if x.size <= 4096:
+                    close(af.var_all(g, bias), orc.var_all(x, bias, code), t * 16, scale * scale, ("var_all-oracle", shape))
+                if not cplx and code != po.F16:
+                    close(af.stdev_all(g, bias), np.sqrt(want), t * 16, scale, ("stdev_all", shape, bias))
+
+
+def test_reference_known_answers_on_gpu(af):
+    A = af.Array.from_numpy
+    # test/mean.cpp:221-241
+    for dt, val, dims in ((np.float64, 2.1, (10, 10)), (np.float32, 2.1, (10, 5, 2)), (np.int32, 2, (5, 5, 2, 2)),
+                          (np.uint32, 2, (100,)), (np.int16, 2, (5, 5, 2, 2)), (np.uint8, 2, (100,))):
+        x = np.full(dims, val, dtype=dt, order="F")
+        assert abs(af.mean_all(A(x)) - float(dt(val))) <= 1e-6
+    assert abs(af.mean_all(A(np.full((10, 5, 2), 2.1 + 0j, dtype=np.complex64, order="F"))) - complex(np.complex64(2.1))) <= 1e-6
+    # test/var.cpp:175-190 Var.ISSUE2117
+    ones = A(np.ones((1000, 3000), dtype=np.float32, order="F"))
+    assert abs(af.sum_all(af.var(ones, 1, af.AF_VARIANCE_SAMPLE))) <= 1e-6
+    # test/mean.cpp:354-368 MeanAll.SubArray
+    rng = np.random.default_rng(3)
+    big = np.asfortranarray(rng.random((10, 10, 10, 10)).astype(np.float32))
+    sub = A(big).index(af.seq(0, 0, 1), af.seq(0, 9, 1), af.seq(0, 9, 1), af.seq(0, 9, 1))
+    assert abs(af.mean_all(sub) - af.sum_all(sub) / 1000) <= np.finfo(np.float32).eps * 1000
+    # test/mean.cpp:370-381 MeanHalf.dim0
+    h = np.asfortranarray(rng.random((1024, 1024)).astype(np.float16))
+    m16 = af.mean(A(h), 0).to_numpy().astype(np.float32).reshape(-1)
+    m32 = af.mean(A(h.astype(np.float32)), 0).to_numpy().reshape(-1)
+    assert np.abs(m16 - m32).max() <= 1e-3
+    # test/stdev.cpp:146-150: invalid dim / complex input
+    with pytest.raises(af.AfError):
+        af.stdev(A(np.full(10, 1 - 1j, dtype=np.complex128)), 0)
+    with pytest.raises(af.AfError):
+        af._check(af.lib.af_stdev(__import__("ctypes").byref(af._vp()), ones.handle, __import__("ctypes").c_longlong(5)))
+    # weighted forms fail loudly
+    with pytest.raises(af.AfError) as ei:
+        af._check(af.lib.af_mean_weighted(__import__("ctypes").byref(af._vp()), ones.handle, ones.handle, __import__("ctypes").c_longlong(0)))
+    assert ei.value.code == 301
+
+
+def test_norm(af, port_oracle):
+    orc = port_oracle
+    rng = np.random.default_rng(12)
+    for dt in (np.float32, np.float64, np.complex64, np.complex128, np.float16):
+        for shape in [(40, 30), (1000,), (300, 2000), (1, 1)]:
+            a = rng.standard_normal(shape)
+            if dt in (np.complex64, np.complex128):
+                a = a + 1j * rng.standard_normal(shape)
+            a = np.asfortranarray(a.astype(dt))
+            g = af.Array.from_numpy(a)
+            tol = 1e-12 if dt in (np.float64, np.complex128) else (2e-3 if dt == np.float16 else 2e-5)
+            A = np.abs(a.astype(np.complex128)).reshape(po.dims4(a.shape)[:2], order="F")
+            cases = [((af.AF_NORM_VECTOR_2,), np.sqrt((A * A).sum())), ((af.AF_NORM_VECTOR_1,), A.sum()),
+                     ((af.AF_NORM_VECTOR_INF,), A.max()), ((af.AF_NORM_VECTOR_P, 3.5), (A ** 3.5).sum() ** (1 / 3.5)),
+                     ((af.AF_NORM_MATRIX_1,), A.sum(0).max()), ((af.AF_NORM_MATRIX_INF,), A.sum(1).max()),
+                     ((af.AF_NORM_MATRIX_L_PQ, 2.0, 3.0), (((A ** 2).sum(0) ** 0.5) ** 3.0).sum() ** (1 / 3.0)),
+                     ((af.AF_NORM_MATRIX_L_PQ, 1.0, 1.0), A.sum())]
+            for args, want in cases:
+                got = af.norm(g, *args)
+                assert abs(got - want) <= tol * max(1.0, abs(want)) * 8, (dt, shape, args, got, want)
+                if a.size <= 4096:
+                    ow = orc.norm(a, *args)
+                    assert abs(got - ow) <= tol * max(1.0, abs(want)) * 8, (dt, shape, args, got, ow)
+    eye = af.Array.from_numpy(np.asfortranarray(np.eye(17, dtype=np.float32)))
+    assert af.norm(eye, af.AF_NORM_MATRIX_1) == 1.0 and af.norm(eye, af.AF_NORM_MATRIX_INF) == 1.0
+    with pytest.raises(af.AfError) as ei:      # test/norm.cpp:247-261
+        af.norm(eye, af.AF_NORM_MATRIX_2)
+    assert ei.value.code == 301
+    with pytest.raises(af.AfError):            # integers are not floating (norm.cpp:128)
+        af.norm(af.Array.from_numpy(np.arange(10, dtype=np.int32)))
+
+
+def test_corrcoef_cov(af, port_oracle):
+    orc = port_oracle
+    rng = np.random.default_rng(13)
+    for dt in (np.float32, np.float64, np.int32, np.uint8, np.int64, np.int16):
+        for shape in [(500, 4), (100000,), (257, 70)]:
+            if np.issubdtype(dt, np.floating):
+                x = rng.standard_normal(shape).astype(dt)
+                y = (0.3 * x + rng.standard_normal(shape)).astype(dt)
+            else:
+                x = rng.integers(0, 100, shape).astype(dt)
+                y = (x // 2 + rng.integers(0, 50, shape)).astype(dt)
+            x, y = np.asfortranarray(x), np.asfortranarray(y)
+            gx, gy = af.Array.from_numpy(x), af.Array.from_numpy(y)
+            x64, y64 = x.astype(np.float64), y.astype(np.float64)
+            tol = 1e-11 if dt in (np.float64, np.int64) else 2e-4
+            want = np.corrcoef(x64.ravel(order="F"), y64.ravel(order="F"))[0, 1]
+            assert abs(af.corrcoef(gx, gy) - want) <= tol, (dt, shape)
+            if x.size <= 4096:
+                assert abs(af.corrcoef(gx, gy) - orc.corrcoef(x, y)) <= tol * 4
+            for bias in (po.AF_VARIANCE_POPULATION, po.AF_VARIANCE_SAMPLE):
+                d4 = po.dims4(x.shape)
+                n = d4[0] - (1 if bias == po.AF_VARIANCE_SAMPLE else 0)
+                wc = ((x64 - x64.mean()) * (y64 - y64.mean())).reshape(d4[:2], order="F").sum(0) / n
+                got = af.cov(gx, gy, bias)
+                assert got.dtype == (po.F64 if dt in (np.float64, np.int64) else po.F32)
+                scale = float(np.abs(x64).max() * np.abs(y64).max()) + 1.0
+                assert np.abs(got.to_numpy().reshape(-1) - wc).max() <= tol * scale, (dt, shape, bias)
+                if x.size <= 4096:
+                    _, oc = orc.cov(x, y, bias)
+                    assert np.abs(got.to_numpy().reshape(-1) - oc.reshape(-1)).max() <= tol * scale
