@@ -563,6 +563,31 @@ def cov(x, y, bias=AF_VARIANCE_POPULATION):
     return Array(h)
 
 
+# ---- callers next to the scan / compaction path: af::sat, af::diff1, af::diff2, af::setUnique (sorted input) ----------------
+def sat(a):
+    h = _vp()
+    _check(lib.af_sat(ctypes.byref(h), a.handle))
+    return Array(h)
+
+
+def diff1(a, dim=0):
+    h = _vp()
+    _check(lib.af_diff1(ctypes.byref(h), a.handle, ctypes.c_int(dim)))
+    return Array(h)
+
+
+def diff2(a, dim=0):
+    h = _vp()
+    _check(lib.af_diff2(ctypes.byref(h), a.handle, ctypes.c_int(dim)))
+    return Array(h)
+
+
+def set_unique(a, is_sorted=False):
+    h = _vp()
+    _check(lib.af_set_unique(ctypes.byref(h), a.handle, ctypes.c_bool(is_sorted)))
+    return Array(h)
+
+
 # ---- issue / collect (include/afb200.h afx_*_async): enqueue many ops, collect their O(1) host results afterwards --------
 OP_ADD, OP_MUL, OP_MIN, OP_MAX, OP_COUNT, OP_ALL, OP_ANY = range(7)
 

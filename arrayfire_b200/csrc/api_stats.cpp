@@ -221,10 +221,13 @@ af_err af_var(af_array *out, const af_array in, const bool isbiased, const dim_t
 }
 af_err af_meanvar(af_array *mean, af_array *var, const af_array in, const af_array weights, const af_var_bias bias,
                   const dim_t dim) {
-    if (weights != nullptr) {
+    if (weights != nullptr) {   // an EMPTY weights array means "unweighted" (var.cpp:113: weights.isEmpty()); af::array() is one
         AFB_API_BEGIN
-        fail(AF_ERR_NOT_SUPPORTED, "af_meanvar: weighted form is not supported by libafb200 yet");
-        AFB_API_END
+        Array *w = from_handle(weights);
+        AFB_ARG(3, w->info.type == f32 || w->info.type == f64);                                  // var.cpp:424-426
+        if (w->elements() > 0) fail(AF_ERR_NOT_SUPPORTED, "af_meanvar: weighted form is not supported by libafb200 yet");
+        }
+        catch (...) { return ::afb::current_exception_to_err(); }
     }
     return moments_dim(var, mean, true, in, (int)bias, dim, false, false, 5);
 }

@@ -239,6 +239,10 @@ bool launch_corr_sums(const LaunchCtx &c, af_dtype t, const void *x, const void 
 // out[j] = scale * sum_i (x[i,j] - *mx)(y[i,j] - *my) over dense [n x ncols] arrays; mx / my device scalars
 bool launch_cov_cols(const LaunchCtx &c, af_dtype t, const void *x, const void *y, dim_t n, dim_t ncols, const void *mx,
                      const void *my, double scale, void *out);
+// ---- callers next to the scan / compaction path (kernels/diff.cu)
+bool launch_diff(const LaunchCtx &c, af_dtype t, const View &in, int dim, int order, void *out);
+bool launch_differs(const LaunchCtx &c, af_dtype t, const void *in, dim_t n, unsigned char *mask);
+bool launch_gather(const LaunchCtx &c, af_dtype t, const void *in, const unsigned *idx, dim_t n, void *out);
 // ---- reductions by key (kernels/rbk_*.cu): keys = n dense 32-bit keys, runs of equal consecutive keys are segments
 // pass 1: number of runs -> published through `ret` (u64); tile_base[t] (device, ntiles + 1 words) = runs starting before tile t
 dim_t rbk_tile_elems();

@@ -223,7 +223,57 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
         post_launch_check("lookback_kernel");
         return;
     }
-    // dim > 0
+    // dim > 0: the tiled single-pass kernel (scanned axis split, look-back carry) for plain scans with 4-byte outputs
+    if constexpr (!KEYED && sizeof(To) == 4) {
+        if (!env_int("AFB200_NO_DIMSCAN", 0) && in.dims[0] > 0 && in.dims[dim] > 0) {
+            DimScanArgs<Ti, To> d;
+            d.in = (const Ti *)in.ptr;
+            d.out = (To *)out;
+            dim_t os[4];
+            dense_strides(in.dims, os);
+            d.d0 = in.dims[0];
+            d.len = in.dims[dim];
+            d.sd = in.strides[dim];
+            d.osd = os[dim];
+            int others[2], m = 0;
+            for (int i = 1; i < 4; i++)
+                if (i != dim) others[m++] = i;
+            d.na = in.dims[others[0]];
+            d.sa = in.strides[others[0]];
+            d.osa = os[others[0]];
+            d.nb = in.dims[others[1]];
+            d.sb = in.strides[others[1]];
+            d.osb = os[others[1]];
+            d.inclusive = inclusive ? 1 : 0;
+            bool vec = (d.d0 % 4 == 0) && aligned_to(in.ptr, sizeof(Ti) * 4) && aligned_to(out, 16) && (d.sd % 4 == 0) &&
+                       (d.na == 1 || d.sa % 4 == 0) && (d.nb == 1 || d.sb % 4 == 0);
+            const int V = vec ? 4 : 1;
+            d.nxb = (d.d0 + 32 * V - 1) / (32 * V);
+            d.nchains = d.nxb * d.na * d.nb;
+            const dim_t splits = (d.len + kDsRows - 1) / kDsRows;
+            d.ntiles = d.nchains * splits;
+            d.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)d.ntiles * 32 * V * 8, c.stream);
+            d.gen = c.scratch->next_wepoch(c.stream);
+            static int resident[64][2] = {{0}};
+            const int dv = c.device & 63;
+            if (!resident[dv][vec ? 1 : 0]) {
+                int occ = 0;
+                if (vec) AFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dim_scan_kernel<OP, Ti, To, 4>, 32 * kDsY, 0));
+                else AFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dim_scan_kernel<OP, Ti, To, 1>, 32 * kDsY, 0));
+                resident[dv][vec ? 1 : 0] = occ < 1 ? 1 : occ;
+            }
+            dim_t grid = (dim_t)c.sms * resident[dv][vec ? 1 : 0];
+            if (grid > d.ntiles) grid = d.ntiles;
+            d.ticket = c.scratch->chain_ticket;
+            d.ticket_base = c.scratch->chain_base;
+            c.scratch->chain_base += (unsigned long long)d.ntiles + (unsigned long long)grid;   // every CTA draws one past the end
+            if (vec) dim_scan_kernel<OP, Ti, To, 4><<<(unsigned)grid, dim3(32, kDsY), 0, c.stream>>>(d);
+            else dim_scan_kernel<OP, Ti, To, 1><<<(unsigned)grid, dim3(32, kDsY), 0, c.stream>>>(d);
+            note_launches(1);
+            post_launch_check("dim_scan_kernel");
+            return;
+        }
+    }
     StripScanArgs<Ti, To, Tk> a;
     a.in = (const Ti *)in.ptr;
     a.key = KEYED ? (const Tk *)key->ptr : nullptr;

@@ -498,4 +498,154 @@ __global__ void __launch_bounds__(32 * kStripY) strip_scan_kernel(const StripSca
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// dim_scan_kernel: scan along dim > 0 with the scanned axis SPLIT into tiles (4-byte outputs, not keyed)
+// ------------------------------------------------------------------------------------------------
+// strip_scan_kernel above gives one CTA a 32-lane slice of dim 0 and lets it walk the whole scanned axis: an 8192 x 8192
+// matrix keeps only 256 CTAs of scalar loads busy, and a 32 x 2^24 one a single CTA.  Here a tile is kDsRows rows of the
+// scanned axis by 32 x VEC elements of dim 0 (VEC = 4: every access is a 16-byte vector, 32 KB per tile); tiles are dealt
+// by ticket in split-major order, so every predecessor of a tile (same dim-0 slice, earlier rows) is already running or
+// done, and the carry travels down the scanned axis by decoupled look-back: ONE pass, 2N words of traffic for any shape.
+// A descriptor is one 64-bit word per dim-0 element {value : 32 | generation : 29 | state : 3}, written and read with
+// single 8-byte accesses -- value and flag can never be seen apart, so no fences.  (The reference: scan_dim + scan_dim_bcast,
+// 3 launches, /root/reference/src/backend/cuda/kernel/scan_dim.cuh:19-169.)
+constexpr int kDsRowsPerThread = 8;
+constexpr int kDsY = 8;
+constexpr int kDsRows = kDsRowsPerThread * kDsY;   // rows of the scanned axis per tile
+
+template<typename Ti, typename To>
+struct DimScanArgs {
+    const Ti *in;
+    To *out;
+    dim_t d0;
+    dim_t len, sd, osd;               // scanned extent; its input / output strides
+    dim_t na, sa, osa;                // batch dim a
+    dim_t nb, sb, osb;                // batch dim b
+    dim_t nxb;                        // dim-0 slices of 32 x VEC elements
+    dim_t nchains;                    // nxb * na * nb
+    dim_t ntiles;                     // nchains * splits
+    int inclusive;
+    uint gen;                         // generation of this launch's descriptors
+    unsigned long long *descs;        // [ntiles][32 * VEC]
+    unsigned long long *ticket;       // monotone counter
+    unsigned long long ticket_base;
+};
+
+template<int OP, typename Ti, typename To, int VEC>
+__global__ void __launch_bounds__(32 * kDsY) dim_scan_kernel(const DimScanArgs<Ti, To> a) {
+    static_assert(sizeof(To) == 4, "packed 64-bit descriptors carry a 4-byte value");
+    typedef Rule<OP, Ti, To> R;
+    constexpr int RPT = kDsRowsPerThread;
+    constexpr int W = 32 * VEC;
+    __shared__ To sm[kDsY][W + 1];
+    __shared__ To sm_carry[W];
+    __shared__ long long sm_tile;
+    const int lane = threadIdx.x, wy = threadIdx.y;
+    const uint tag = a.gen << 3;
+    auto bits_of = [](To v) -> uint { uint b; memcpy(&b, &v, 4); return b; };
+    auto val_of = [](uint b) -> To { To v; memcpy(&v, &b, 4); return v; };
+
+    while (true) {
+        __syncthreads();
+        if (lane == 0 && wy == 0) sm_tile = (long long)(atomicAdd(a.ticket, 1ULL) - a.ticket_base);
+        __syncthreads();
+        const long long tile = sm_tile;
+        if (tile >= a.ntiles) return;
+        const dim_t split = tile / a.nchains, chain = tile % a.nchains;
+        const dim_t xb = chain % a.nxb, batch = chain / a.nxb;
+        const dim_t ia = batch % a.na, ib = batch / a.na;
+        const dim_t x0 = (xb * 32 + lane) * VEC;
+        const bool live = x0 < a.d0;       // d0 is a multiple of VEC when VEC > 1
+        const Ti *in = a.in + ia * a.sa + ib * a.sb + x0;
+        To *out = a.out + ia * a.osa + ib * a.osb + x0;
+        const dim_t rs = split * kDsRows + (dim_t)wy * RPT;
+
+        // ---- load the thread's RPT rows x VEC elements, scan down the rows
+        To x[RPT][VEC];
+        if (live) {
+            Pack<Ti, VEC> v[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; j++)
+                if (rs + j < a.len) v[j] = load_pack<Ti, VEC>(in + (rs + j) * a.sd);
+#pragma unroll
+            for (int j = 0; j < RPT; j++)
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    const To e = (rs + j < a.len) ? R::pre(v[j].e[k]) : R::init();
+                    x[j][k] = (j == 0) ? e : R::join(x[j - 1][k], e);
+                }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RPT; j++)
+#pragma unroll
+                for (int k = 0; k < VEC; k++) x[j][k] = R::init();
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; k++) sm[wy][lane * VEC + k] = x[RPT - 1][k];
+        __syncthreads();
+
+        // ---- the first warp owns the tile's descriptors: aggregate, look-back, inclusive prefix
+        if (wy == 0) {
+            unsigned long long *mine = a.descs + (size_t)tile * W;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                const int xi = lane + 32 * k;             // descriptor words are lane-contiguous: coalesced
+                To agg = sm[0][xi];
+#pragma unroll
+                for (int y = 1; y < kDsY; y++) agg = R::join(agg, sm[y][xi]);
+                To carry = R::init();
+                if (split > 0) {
+                    st_relaxed64(mine + xi, ((unsigned long long)bits_of(agg) << 32) | tag | TILE_AGGREGATE);
+                    To acc = R::init();
+                    bool first = true;
+                    for (dim_t p = split - 1;; p--) {
+                        const unsigned long long *d = a.descs + (size_t)(p * a.nchains + chain) * W + xi;
+                        unsigned long long w;
+                        unsigned long long spins = 0;
+                        while (true) {
+                            w = ld_relaxed64(d);
+                            if (((uint)w & ~7u) == tag && ((uint)w & 7u) != TILE_INVALID) break;
+                            if (++spins > (1ull << 28)) __trap();
+                        }
+                        const To v = val_of((uint)(w >> 32));
+                        acc = first ? v : R::join(v, acc);      // v covers EARLIER rows
+                        first = false;
+                        if (((uint)w & 7u) == TILE_PREFIX) break;
+                    }
+                    carry = acc;
+                    agg = R::join(carry, agg);
+                }
+                st_relaxed64(mine + xi, ((unsigned long long)bits_of(agg) << 32) | tag | TILE_PREFIX);
+                sm_carry[xi] = carry;
+            }
+        }
+        __syncthreads();
+
+        // ---- carry + the rows of the warps above, then the stores
+        if (live) {
+            To before[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                const int xi = lane * VEC + k;
+                To b = (split > 0) ? sm_carry[xi] : R::init();     // R::init() joins as the identity, as in the serial loop
+                for (int y = 0; y < kDsY; y++)
+                    if (y < wy) b = R::join(b, sm[y][xi]);
+                before[k] = b;
+            }
+#pragma unroll
+            for (int j = 0; j < RPT; j++) {
+                if (rs + j >= a.len) break;
+                Pack<To, VEC> o;
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    if (a.inclusive) o.e[k] = R::join(before[k], x[j][k]);
+                    else o.e[k] = (j == 0) ? before[k] : R::join(before[k], x[j - 1][k]);
+                }
+                store_pack<To, VEC>(out + (rs + j) * a.osd, o);
+            }
+        }
+    }
+}
+
 }  // namespace afb

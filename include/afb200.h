@@ -275,6 +275,14 @@ AFAPI af_err af_cov_v2(af_array *out, const af_array X, const af_array Y, const 
 AFAPI af_err af_corrcoef(double *realVal, double *imagVal, const af_array X, const af_array Y);           /* corrcoef.cpp:63 */
 AFAPI af_err af_norm(double *out, const af_array in, const af_norm_type type, const double p, const double q); /* norm.cpp:119 */
 
+/* ===================== callers next to the scan / compaction path =====================
+ * include/af/image.h (af_sat), include/af/algorithm.h (af_diff1, af_diff2, af_set_unique).  af_sat is two single-pass scans
+ * (dim 0 by the pipelined kernel, dim 1 by the tiled look-back kernel); af_set_unique takes SORTED input only. */
+AFAPI af_err af_sat(af_array *out, const af_array in);                                                    /* sat.cpp:32 */
+AFAPI af_err af_diff1(af_array *out, const af_array in, const int dim);                                   /* diff.cpp:36 */
+AFAPI af_err af_diff2(af_array *out, const af_array in, const int dim);                                   /* diff.cpp:76 */
+AFAPI af_err af_set_unique(af_array *out, const af_array in, const bool is_sorted);                       /* set.cpp:32 */
+
 /* ===================== afx_*: sharded whole-array extension ============================
  * New functionality (the reference has no multi-GPU path).  One process
  * per GPU holds the shard [rank*N/G, (rank+1)*N/G) of a flattened array; each call below

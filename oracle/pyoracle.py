@@ -700,3 +700,41 @@ class AfOracle:
                 acc = rt(e + acc)
             out[0, j] = acc / rt(n)
         return (F64 if rt is np.float64 else F32), out
+
+    # ---- callers next to the path: thin numpy restatements of serial loops --------------------
+    def sat(self, x, dtype=None):
+        """af_sat (api/c/sat.cpp:32-61): cast (b8 -> s32, narrow ints as the scan promotes), scan dim 0, scan dim 1"""
+        ti = code_of(np.asarray(x), dtype)
+        if ti in (C32, C64, F16):
+            raise AfTypeError
+        if af_ndims(dims4(np.asarray(x).shape)) < 2:
+            raise AfArgError("ndims")
+        a = np.asarray(x)
+        if ti == B8:
+            a = np.asfortranarray(a.astype(np.int32))
+            ti = S32
+        t1, r1 = self.scan(a, 0, AF_BINARY_ADD, True, dtype=ti)
+        return self.scan(r1, 1, AF_BINARY_ADD, True, dtype=t1)
+
+    @staticmethod
+    def diff(x, dim, order):
+        """af_diff1 / af_diff2 (cpu/kernel/diff.hpp:18-81): same dtype, wrap-around for integers"""
+        a = np.asarray(x).reshape(dims4(np.asarray(x).shape), order="F")
+        if a.shape[dim] < order + 1:
+            return np.zeros((0,), dtype=a.dtype)
+        sl = lambda lo, hi: tuple(slice(lo, hi) if i == dim else slice(None) for i in range(4))   # noqa: E731
+        n = a.shape[dim]
+        with np.errstate(over="ignore"):
+            if order == 1:
+                return (a[sl(1, n)] - a[sl(0, n - 1)]).astype(a.dtype)
+            return (((a[sl(2, n)] + a[sl(0, n - 2)]).astype(a.dtype) - a[sl(1, n - 1)]).astype(a.dtype) - a[sl(1, n - 1)]).astype(a.dtype)
+
+    @staticmethod
+    def set_unique_sorted(x):
+        """std::unique of an already sorted vector (cpu/set.cpp:32-51)"""
+        a = np.asarray(x).reshape(-1, order="F")
+        if a.size <= 1:
+            return a.copy()
+        keep = np.ones(a.size, dtype=bool)
+        keep[1:] = ~(a[1:] == a[:-1])
+        return a[keep]

@@ -105,6 +105,23 @@ int main(int argc, char **argv) {
         af::array c = af::constant(3.0, 1000, f32);
         double cs = af::sum<float>(c);
         dump_bytes("const_sum.out", &cs, sizeof(cs));
+        // statistics on the reduction path (af::mean / var / stdev / meanvar / corrcoef / cov): NaN-free input
+        af::array z((dim_t)rows, (dim_t)cols, slurp<float>("z.f32").data());
+        dump<float>("mean_d0.out", af::mean(z, 0));
+        dump<float>("mean_d1.out", af::mean(z, 1));
+        dump<float>("var_d0.out", af::var(z, AF_VARIANCE_SAMPLE, 0));
+        dump<float>("stdev_d1.out", af::stdev(z, AF_VARIANCE_POPULATION, 1));
+        af::array mv_m, mv_v;
+        af::meanvar(mv_m, mv_v, z, af::array(), AF_VARIANCE_POPULATION, 0);
+        dump<float>("meanvar_m.out", mv_m);
+        dump<float>("meanvar_v.out", mv_v);
+        dump<float>("cov.out", af::cov(z, z, AF_VARIANCE_SAMPLE));
+        double stats[4];
+        stats[0] = af::mean<float>(z);
+        stats[1] = af::var<float>(z, AF_VARIANCE_SAMPLE);
+        stats[2] = af::stdev<float>(z, AF_VARIANCE_POPULATION);
+        stats[3] = af::corrcoef<float>(z, z);
+        dump_bytes("stats.out", stats, sizeof(stats));
         // an entry point outside the path must fail loudly (af::exception carrying AF_ERR_NOT_SUPPORTED = 301)
         int unsupported = 0;
         try {

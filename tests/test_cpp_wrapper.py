@@ -44,7 +44,8 @@ def test_wrapper_links_with_no_undefined_af_symbol():
     assert not missing, missing
     # the symbols of the path are among them: the wrapper really binds to this library for af::sum & co.
     for s in ("af_sum", "af_sum_all", "af_imax", "af_imax_all", "af_accum", "af_scan", "af_scan_by_key", "af_where",
-              "af_sum_by_key", "af_max_ragged", "af_create_array", "af_get_data_ptr", "af_index_gen"):
+              "af_sum_by_key", "af_max_ragged", "af_create_array", "af_get_data_ptr", "af_index_gen", "af_mean", "af_mean_all",
+              "af_var_v2", "af_var_all_v2", "af_stdev_v2", "af_meanvar", "af_cov_v2", "af_corrcoef"):
         assert s in need and s in have, s
     ldd = subprocess.check_output(["ldd", WRAP]).decode()
     assert "libafb200.so" in ldd and "not found" not in ldd
@@ -75,6 +76,8 @@ def test_cpp_program_through_the_reference_wrapper(port_oracle):
         x.reshape(-1, order="F").tofile(os.path.join(d, "x.f32"))
         k.reshape(-1, order="F").tofile(os.path.join(d, "k.s32"))
         m.tofile(os.path.join(d, "m.u8"))
+        z = np.asfortranarray((rng.standard_normal((rows, cols)) * 3 + 1).astype(np.float32))
+        z.reshape(-1, order="F").tofile(os.path.join(d, "z.f32"))
         np.array([rows, cols], np.int64).tofile(os.path.join(d, "shape.s64"))
         r = subprocess.run([DEMO, d], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
@@ -130,4 +133,21 @@ def test_cpp_program_through_the_reference_wrapper(port_oracle):
         same("flat_accum.out", np.float32, orc.accum(np.asfortranarray(sub).reshape(-1, order="F"), 0)[1], po.F32)
         same("moddims_sum.out", np.float32, orc.sum(x.reshape((cols, rows), order="F"), 0)[1], po.F32)
         assert np.fromfile(os.path.join(d, "const_sum.out"), np.float64)[0] == 3000.0
+
+        # statistics through af::mean / var / stdev / meanvar / cov / corrcoef: float64 truth at the f32 tolerance
+        def near(name, want, tol):
+            got, t = _read(d, name, np.float32)
+            assert t == po.F32, (name, t)
+            assert np.abs(got.reshape(-1, order="F") - np.asarray(want).reshape(-1)).max() <= tol, name
+        z64 = z.astype(np.float64)
+        near("mean_d0.out", z64.mean(0), 1e-4)
+        near("mean_d1.out", z64.mean(1), 1e-4)
+        near("var_d0.out", z64.var(0, ddof=1), 1e-3)
+        near("stdev_d1.out", z64.std(1), 1e-3)
+        near("meanvar_m.out", z64.mean(0), 1e-4)
+        near("meanvar_v.out", z64.var(0), 1e-3)
+        near("cov.out", ((z64 - z64.mean()) ** 2).sum(0) / (rows - 1), 1e-3)
+        st = np.fromfile(os.path.join(d, "stats.out"), dtype=np.float64)
+        assert abs(st[0] - z64.mean()) <= 1e-4 and abs(st[1] - z64.var(ddof=1)) <= 1e-3
+        assert abs(st[2] - z64.std()) <= 1e-3 and abs(st[3] - 1.0) <= 1e-4
         assert int(np.fromfile(os.path.join(d, "unsupported.out"), np.int32)[0]) == 301   # AF_ERR_NOT_SUPPORTED

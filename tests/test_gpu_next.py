@@ -1,0 +1,106 @@
+"""`-m gpu`: SURVEY.md section 8(f)-3 -- af_sat, af_diff1 / af_diff2, af_set_unique (sorted input) and the tiled single-pass
+scan along dim > 0 (dim_scan_kernel) that af_sat stands on, against the oracle.  Integer and exactly-representable float
+inputs: bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from tests.gpu_util import gpu_available, rand_data, random_subview, same_bits, to_gpu
+
+pytestmark = pytest.mark.gpu
+
+SAT_TYPES = [po.F32, po.F64, po.S32, po.U32, po.B8, po.S8, po.U8, po.S64, po.U64, po.S16, po.U16]
+DIFF_TYPES = [po.F32, po.F64, po.C32, po.C64, po.S32, po.U32, po.S64, po.U64, po.S16, po.U16, po.S8, po.U8, po.B8]
+
+
+@pytest.fixture(scope="module")
+def af():
+    if not gpu_available():
+        pytest.skip("no CUDA device")
+    import arrayfire_b200
+    return arrayfire_b200
+
+
+def d4(a):
+    return np.asarray(a).reshape(po.dims4(np.asarray(a).shape), order="F")
+
+
+@pytest.mark.parametrize("code", [po.F32, po.S32, po.U32, po.U8, po.S16, po.B8, po.F64, po.C32])
+def test_scan_along_higher_dims_at_scale(af, port_oracle, code):
+    """shapes that give the tiled look-back kernel many splits, ragged last tiles, narrow and unaligned dim 0, batches"""
+    orc = port_oracle
+    rng = np.random.default_rng(8100 + code)
+    shapes = [(128, 1000), (4, 50001), (32, 4097, 3), (130, 515), (1000, 70, 2, 3), (7, 300, 5), (256, 2, 700), (512, 2048)]
+    for shape in shapes:
+        base = rand_data(rng, code, shape, small=True)
+        views = [(base, None)]
+        sl = random_subview(rng, base.shape)
+        if base[sl].size:
+            views.append((base[sl], sl))
+        for x, s in views:
+            g = to_gpu(af, base, s, dtype=code)
+            for dim in range(1, len(shape)):
+                for op, incl in ((po.AF_BINARY_ADD, True), (po.AF_BINARY_ADD, False), (po.AF_BINARY_MAX, True), (po.AF_BINARY_MIN, False)):
+                    if op != po.AF_BINARY_ADD and code in (po.B8,):
+                        continue
+                    t, want = orc.scan(x, dim, op, incl, dtype=code)
+                    got = af.scan(g, dim, op, incl)
+                    assert got.dtype == t
+                    same_bits(got.to_numpy(), d4(want), "scan %s dim %d op %d incl %s" % (shape, dim, op, incl))
+            t, want = orc.accum(x, 1, dtype=code)
+            same_bits(af.accum(g, 1).to_numpy(), d4(want), "accum %s" % (shape,))
+
+
+@pytest.mark.parametrize("code", SAT_TYPES)
+def test_sat(af, port_oracle, code):
+    orc = port_oracle
+    rng = np.random.default_rng(8200 + code)
+    for shape in [(5, 3), (64, 64), (257, 70), (1000, 300), (33, 65, 3), (3000, 2000)]:
+        x = rand_data(rng, code, shape, small=True)
+        t, want = orc.sat(x, dtype=code)
+        got = af.sat(af.Array.from_numpy(x, dtype=code))
+        assert got.dtype == t, (shape, got.dtype, t)
+        same_bits(got.to_numpy(), d4(want), "sat %s" % (shape,))
+    with pytest.raises(af.AfError):      # sat.cpp:38: at least two dimensions
+        af.sat(af.Array.from_numpy(np.arange(10, dtype=np.float32)))
+    with pytest.raises(af.AfError):
+        af.sat(af.Array.from_numpy(np.zeros((4, 4), dtype=np.complex64, order="F")))
+
+
+@pytest.mark.parametrize("code", DIFF_TYPES)
+def test_diff(af, port_oracle, code):
+    orc = port_oracle
+    rng = np.random.default_rng(8300 + code)
+    for shape in [(1,), (2,), (1000,), (5, 3), (33, 1, 4), (4, 5, 3, 2), (257, 70), (100000, 3)]:
+        base = rand_data(rng, code, shape, small=True)
+        views = [(base, None)]
+        if base.size > 1:
+            sl = random_subview(rng, base.shape)
+            if base[sl].size:
+                views.append((base[sl], sl))
+        for x, s in views:
+            g = to_gpu(af, base, s, dtype=code)
+            for dim in range(4):
+                for order, fn in ((1, af.diff1), (2, af.diff2)):
+                    want = orc.diff(x.view(np.int8) if code == po.B8 and x.dtype == np.bool_ else x, dim, order)
+                    got = fn(g, dim)
+                    assert got.dtype == code
+                    if want.size == 0:
+                        assert got.elements == 0, (shape, dim, order)
+                    else:
+                        same_bits(got.to_numpy(), want, "diff%d %s dim %d" % (order, shape, dim))
+
+
+def test_set_unique_sorted(af, port_oracle):
+    orc = port_oracle
+    rng = np.random.default_rng(8400)
+    for dt in (np.float32, np.float64, np.int32, np.uint32, np.int64, np.uint64, np.int16, np.uint16, np.int8, np.uint8):
+        for n in (1, 2, 1000, 300001):
+            x = np.sort(rng.integers(0, max(2, n // 3), n)).astype(dt)
+            got = af.set_unique(af.Array.from_numpy(x), True)
+            want = orc.set_unique_sorted(x)
+            assert got.elements == want.size
+            assert got.to_numpy().reshape(-1).tobytes() == want.tobytes()
+    with pytest.raises(af.AfError) as ei:
+        af.set_unique(af.Array.from_numpy(np.array([3, 1, 2], dtype=np.int32)), False)
+    assert ei.value.code == 301

@@ -26,7 +26,10 @@ def timeit(fns):
     keep = []
     e0.record(stream)
     for i in range(reps):
-        keep.append(fns[i % len(fns)]())
+        r = fns[i % len(fns)]()
+        if hasattr(r, "result"):
+            keep.append(r)          # array results are dropped at once: their buffers go back to the pool (stream-ordered)
+        del r
     e1.record(stream)
     for r in keep:
         if hasattr(r, "result"):
@@ -63,6 +66,13 @@ def main():
         ("count u8", bigu8, 1, lambda t: (lambda a: (lambda: af.reduce_all_async(a, af.OP_COUNT)))(A(t))),
         ("where u8 50%", bigu8, 1, lambda t: (lambda a: (lambda: af.where_async(a)))(A(t))),
         ("accum f32", bigf, 4, lambda t: (lambda a: (lambda: af.accum(a, 0)))(A(t))),
+        ("accum dim1 (8192 rows)", bigf, 4, lambda t: (lambda a: (lambda: af.accum(a, 1)))(mat(t, 8192))),
+        ("accum dim1 (1024 rows)", bigf, 4, lambda t: (lambda a: (lambda: af.accum(a, 1)))(mat(t, 1024))),
+        ("accum dim1 (32 rows)", bigf, 4, lambda t: (lambda a: (lambda: af.accum(a, 1)))(mat(t, 32))),
+        ("mean_all f32", bigf, 4, lambda t: (lambda a: (lambda: af.mean_all(a)))(A(t))),
+        ("var_all f32", bigf, 4, lambda t: (lambda a: (lambda: af.var_all(a)))(A(t))),
+        ("var dim0 (8192 rows)", bigf, 4, lambda t: (lambda a: (lambda: af.var(a, 0)))(mat(t, 8192))),
+        ("norm2 f32", bigf, 4, lambda t: (lambda a: (lambda: af.norm(a)))(A(t))),
         ("sum dim0 (8192 rows)", bigf, 4, lambda t: (lambda a: (lambda: af.sum(a, 0)))(mat(t, 8192))),
         ("sum dim1 (8192 rows)", bigf, 4, lambda t: (lambda a: (lambda: af.sum(a, 1)))(mat(t, 8192))),
         ("sum dim1 (1024 rows)", bigf, 4, lambda t: (lambda a: (lambda: af.sum(a, 1)))(mat(t, 1024))),
