@@ -185,8 +185,43 @@ static size_t round_up(size_t bytes) {
     return (bytes + step - 1) / step * step;
 }
 
+// The reference's garbage-collection thresholds (common/DefaultMemoryManager.cpp:117-126, 88-89, 175-187): before an
+// allocation, free the cached buffers when the bytes in use reach max_bytes = max(0.75 * memsize, memsize - 1 GB), or when
+// the number of buffers (in use + cached) reaches AF_MAX_BUFFERS (default 1000).
+static size_t pool_max_bytes(Device &D) {
+    static size_t cached[64] = {0};
+    size_t &m = cached[D.id & 63];
+    if (!m) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || total_b == 0) {
+            cudaGetLastError();
+            m = (size_t)1 << 30;
+        } else {
+            const double a = (double)total_b * 0.75, b = (double)total_b - (double)((size_t)1 << 30);
+            m = (size_t)(a > b ? a : b);
+        }
+    }
+    return m;
+}
+static size_t pool_max_buffers() {
+    static size_t n = 0;
+    if (!n) {
+        const char *e = getenv("AF_MAX_BUFFERS");
+        long v = e ? atol(e) : 1000;
+        n = (size_t)(v < 1 ? 1 : v);
+    }
+    return n;
+}
+
 static void *pool_take(Device &D, size_t rounded) {
     Pool &P = D.pool;
+    bool run_gc = false;
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        run_gc = !P.free_list.empty() &&
+                 (P.live_bytes >= pool_max_bytes(D) || P.live.size() + P.free_list.size() >= pool_max_buffers());
+    }
+    if (run_gc) pool_gc(D.id);
     {
         std::lock_guard<std::mutex> lk(P.mu);
         auto it = P.free_list.find(rounded);

@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sync-ops", action="store_true", help="device-resident arm through the blocking calls (one host round trip per op)")
     ap.add_argument("--no-sync-compare", action="store_true", help="skip the extra timed pass through the blocking calls")
+    ap.add_argument("--no-extras", action="store_true", help="skip the ops outside BASELINE's suite (timed on their own)")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check of the warm-up step")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -542,6 +542,46 @@ def gpu_arm(args):
                            "scalar / hit count before it enqueues the next op)"}
         del suite_s, keep_s
 
+    # ---- ops outside BASELINE's suite (SURVEY.md section 8f rows and the dim > 0 scan): timed on their own, NOT part of
+    # `value`; N = 1 only.  Each: 2 warm-ups, then 5 launches bracketed by events on the library's stream.
+    extras = None
+    if world == 1 and not args.no_extras:
+        A = af.Array
+        m2 = A.from_device_ptr(d["m2_rows"].data_ptr(), d["m2_rows_dims"], af.f32, keepalive=d["m2_rows"])
+        x3, u3, k4, v4 = A.from_torch(d["x3"]), A.from_torch(d["u3"]), A.from_torch(d["k4"]), A.from_torch(d["v4"])
+        c2, c3, c4 = w["C2"]["rows"] * w["C2"]["cols"], w["C3"]["n"], w["C4"]["n"]
+        xs = {
+            "X.scan_dim1_f32 (C2 matrix, along dim 1)": (lambda: af.accum(m2, 1), 8 * c2),
+            "X.sat_f32 (C2 matrix: scan dim 0 + scan dim 1)": (lambda: af.sat(m2), 16 * c2),
+            "X.var_dim0_f32 (C2 matrix)": (lambda: af.var(m2, 0), 4 * c2),
+            "X.mean_dim1_f32 (C2 matrix)": (lambda: af.mean(m2, 1), 4 * c2),
+            "X.mean_all_f32 (C3)": (lambda: af.mean_all(x3), 4 * c3),
+            "X.var_all_f32 (C3)": (lambda: af.var_all(x3), 4 * c3),
+            "X.norm2_f32 (C3)": (lambda: af.norm(x3), 4 * c3),
+            "X.corrcoef_f32 (C3 x, C3 u)": (lambda: af.corrcoef(x3, u3), 8 * c3),
+            "X.sum_by_key_s32 (C4 keys + values)": (lambda: af.sum_by_key(k4, v4, 0), 8 * c4),
+        }
+        extras = {}
+        for name, (fn, nbytes) in xs.items():
+            try:
+                for _ in range(2):
+                    r = fn()
+                    del r
+                torch.cuda.synchronize()
+                x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                x0.record(lib_stream)
+                for _ in range(5):
+                    r = fn()
+                    del r
+                x1.record(lib_stream)
+                torch.cuda.synchronize()
+                ms = x0.elapsed_time(x1) / 5
+                extras[name] = {"ms": round(ms, 4), "GBps": round(nbytes / (ms * 1e-3) / 1e9, 1),
+                                "frac_of_peak": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4)}
+            except Exception as ex:  # an extra never takes the headline down
+                extras[name] = {"error": repr(ex)}
+        del m2, x3, u3, k4, v4
+
     # ---- end-to-end arm (host buffers) ------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -602,6 +642,7 @@ def gpu_arm(args):
             "parity_checked": parity_failed is not None and not parity_failed,
             "parity_failed_ops": parity_failed,
             "sync_api": sync_api,
+            "extras": extras,
             "host_issue_ms_per_step": round(host_issue_ms, 4),
             "bytes_per_step": int(total_bytes), "ops": ops, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "where_counts": counts,
