@@ -14,8 +14,8 @@
 //                              every run TAIL writes its reduction straight to out[tile_base + local run index]; heads
 //                              write keys_out.  Only the run that enters a tile from the left is incomplete: its partial is
 //                              written anyway and the tile's (value, has-head) aggregate goes to a side array ...
-//   pass 3  rbk_fixup_kernel   ... which one CTA per column scans (segmented, in tile order) to add the carried-in part to
-//                              the first output of each tile.  Deterministic: no atomics on values, fixed fold order.
+//   pass 3  rbk_carry_*        ... which two small launches scan (segmented, one thread per tile) to add the carried-in
+//                              part to the first output of each tile.  Deterministic: no atomics on values, fixed order.
 //           rbk_dim_kernel     dim > 0: lanes along the contiguous dim 0, every thread walks its line serially.
 // Traffic (dim 0): keys twice + values once + outputs; the reference's loop re-reads keys and values every round.
 #pragma once
@@ -66,19 +66,19 @@ static __global__ void __launch_bounds__(kRbkThreads) rbk_count_kernel(const Rbk
     __shared__ uint sm[kRbkThreads / 32];
     __shared__ int sm_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (dim_t t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-        uint k[kRbkEPT];
-        uint c = __popc(rbk_heads(a.keys, a.n, t * kRbkTile + (dim_t)tid * kRbkEPT, k));
-        c = __reduce_add_sync(0xffffffffu, c);
-        __syncthreads();
-        if (lane == 0) sm[warp] = c;
-        __syncthreads();
-        if (tid == 0) {
-            uint s = 0;
+    // a WARP owns a tile: its 8 sub-chunks of 256 keys are independent loads (16 x 16 bytes in flight per lane), one warp
+    // reduction per tile, no CTA barrier in the streaming loop (first cut: a CTA per tile with two barriers and a serial
+    // sum by thread 0 per 8 KB -- 2.5 TB/s)
+    const dim_t nwarps = (dim_t)gridDim.x * (kRbkThreads / 32);
+    for (dim_t t = (dim_t)blockIdx.x * (kRbkThreads / 32) + warp; t < a.ntiles; t += nwarps) {
+        uint c = 0;
 #pragma unroll
-            for (int w = 0; w < kRbkThreads / 32; w++) s += sm[w];
-            a.tile_base[t] = s;
+        for (int sub = 0; sub < kRbkThreads / 32; sub++) {
+            uint k[kRbkEPT];
+            c += __popc(rbk_heads(a.keys, a.n, t * kRbkTile + (dim_t)(sub * 32 + lane) * kRbkEPT, k));
         }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) a.tile_base[t] = c;
     }
     // ---- the last CTA to arrive scans the counts in place
     __syncthreads();
@@ -229,13 +229,20 @@ __global__ void __launch_bounds__(kRbkThreads) rbk_tile_kernel(const RbkArgs<Ti,
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass 3 (dim 0): add what a run accumulated in earlier tiles to the tile that holds its tail
+// pass 3 (dim 0): add what a run accumulated in earlier tiles to the tile that holds its tail.
+// A segmented scan over the per-tile aggregates, ONE THREAD PER TILE (coalesced), in two small launches:
+//   rbk_carry_local_kernel   every CTA scans its 256 aggregates (warp shuffles + shared memory), leaves each tile's
+//                            CTA-local exclusive state and the CTA's own aggregate;
+//   rbk_carry_apply_kernel   every CTA folds the aggregates of the CTAs before it (one warp, in order), completes its
+//                            tiles' carries and applies them.
+// (First cut: one CTA walked all tiles with a dependent-load chain per tile -- 1.03 ms for the 131072 tiles of 2^28 keys,
+// more than the two streaming passes together.)
 // ------------------------------------------------------------------------------------------------
 template<int OP, typename To>
-__global__ void __launch_bounds__(kRbkThreads) rbk_fixup_kernel(const uint *__restrict__ keys, dim_t ntiles,
-                                                                 const uint *__restrict__ tile_base,
-                                                                 const Slot<Seg<typename compute_of<To>::type>> *__restrict__ tile_agg,
-                                                                 To *vals_out, dim_t n_reduced) {
+__global__ void __launch_bounds__(kRbkThreads) rbk_carry_local_kernel(dim_t ntiles,
+                                                                       const Slot<Seg<typename compute_of<To>::type>> *__restrict__ tile_agg,
+                                                                       Slot<Seg<typename compute_of<To>::type>> *__restrict__ loc_exc,
+                                                                       Slot<Seg<typename compute_of<To>::type>> *__restrict__ blk_agg) {
     typedef typename compute_of<To>::type Acc;
     typedef Rule<OP, To, Acc> R;
     typedef SOps<R, Acc, true> S;
@@ -243,14 +250,10 @@ __global__ void __launch_bounds__(kRbkThreads) rbk_fixup_kernel(const uint *__re
     constexpr int NW = kRbkThreads / 32;
     __shared__ State sm_w[NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const dim_t c = blockIdx.x;
-    const Slot<State> *agg = tile_agg + c * ntiles;
-    To *out = vals_out + c * n_reduced;
-    const dim_t per = (ntiles + kRbkThreads - 1) / kRbkThreads;
-    const dim_t lo = (dim_t)tid * per, hi = min(lo + per, ntiles);
-    State tot = S::identity();
-    for (dim_t t = lo; t < hi; t++) tot = S::join(tot, agg[t].v);
-    State inc = tot;
+    const dim_t c = blockIdx.y, nblk = gridDim.x;
+    const dim_t t = (dim_t)blockIdx.x * kRbkThreads + tid;
+    const State mine = t < ntiles ? tile_agg[c * ntiles + t].v : S::identity();
+    State inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const State o = shfl_up(inc, d);
@@ -264,19 +267,49 @@ __global__ void __launch_bounds__(kRbkThreads) rbk_fixup_kernel(const uint *__re
 #pragma unroll
     for (int q = 0; q < NW; q++)
         if (q < warp) carry = S::join(carry, sm_w[q]);
-    carry = S::join(carry, exc);
-    for (dim_t t = lo; t < hi; t++) {
-        if (t > 0) {
-            const dim_t p = t * kRbkTile;
-            const bool starts_run = __ldg(keys + p) != __ldg(keys + p - 1);
-            const uint b = __ldg(tile_base + t), heads = __ldg(tile_base + t + 1) - b;
-            // the run entering from the left ends in this tile iff the tile has a head or is the last one
-            if (!starts_run && (heads > 0u || t == ntiles - 1)) {
-                To *o = out + (b - 1u);
-                *o = conv<To, Acc>(R::join(carry.val, conv<Acc, To>(*o)));
-            }
+    if (t < ntiles) loc_exc[c * ntiles + t].v = S::join(carry, exc);
+    if (tid == kRbkThreads - 1) blk_agg[c * nblk + blockIdx.x].v = S::join(carry, inc);
+}
+
+template<int OP, typename To>
+__global__ void __launch_bounds__(kRbkThreads) rbk_carry_apply_kernel(const uint *__restrict__ keys, dim_t ntiles,
+                                                                       const uint *__restrict__ tile_base,
+                                                                       const Slot<Seg<typename compute_of<To>::type>> *__restrict__ loc_exc,
+                                                                       const Slot<Seg<typename compute_of<To>::type>> *__restrict__ blk_agg,
+                                                                       To *vals_out, dim_t n_reduced) {
+    typedef typename compute_of<To>::type Acc;
+    typedef Rule<OP, To, Acc> R;
+    typedef SOps<R, Acc, true> S;
+    typedef typename S::State State;
+    __shared__ State sm_before;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const dim_t c = blockIdx.y, nblk = gridDim.x;
+    if (warp == 0) {
+        // state of everything before this CTA's first tile: the aggregates of the CTAs before it, folded in order
+        // (each lane takes a contiguous share, then an ordered shuffle scan)
+        const dim_t nb = blockIdx.x;
+        const dim_t per = (nb + 31) / 32;
+        const dim_t lo = min((dim_t)lane * per, nb), hi = min(lo + per, nb);
+        State tot = S::identity();
+        for (dim_t q = lo; q < hi; q++) tot = S::join(tot, blk_agg[c * nblk + q].v);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const State o = shfl_up(tot, d);
+            if (lane >= d) tot = S::join(o, tot);
         }
-        carry = S::join(carry, agg[t].v);
+        if (lane == 31) sm_before = tot;
+    }
+    __syncthreads();
+    const dim_t t = (dim_t)blockIdx.x * kRbkThreads + tid;
+    if (t == 0 || t >= ntiles) return;
+    const dim_t p = t * kRbkTile;
+    const bool starts_run = __ldg(keys + p) != __ldg(keys + p - 1);
+    const uint b = __ldg(tile_base + t), heads = __ldg(tile_base + t + 1) - b;
+    // the run entering from the left ends in this tile iff the tile has a head or is the last one
+    if (!starts_run && (heads > 0u || t == ntiles - 1)) {
+        const State carry = S::join(sm_before, loc_exc[c * ntiles + t].v);
+        To *o = vals_out + c * n_reduced + (b - 1u);
+        *o = conv<To, Acc>(R::join(carry.val, conv<Acc, To>(*o)));
     }
 }
 
@@ -377,17 +410,29 @@ void run_rbk(const LaunchCtx &c, const void *keys, dim_t n, const View &vals, in
         a.n_reduced = n_reduced;
         a.prm = prm;
         if (a.g.ncols == 0) return;
-        a.tile_agg = (Slot<Seg<Acc>> *)c.scratch->need_partials((size_t)ntiles * a.g.ncols * sizeof(Slot<Seg<Acc>>));
+        // one partials block: [tile aggregates | CTA-local exclusive states | per-CTA aggregates of the carry scan]
+        const dim_t nblk = (ntiles + kRbkThreads - 1) / kRbkThreads;
+        const size_t per = (size_t)ntiles * a.g.ncols;
+        Slot<Seg<Acc>> *scr = (Slot<Seg<Acc>> *)c.scratch->need_partials((2 * per + (size_t)nblk * a.g.ncols) * sizeof(Slot<Seg<Acc>>));
+        a.tile_agg = scr;
+        Slot<Seg<Acc>> *loc_exc = scr + per, *blk_agg = scr + 2 * per;
         dim_t grid = ntiles * a.g.ncols;
         const dim_t cap = (dim_t)c.sms * 32;
         if (grid > cap) grid = cap;
         rbk_tile_kernel<OP, Ti, To><<<(unsigned)grid, kRbkThreads, 0, c.stream>>>(a);
         post_launch_check("rbk_tile_kernel");
-        if (a.g.ncols > 0x7fffffffLL) fail(AF_ERR_SIZE, "reduce by key: too many columns");
-        rbk_fixup_kernel<OP, To><<<(unsigned)a.g.ncols, kRbkThreads, 0, c.stream>>>((const uint *)keys, ntiles, tile_base,
-                                                                                    a.tile_agg, (To *)vals_out, n_reduced);
-        post_launch_check("rbk_fixup_kernel");
-        note_launches(2);
+        if (a.g.ncols > 65535) fail(AF_ERR_SIZE, "reduce by key: too many columns (%lld)", (long long)a.g.ncols);
+        if (ntiles > 1) {
+            const dim3 cgrid((unsigned)nblk, (unsigned)a.g.ncols, 1);
+            rbk_carry_local_kernel<OP, To><<<cgrid, kRbkThreads, 0, c.stream>>>(ntiles, a.tile_agg, loc_exc, blk_agg);
+            post_launch_check("rbk_carry_local_kernel");
+            rbk_carry_apply_kernel<OP, To><<<cgrid, kRbkThreads, 0, c.stream>>>((const uint *)keys, ntiles, tile_base, loc_exc,
+                                                                                 blk_agg, (To *)vals_out, n_reduced);
+            post_launch_check("rbk_carry_apply_kernel");
+            note_launches(3);
+        } else {
+            note_launches(1);
+        }
         return;
     }
     if (keys_out) {

@@ -117,12 +117,38 @@ template<typename Ti, typename Tc, typename To> struct VarPolicy {
         o.val[i] = conv<To, Tc>(v);
         if (o.mean) o.mean[i] = conv<To, Tc>(a.m);
     }
+    // a 16-byte vector at a time: mean and M2 of its V elements with compile-time weights, then ONE pairwise merge -- one
+    // division per vector instead of one per element (the per-element Welford update ran at 3.1 TB/s on f32 columns)
     AFB_DI static Acc fold16(const Params &p, Acc acc, const Vec16 &v, uint idx0) {
         constexpr int V = VecN<In>::value;
         const In *e = reinterpret_cast<const In *>(&v);
+        if constexpr (V == 1) {
+            return step(acc, ToCompute<Tc, Ti>::go(e[0]));
+        } else {
+            Tc x[V];
+            Tc sum = zero_<Tc>();
 #pragma unroll
-        for (int k = 0; k < V; k++) acc = step(acc, ToCompute<Tc, Ti>::go(e[k]));
-        return acc;
+            for (int k = 0; k < V; k++) {
+                x[k] = ToCompute<Tc, Ti>::go(e[k]);
+                sum = add_<Tc>(sum, x[k]);
+            }
+            const Tc mb = scale_<Tc, B>(sum, (B)1 / (B)V);
+            Tc m2b = zero_<Tc>();
+#pragma unroll
+            for (int k = 0; k < V; k++) {
+                const Tc d = sub_<Tc>(x[k], mb);
+                m2b = add_<Tc>(m2b, mul_<Tc>(d, d));
+            }
+            if (acc.n == 0u) return Acc{mb, m2b, (uint)V};
+            const uint n = acc.n + (uint)V;
+            const B fb = (B)V / (B)n;
+            const Tc d = sub_<Tc>(mb, acc.m);
+            Acc r;
+            r.n = n;
+            r.m = add_<Tc>(acc.m, scale_<Tc, B>(d, fb));
+            r.m2 = add_<Tc>(add_<Tc>(acc.m2, m2b), scale_<Tc, B>(mul_<Tc>(d, d), fb * (B)acc.n));
+            return r;
+        }
     }
 };
 
