@@ -588,6 +588,52 @@ def set_unique(a, is_sorted=False):
     return Array(h)
 
 
+# ---- lazily evaluated element-wise expressions (af::operator+ ... af::sqrt): fused into whole-array reductions ------------
+def _binary(fn, a, b):
+    h = _vp()
+    _check(fn(ctypes.byref(h), a.handle, b.handle, ctypes.c_bool(False)))
+    return Array(h)
+
+
+def _unary(fn, a):
+    h = _vp()
+    _check(fn(ctypes.byref(h), a.handle))
+    return Array(h)
+
+
+def _operand(a, like):
+    """a scalar becomes a (lazy) constant of `like`'s dims, typed as the C++ operators do (array op double)"""
+    if isinstance(a, Array):
+        return a
+    t = like.dtype if like.dtype in (f32, f64) else f32
+    return constant(float(a), [int(d) for d in like.dims], t)
+
+
+def _bin(fn):
+    def op(a, b):
+        like = a if isinstance(a, Array) else b
+        return _binary(fn, _operand(a, like), _operand(b, like))
+    return op
+
+
+add, sub, mul, div = _bin(lib.af_add), _bin(lib.af_sub), _bin(lib.af_mul), _bin(lib.af_div)
+lt, gt, le, ge, eq, neq = _bin(lib.af_lt), _bin(lib.af_gt), _bin(lib.af_le), _bin(lib.af_ge), _bin(lib.af_eq), _bin(lib.af_neq)
+logical_and, logical_or = _bin(lib.af_and), _bin(lib.af_or)
+minof, maxof, pow = _bin(lib.af_minof), _bin(lib.af_maxof), _bin(lib.af_pow)   # noqa: A001
+
+
+def sqrt(a):
+    return _unary(lib.af_sqrt, a)
+
+
+def abs(a):   # noqa: A001
+    return _unary(lib.af_abs, a)
+
+
+def logical_not(a):
+    return _unary(lib.af_not, a)
+
+
 # ---- issue / collect (include/afb200.h afx_*_async): enqueue many ops, collect their O(1) host results afterwards --------
 OP_ADD, OP_MUL, OP_MIN, OP_MAX, OP_COUNT, OP_ALL, OP_ANY = range(7)
 

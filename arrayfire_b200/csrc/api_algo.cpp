@@ -17,6 +17,7 @@ using namespace afb;
 
 namespace afb {
 Array *make_dense_copy(const Array &a);
+bool expr_reduce_all(const Array &a, int mode, af_dtype *result_type, HostRet *ret_out);
 }
 
 namespace {
@@ -145,6 +146,29 @@ void decode_scalar(af_dtype t, const void *raw, double *real, double *imag) {
 af_err reduce_all_scalar(double *real, double *imag, const af_array in_h, Family fam, Op op, bool change_nan,
                          double nanval, bool need_ndims) {
     AFB_API_BEGIN
+    // an unevaluated element-wise expression (api_expr.cpp) is reduced FUSED: the interpreter runs in the reduction's load
+    // path, the operands are streamed once and no temporary is written
+    {
+        Array *lazy = peek_handle(in_h);
+        if (lazy->expr && real != nullptr && lazy->elements() > 0 && !change_nan &&
+            (op == OP_ADD || op == OP_NOTZERO || op == OP_MIN || op == OP_MAX || op == OP_OR || op == OP_AND)) {
+            check_same_device(*lazy);
+            *real = 0;
+            if (imag) *imag = 0;
+            // sum of a b8 expression counts (reduce.cpp:358-366), like the evaluated path
+            int mode = op == OP_ADD ? (lazy->info.type == b8 ? EXR_COUNT : EXR_SUM)
+                     : op == OP_NOTZERO ? EXR_COUNT : op == OP_MIN ? EXR_MIN : op == OP_MAX ? EXR_MAX : op == OP_OR ? EXR_ANY : EXR_ALL;
+            if ((op == OP_MIN || op == OP_MAX) && lazy->info.type == b8) mode = op == OP_MIN ? EXR_ALL : EXR_ANY;   // b8 min = and, max = or
+            af_dtype rt;
+            HostRet ret;
+            if (expr_reduce_all(*lazy, mode, &rt, &ret)) {
+                LaunchCtx c = ctx_for_active_device();
+                wait_host_ret(c, ret);
+                decode_scalar(rt, ret.host, real, imag);
+                return AF_SUCCESS;
+            }
+        }
+    }
     Array *in = from_handle(in_h);
     if (need_ndims) AFB_ARG(2, in->ndims() > 0);  // reduce.cpp:646
     AFB_ARG(0, real != nullptr);

@@ -17,6 +17,10 @@
 
 using namespace afb;
 
+namespace afb {
+Array *lazy_constant(af_dtype type, const dim_t dims[4], double val);
+}
+
 namespace {
 
 void dims_from(unsigned ndims, const dim_t *dims, dim_t out[4]) {
@@ -168,7 +172,7 @@ af_err af_get_data_ptr(void *data, const af_array arr) {
 af_err af_release_array(af_array arr) {
     AFB_API_BEGIN
     if (arr == nullptr) return AF_SUCCESS;  // array.cpp:231
-    Array *a = from_handle(arr);
+    Array *a = peek_handle(arr);
     a->magic = 0;
     delete a;
     AFB_API_END
@@ -177,7 +181,7 @@ af_err af_release_array(af_array arr) {
 af_err af_retain_array(af_array *out, const af_array in) {
     AFB_API_BEGIN
     AFB_ARG(0, out != nullptr);
-    *out = retain(*from_handle(in));
+    *out = retain(*peek_handle(in));
     AFB_API_END
 }
 
@@ -198,18 +202,18 @@ af_err af_eval(af_array in) {
 af_err af_get_elements(dim_t *elems, const af_array arr) {
     AFB_API_BEGIN
     AFB_ARG(0, elems != nullptr);
-    *elems = from_handle(arr)->elements();
+    *elems = peek_handle(arr)->elements();
     AFB_API_END
 }
 af_err af_get_type(af_dtype *type, const af_array arr) {
     AFB_API_BEGIN
     AFB_ARG(0, type != nullptr);
-    *type = from_handle(arr)->info.type;
+    *type = peek_handle(arr)->info.type;
     AFB_API_END
 }
 af_err af_get_dims(dim_t *d0, dim_t *d1, dim_t *d2, dim_t *d3, const af_array arr) {
     AFB_API_BEGIN
-    Array *a = from_handle(arr);
+    Array *a = peek_handle(arr);
     if (d0) *d0 = a->info.dims[0];
     if (d1) *d1 = a->info.dims[1];
     if (d2) *d2 = a->info.dims[2];
@@ -240,25 +244,25 @@ af_err af_is_linear(bool *result, const af_array arr) {
 af_err af_get_numdims(unsigned *result, const af_array arr) {
     AFB_API_BEGIN
     AFB_ARG(0, result != nullptr);
-    *result = (unsigned)from_handle(arr)->ndims();
+    *result = (unsigned)peek_handle(arr)->ndims();
     AFB_API_END
 }
 af_err af_is_empty(bool *result, const af_array arr) {
     AFB_API_BEGIN
     AFB_ARG(0, result != nullptr);
-    *result = from_handle(arr)->elements() == 0;
+    *result = peek_handle(arr)->elements() == 0;
     AFB_API_END
 }
 af_err af_is_scalar(bool *result, const af_array arr) {
     AFB_API_BEGIN
     AFB_ARG(0, result != nullptr);
-    *result = from_handle(arr)->elements() == 1;
+    *result = peek_handle(arr)->elements() == 1;
     AFB_API_END
 }
 af_err af_is_vector(bool *result, const af_array arr) {
     AFB_API_BEGIN
     AFB_ARG(0, result != nullptr);
-    Array *a = from_handle(arr);
+    Array *a = peek_handle(arr);
     int big = 0;
     for (int i = 0; i < 4; i++) big += a->info.dims[i] > 1;
     *result = a->elements() > 0 && big == 1;
@@ -293,6 +297,11 @@ af_err af_constant(af_array *arr, const double val, const unsigned ndims, const 
     dim_t d[4];
     dims_from(ndims, dims, d);
     for (int i = 0; i < 4; i++) AFB_ARG(3, d[i] >= 0);
+    if ((type == f32 || type == f64 || type == b8) && d[0] * d[1] * d[2] * d[3] > 0) {
+        // a ScalarNode, as in the reference (data.cpp:45-90): no memory until a consumer needs the values
+        *arr = lazy_constant(type, d, val);
+        return AF_SUCCESS;
+    }
     Array *a = new_array(type, d);
     try {
         LaunchCtx c = ctx_for_active_device();

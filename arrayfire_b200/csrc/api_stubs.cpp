@@ -18,11 +18,11 @@
     }
 
 // element-wise arithmetic / logic used by af::array's operators (include/af/arith.h)
-AFB_STUB(af_add) AFB_STUB(af_sub) AFB_STUB(af_mul) AFB_STUB(af_div) AFB_STUB(af_mod)
-AFB_STUB(af_lt) AFB_STUB(af_gt) AFB_STUB(af_le) AFB_STUB(af_ge) AFB_STUB(af_eq) AFB_STUB(af_neq)
-AFB_STUB(af_and) AFB_STUB(af_or) AFB_STUB(af_not) AFB_STUB(af_bitnot)
+AFB_STUB(af_mod)
+
+AFB_STUB(af_bitnot)
 AFB_STUB(af_bitand) AFB_STUB(af_bitor) AFB_STUB(af_bitxor) AFB_STUB(af_bitshiftl) AFB_STUB(af_bitshiftr)
-AFB_STUB(af_real) AFB_STUB(af_imag) AFB_STUB(af_cplx) AFB_STUB(af_cplx2) AFB_STUB(af_conjg) AFB_STUB(af_abs)
+AFB_STUB(af_real) AFB_STUB(af_imag) AFB_STUB(af_cplx) AFB_STUB(af_cplx2) AFB_STUB(af_conjg) 
 // data movement / generation (include/af/data.h, index.h)
 AFB_STUB(af_tile) AFB_STUB(af_reorder) AFB_STUB(af_join) AFB_STUB(af_join_many) AFB_STUB(af_shift) AFB_STUB(af_flip)
 AFB_STUB(af_lower) AFB_STUB(af_upper) AFB_STUB(af_pad) AFB_STUB(af_range) AFB_STUB(af_iota) AFB_STUB(af_identity)

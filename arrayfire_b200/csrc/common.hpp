@@ -123,10 +123,13 @@ struct Info {
 
 constexpr unsigned kMagic = 0xAFB20001u;
 
+struct ExprNode;   // api_expr.cpp
+
 struct Array {
     Info info;
     unsigned magic = kMagic;
     std::shared_ptr<Buffer> buf;  // shared between retained handles and views
+    std::shared_ptr<ExprNode> expr;   // set (and buf empty) while the array is an unevaluated element-wise expression
 
     int device() const { return (int)(info.devId & 0xff); }
     dim_t elements() const { return info.dims[0] * info.dims[1] * info.dims[2] * info.dims[3]; }
@@ -136,7 +139,9 @@ struct Array {
     void *data() { return (char *)buf->ptr + (size_t)info.offset * dtype_size(info.type); }
 };
 
-Array *from_handle(af_array h);              // validates; throws AF_ERR_ARG on null/bad magic
+Array *from_handle(af_array h);              // validates; throws AF_ERR_ARG on null/bad magic; EVALUATES a lazy expression
+Array *peek_handle(af_array h);              // the same without evaluating (metadata getters, the fused consumers)
+void materialize(Array &a);                  // api_expr.cpp: expression -> dense buffer (in place)
 Array *new_array(af_dtype t, const dim_t dims[4]);  // dense, freshly allocated on the active device
 Array *new_view(const Array &parent, const dim_t dims[4], dim_t offset, const dim_t strides[4]);
 Array *retain(const Array &a);
@@ -243,6 +248,27 @@ bool launch_cov_cols(const LaunchCtx &c, af_dtype t, const void *x, const void *
 bool launch_diff(const LaunchCtx &c, af_dtype t, const View &in, int dim, int order, void *out);
 bool launch_differs(const LaunchCtx &c, af_dtype t, const void *in, dim_t n, unsigned char *mask);
 bool launch_gather(const LaunchCtx &c, af_dtype t, const void *in, const unsigned *idx, dim_t n, void *out);
+// ---- lazily evaluated element-wise expressions (api_expr.cpp builds them, kernels/expr.cu interprets them)
+enum ExprOp {
+    EX_LEAF = 0, EX_CONST = 1,
+    EX_ADD, EX_SUB, EX_MUL, EX_DIV, EX_LT, EX_GT, EX_LE, EX_GE, EX_EQ, EX_NEQ, EX_AND, EX_OR, EX_MIN, EX_MAX, EX_POW,
+    EX_SQRT, EX_ABS, EX_NEG, EX_NOT,
+    EX_FIRST_UNARY = EX_SQRT
+};
+enum ExprReduce { EXR_SUM = 0, EXR_COUNT = 1, EXR_MIN = 2, EXR_MAX = 3, EXR_ANY = 4, EXR_ALL = 5 };
+constexpr int kExprMaxOps = 48, kExprMaxLeaves = 8, kExprMaxConsts = 8;
+struct ExprProg {                 // a postfix program over dense, equally shaped operands
+    int n;                        // instructions
+    unsigned char op[kExprMaxOps], arg[kExprMaxOps];
+    const void *leaf[kExprMaxLeaves];
+    int leaf_type[kExprMaxLeaves];   // 0 f32, 1 f64, 2 b8
+    double cst[kExprMaxConsts];
+    int aligned;                  // every f32 leaf is 16-byte aligned
+};
+// out_type: 0 f32, 1 f64, 2 b8; dbl: interpret in double (any f64 operand) instead of float
+void launch_expr_eval(const LaunchCtx &c, const ExprProg &p, bool dbl, void *out, int out_type, dim_t n);
+// result (device `out`, also published through ret): float / double for sum, min, max; u32 for count; b8 for any / all
+void launch_expr_reduce(const LaunchCtx &c, const ExprProg &p, bool dbl, int mode, dim_t n, void *out, const HostRet *ret);
 // ---- reductions by key (kernels/rbk_*.cu): keys = n dense 32-bit keys, runs of equal consecutive keys are segments
 // pass 1: number of runs -> published through `ret` (u64); tile_base[t] (device, ntiles + 1 words) = runs starting before tile t
 dim_t rbk_tile_elems();

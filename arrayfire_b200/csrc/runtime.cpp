@@ -511,10 +511,16 @@ void dense_strides(const dim_t dims[4], dim_t strides[4]) {
     for (int i = 1; i < 4; i++) strides[i] = strides[i - 1] * dims[i - 1];
 }
 
-Array *from_handle(af_array h) {
+Array *peek_handle(af_array h) {
     if (!h) fail(AF_ERR_ARG, "null af_array handle");
     Array *a = reinterpret_cast<Array *>(h);
     if (a->magic != kMagic) fail(AF_ERR_INVALID_ARRAY, "af_array handle was not created by libafb200");
+    return a;
+}
+
+Array *from_handle(af_array h) {
+    Array *a = peek_handle(h);
+    if (a->expr) materialize(*a);
     return a;
 }
 
@@ -554,6 +560,7 @@ Array *retain(const Array &p) {
     Array *a = new Array();
     a->info = p.info;
     a->buf = p.buf;
+    a->expr = p.expr;
     return a;
 }
 

@@ -283,6 +283,32 @@ AFAPI af_err af_diff1(af_array *out, const af_array in, const int dim);         
 AFAPI af_err af_diff2(af_array *out, const af_array in, const int dim);                                   /* diff.cpp:76 */
 AFAPI af_err af_set_unique(af_array *out, const af_array in, const bool is_sorted);                       /* set.cpp:32 */
 
+/* ===================== lazily evaluated element-wise expressions =====================
+ * include/af/arith.h.  These return UNEVALUATED arrays (the reference's JIT nodes, src/api/c/binary.cpp:40-120); a
+ * whole-array reduction (af_sum_all, af_count_all, af_min_all, af_max_all, af_any_true_all, af_all_true_all) that consumes
+ * one interprets the expression in its load path -- sum<float>(sqrt(x*x + y*y) < 1) of examples/benchmarks/pi.cpp streams x
+ * and y once and writes nothing.  Any other consumer evaluates the expression into an array first.  f32 / f64 / b8 operands
+ * of identical dims (`batch` is ignored); everything else returns AF_ERR_NOT_SUPPORTED.  af_constant of these types is
+ * lazy as well (no memory until needed). */
+AFAPI af_err af_add(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_sub(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_mul(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_div(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_minof(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_maxof(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_pow(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_lt(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_gt(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_le(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_ge(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_eq(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_neq(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_and(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_or(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
+AFAPI af_err af_not(af_array *out, const af_array in);
+AFAPI af_err af_sqrt(af_array *out, const af_array in);
+AFAPI af_err af_abs(af_array *out, const af_array in);
+
 /* ===================== afx_*: sharded whole-array extension ============================
  * New functionality (the reference has no multi-GPU path).  One process
  * per GPU holds the shard [rank*N/G, (rank+1)*N/G) of a flattened array; each call below

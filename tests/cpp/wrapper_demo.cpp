@@ -122,10 +122,13 @@ int main(int argc, char **argv) {
         stats[2] = af::stdev<float>(z, AF_VARIANCE_POPULATION);
         stats[3] = af::corrcoef<float>(z, z);
         dump_bytes("stats.out", stats, sizeof(stats));
+        // the pi benchmark's expression through af::array's operators: unevaluated, then fused into the reduction
+        stats[0] = af::sum<float>((z * z + z * z) < 9.0);   // (af::sqrt lives in the wrapper's unary.cpp, not linked here)
+        dump_bytes("pi_like.out", stats, sizeof(double));
         // an entry point outside the path must fail loudly (af::exception carrying AF_ERR_NOT_SUPPORTED = 301)
         int unsupported = 0;
         try {
-            af::array y = x + x;
+            af::array y = x % x;      // af_mod: outside the path
             (void)y;
         } catch (af::exception &e) { unsupported = (int)e.err(); }
         dump_bytes("unsupported.out", &unsupported, sizeof(unsupported));

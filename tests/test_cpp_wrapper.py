@@ -150,4 +150,6 @@ def test_cpp_program_through_the_reference_wrapper(port_oracle):
         st = np.fromfile(os.path.join(d, "stats.out"), dtype=np.float64)
         assert abs(st[0] - z64.mean()) <= 1e-4 and abs(st[1] - z64.var(ddof=1)) <= 1e-3
         assert abs(st[2] - z64.std()) <= 1e-3 and abs(st[3] - 1.0) <= 1e-4
+        inside = np.fromfile(os.path.join(d, "pi_like.out"), dtype=np.float64)[0]
+        assert inside == float(np.count_nonzero((z * z + z * z) < np.float32(9.0)))
         assert int(np.fromfile(os.path.join(d, "unsupported.out"), np.int32)[0]) == 301   # AF_ERR_NOT_SUPPORTED
