@@ -386,16 +386,109 @@ af_err af_cov(af_array *out, const af_array x, const af_array y, const bool isbi
     return af_cov_v2(out, x, y, isbiased ? AF_VARIANCE_SAMPLE : AF_VARIANCE_POPULATION);
 }
 
-// the weighted forms need a second input stream in the reduction load: not built yet -- fail loudly, never silently
-#define AFB_NOT_YET(name, ...)                                                                       \
-    af_err name(__VA_ARGS__) {                                                                       \
-        AFB_API_BEGIN                                                                                \
-        fail(AF_ERR_NOT_SUPPORTED, #name ": weighted statistics are not supported by libafb200 yet"); \
-        AFB_API_END                                                                                  \
+// ---- weighted forms, composed from this library's own lazy element-wise expressions (api_expr.cpp) and reductions:
+//   mean_w     = sum(w * x) / sum(w)                      (mean.cpp:97-149, cpu/kernel/mean.hpp:41-82 computes a running form)
+//   var_all_w  = sum(w * (x - mean_w)^2) / sum(w)         (var.cpp:77-102) -- the whole-array forms run FUSED: x and w are
+//                streamed once per reduction and no temporary is written
+// Real inputs only (integers are cast to the f32 / f64 the reference computes in); the dim-wise weighted variance needs a
+// broadcast of the means along `dim`, which this library has no kernel for yet.
+namespace {
+struct H {           // releases af_array temporaries
+    af_array h = nullptr;
+    ~H() { if (h) af_release_array(h); }
+};
+#define AFB_TRY(call)                        \
+    do {                                     \
+        af_err e_ = (call);                  \
+        if (e_ != AF_SUCCESS) return e_;     \
+    } while (0)
+
+// x as the compute type (f32, or f64 for f64 / s64 / u64) and w as the same type; complex / f16 are not handled
+af_err weighted_operands(H &x, H &w, const af_array in, const af_array weights, int arg_w) {
+    AFB_API_BEGIN
+    Array *a = from_handle(in), *ww = from_handle(weights);
+    AFB_ARG(arg_w, ww->info.type == f32 || ww->info.type == f64);            // mean.cpp:105-110
+    const af_dtype t = a->info.type;
+    if (t == c32 || t == c64 || t == f16) fail(AF_ERR_NOT_SUPPORTED, "weighted statistics: complex and f16 inputs are not supported by libafb200");
+    for (int i = 0; i < 4; i++)
+        if (a->info.dims[i] != ww->info.dims[i]) fail(AF_ERR_NOT_SUPPORTED, "weighted statistics: the weights must have the dims of the input (no broadcast)");
+    AFB_API_END
+}
+af_err weighted_cast(H &x, H &w, const af_array in, const af_array weights) {
+    af_dtype t;
+    AFB_TRY(af_get_type(&t, in));
+    const af_dtype tc = (t == f64 || t == s64 || t == u64) ? f64 : f32;
+    AFB_TRY(af_cast(&x.h, in, tc));
+    AFB_TRY(af_cast(&w.h, weights, tc));
+    return AF_SUCCESS;
+}
+}  // namespace
+
+af_err af_mean_weighted(af_array *out, const af_array in, const af_array weights, const dim_t dim) {
+    {
+        AFB_API_BEGIN
+        AFB_ARG(3, dim >= 0 && dim <= 3);
+        AFB_ARG(0, out != nullptr);
+        }
+        catch (...) { return ::afb::current_exception_to_err(); }
     }
-AFB_NOT_YET(af_mean_weighted, af_array *, const af_array, const af_array, const dim_t)
-AFB_NOT_YET(af_var_weighted, af_array *, const af_array, const af_array, const dim_t)
-AFB_NOT_YET(af_mean_all_weighted, double *, double *, const af_array, const af_array)
-AFB_NOT_YET(af_var_all_weighted, double *, double *, const af_array, const af_array)
+    H x, w, xw, num, den, q;
+    AFB_TRY(weighted_operands(x, w, in, weights, 2));
+    AFB_TRY(weighted_cast(x, w, in, weights));
+    AFB_TRY(af_mul(&xw.h, x.h, w.h, false));
+    AFB_TRY(af_sum(&num.h, xw.h, (int)dim));
+    AFB_TRY(af_sum(&den.h, w.h, (int)dim));
+    AFB_TRY(af_div(&q.h, num.h, den.h, false));
+    AFB_TRY(af_eval(q.h));
+    *out = q.h;
+    q.h = nullptr;
+    return AF_SUCCESS;
+}
+
+af_err af_mean_all_weighted(double *real, double *imag, const af_array in, const af_array weights) {
+    {
+        AFB_API_BEGIN
+        AFB_ARG(0, real != nullptr);
+        }
+        catch (...) { return ::afb::current_exception_to_err(); }
+    }
+    H x, w, xw;
+    AFB_TRY(weighted_operands(x, w, in, weights, 3));
+    AFB_TRY(weighted_cast(x, w, in, weights));
+    AFB_TRY(af_mul(&xw.h, x.h, w.h, false));
+    double num = 0, den = 0, im = 0;
+    AFB_TRY(af_sum_all(&num, &im, xw.h));          // fused: one pass over x and w
+    AFB_TRY(af_sum_all(&den, &im, w.h));
+    *real = num / den;
+    if (imag) *imag = 0;
+    return AF_SUCCESS;
+}
+
+af_err af_var_all_weighted(double *real, double *imag, const af_array in, const af_array weights) {
+    double mean = 0, im = 0;
+    AFB_TRY(af_mean_all_weighted(&mean, &im, in, weights));
+    H x, w, m, d, d2, wd2;
+    AFB_TRY(weighted_cast(x, w, in, weights));
+    af_dtype tc;
+    AFB_TRY(af_get_type(&tc, x.h));
+    dim_t dims[4];
+    AFB_TRY(af_get_dims(&dims[0], &dims[1], &dims[2], &dims[3], x.h));
+    AFB_TRY(af_constant(&m.h, mean, 4, dims, tc));
+    AFB_TRY(af_sub(&d.h, x.h, m.h, false));
+    AFB_TRY(af_mul(&d2.h, d.h, d.h, false));
+    AFB_TRY(af_mul(&wd2.h, d2.h, w.h, false));
+    double num = 0, den = 0;
+    AFB_TRY(af_sum_all(&num, &im, wd2.h));         // fused: sum(w * (x - mean)^2) in one pass
+    AFB_TRY(af_sum_all(&den, &im, w.h));
+    *real = num / den;
+    if (imag) *imag = 0;
+    return AF_SUCCESS;
+}
+
+af_err af_var_weighted(af_array *, const af_array, const af_array, const dim_t) {
+    AFB_API_BEGIN
+    fail(AF_ERR_NOT_SUPPORTED, "af_var_weighted: the dim-wise weighted variance needs a broadcast of the means; not supported by libafb200 yet");
+    AFB_API_END
+}
 
 }  // extern "C"

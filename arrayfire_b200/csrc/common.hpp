@@ -48,7 +48,13 @@ af_err current_exception_to_err() noexcept;                 // the CATCHALL of t
             ::afb::fail(e_ == cudaErrorMemoryAllocation ? AF_ERR_NO_MEM : AF_ERR_RUNTIME,           \
                         "CUDA error %d (%s) at %s:%d: %s", (int)e_, cudaGetErrorName(e_), __FILE__, __LINE__, #call); \
     } while (0)
-#define AFB_API_BEGIN try {
+// every public entry point is an NVTX range named after the function (visible in Nsight Systems / Compute timelines, like
+// the reference's AF_TRACE spans; a no-op costing a few nanoseconds when no tool is attached)
+struct NvtxScope {
+    explicit NvtxScope(const char *name);
+    ~NvtxScope();
+};
+#define AFB_API_BEGIN try { ::afb::NvtxScope afb_nvtx_scope_(__func__);
 #define AFB_API_END                                    \
     }                                                  \
     catch (...) { return ::afb::current_exception_to_err(); } \

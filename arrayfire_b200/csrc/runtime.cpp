@@ -9,6 +9,8 @@
 //   garbage-collect and retry once on out-of-memory
 // The implementation is this library's own: a mutex-protected size-bucketed pool per
 // device plus a persistent scratch arena so that hot ops allocate nothing per call.
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.hpp"
 
 #include <atomic>
@@ -127,7 +129,11 @@ Device &dev(int d) {
 
 thread_local int tls_device = -1;
 
+
 }  // namespace
+
+NvtxScope::NvtxScope(const char *name) { nvtxRangePushA(name); }
+NvtxScope::~NvtxScope() { nvtxRangePop(); }
 
 int device_count() {
     std::call_once(g_once, init_globals);

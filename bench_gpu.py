@@ -560,6 +560,8 @@ def gpu_arm(args):
             "X.norm2_f32 (C3)": (lambda: af.norm(x3), 4 * c3),
             "X.corrcoef_f32 (C3 x, C3 u)": (lambda: af.corrcoef(x3, u3), 8 * c3),
             "X.sum_by_key_s32 (C4 keys + values)": (lambda: af.sum_by_key(k4, v4, 0), 8 * c4),
+            "X.pi_count_f32 sum(sqrt(x*x+y*y)<1) (C3 x, C3 u), fused expression": (
+                lambda: af.sum_all(af.lt(af.sqrt(af.add(af.mul(x3, x3), af.mul(u3, u3))), 1.0)), 8 * c3),
         }
         extras = {}
         for name, (fn, nbytes) in xs.items():

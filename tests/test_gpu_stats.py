@@ -162,9 +162,9 @@ def test_reference_known_answers_on_gpu(af):
         af.stdev(A(np.full(10, 1 - 1j, dtype=np.complex128)), 0)
     with pytest.raises(af.AfError):
         af._check(af.lib.af_stdev(__import__("ctypes").byref(af._vp()), ones.handle, __import__("ctypes").c_longlong(5)))
-    # weighted forms fail loudly
+    # the one weighted form without a kernel fails loudly
     with pytest.raises(af.AfError) as ei:
-        af._check(af.lib.af_mean_weighted(__import__("ctypes").byref(af._vp()), ones.handle, ones.handle, __import__("ctypes").c_longlong(0)))
+        af._check(af.lib.af_var_weighted(__import__("ctypes").byref(af._vp()), ones.handle, ones.handle, __import__("ctypes").c_longlong(0)))
     assert ei.value.code == 301
 
 
@@ -230,3 +230,38 @@ def test_corrcoef_cov(af, port_oracle):
                 if x.size <= 4096:
                     _, oc = orc.cov(x, y, bias)
                     assert np.abs(got.to_numpy().reshape(-1) - oc.reshape(-1)).max() <= tol * scale
+
+
+def test_weighted_mean_and_variance(af):
+    """af_mean_weighted / af_mean_all_weighted / af_var_all_weighted (mean.cpp:97-229, var.cpp:77-102, 374-416): composed from
+    the lazy element-wise expressions, the whole-array forms fused into one pass per reduction (test/mean.cpp:311-352)"""
+    import ctypes
+    rng = np.random.default_rng(14)
+    for dt in (np.float32, np.float64, np.int32, np.uint8):
+        for shape in [(512,), (100, 30), (20, 7, 3)]:
+            x = (rng.standard_normal(shape) * 3 + 1).astype(dt) if np.issubdtype(dt, np.floating) else rng.integers(0, 50, shape).astype(dt)
+            wdt = np.float64 if dt == np.float64 else np.float32
+            w = (rng.random(shape) + 0.1).astype(wdt)
+            x, w = np.asfortranarray(x), np.asfortranarray(w)
+            gx, gw = af.Array.from_numpy(x), af.Array.from_numpy(w)
+            x64, w64 = x.astype(np.float64), w.astype(np.float64)
+            tol = 1e-11 if dt == np.float64 else 2e-5
+            scale = float(np.abs(x64).max()) + 1.0
+            re, im = ctypes.c_double(), ctypes.c_double()
+            af._check(af.lib.af_mean_all_weighted(ctypes.byref(re), ctypes.byref(im), gx.handle, gw.handle))
+            wm = (x64 * w64).sum() / w64.sum()
+            assert abs(re.value - wm) <= tol * scale
+            af._check(af.lib.af_var_all_weighted(ctypes.byref(re), ctypes.byref(im), gx.handle, gw.handle))
+            assert abs(re.value - (w64 * (x64 - wm) ** 2).sum() / w64.sum()) <= tol * scale * scale * 4
+            for dim in range(len(shape)):
+                h = af._vp()
+                af._check(af.lib.af_mean_weighted(ctypes.byref(h), gx.handle, gw.handle, ctypes.c_longlong(dim)))
+                got = af.Array(h).to_numpy()
+                want = (x64 * w64).sum(axis=dim) / w64.sum(axis=dim)
+                assert np.abs(got.reshape(-1, order="F") - want.reshape(-1, order="F")).max() <= tol * scale * 2, (dt, shape, dim)
+    # Mean.Issue2093 (test/mean.cpp:335-352): unit weights reproduce the plain mean
+    data = rng.random((1, 512)).astype(np.float32)
+    h = af._vp()
+    gd, g1 = af.Array.from_numpy(np.asfortranarray(data)), af.Array.from_numpy(np.ones((1, 512), np.float32, order="F"))
+    af._check(af.lib.af_mean_weighted(ctypes.byref(h), gd.handle, g1.handle, ctypes.c_longlong(1)))
+    assert abs(float(af.Array(h).to_numpy().reshape(-1)[0]) - float(data.astype(np.float64).mean())) <= 1e-3
