@@ -309,37 +309,11 @@ class LocalGpu:
         af._check(af.lib.afx_scan_shard(ct.byref(h), None, a.handle, ct.c_int(binop), ct.c_bool(inclusive), carry_ptr, None))
         return af.Array(h)
 
-    _TORCH_OF = {0: "float32", 2: "float64", 5: "int32", 8: "int64", 6: "int32", 9: "int64"}   # u32/u64: two's complement
-
     def scan_with_device_carry(self, a, binop, inclusive, gathered, part_code, out_code, rank):
-        """like scan_with_carry, but the carry-in is folded ON THE DEVICE from the all-gathered shard totals
-        (`gathered`: [world, PAYLOAD_BYTES] uint8 device tensor), in rank order, on the library's stream: the
-        sharded scan then needs no host synchronisation at all.  Returns None when the dtype / op pair has no
-        device fold here (the caller falls back to the host fold)."""
-        af, ct, torch = self.af, self.ct, self.torch
-        if part_code != out_code or out_code not in self._TORCH_OF:
-            return None
-        if out_code in (6, 9) and binop in (2, 3):
-            return None      # unsigned min / max do not survive the signed view
-        carry_ptr = None
-        if rank > 0:
-            tdt = getattr(torch, self._TORCH_OF[out_code])
-            isz = af._SIZE[out_code]
-            totals = gathered[:, :isz].contiguous().view(tdt).reshape(-1)[:rank]
-            if binop == 0:
-                c = torch.cumsum(totals, 0)[-1:]
-            elif binop == 1:
-                c = torch.cumprod(totals, 0)[-1:]
-            elif binop == 2:
-                c = torch.cummin(totals, 0).values[-1:]
-            else:
-                c = torch.cummax(totals, 0).values[-1:]
-            c = c.to(tdt).contiguous()
-            self._keep = c
-            carry_ptr = ct.c_void_p(c.data_ptr())
-        h = ct.c_void_p()
-        af._check(af.lib.afx_scan_shard(ct.byref(h), None, a.handle, ct.c_int(binop), ct.c_bool(inclusive), carry_ptr, None))
-        return af.Array(h)
+        """NCCL fall-back only (no peer memory): the carry-in is folded on the HOST from the gathered totals (the caller's
+        path when this returns None).  A device-side fold belongs to the fused kernels (afx_sharded_scan); round 1 had an
+        eager-torch fold here, removed so that no library-external kernel sits on the data path."""
+        return None
 
     def scan_by_key_local(self, buf, key, a, binop, inclusive):
         """carry-less segmented scan; buf[0:32] <- summary, buf[32:40] <- first key, buf[40:48] <- last key"""

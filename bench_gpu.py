@@ -508,8 +508,8 @@ def gpu_arm(args):
                 "algorithmic_bytes_per_launch": round(span_bytes / world / len(SPAN_OPS)),
                 "how": "mean over the 5 whole-array span_kernel launches of a step: algorithmic bytes / CUDA-event time of "
                        "those API calls on the library's stream (includes the scalar D2H); traffic = mean ncu dram read+write "
-                       "bytes of the same 5 launches (profiles/r01_span_kernel_traffic.json)"}
-    prof = os.path.join(ROOT, "profiles", "r01_span_kernel_traffic.json")
+                       "bytes of the same 5 launches (profiles/r02_span_kernel_traffic.json)"}
+    prof = os.path.join(ROOT, "profiles", "r02_span_kernel_traffic.json")
     if os.path.exists(prof):
         try:
             with open(prof) as f:
