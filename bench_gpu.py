@@ -505,6 +505,8 @@ def gpu_arm(args):
                 "frac": round(achieved / peak, 4), "traffic": None,
                 "kernel": "span_kernel (whole-array / long-column streaming reduction): " + ", ".join(SPAN_OPS),
                 "peak_source": peak_src, "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                "note": "the peak is a COPY figure (read + write streams); a read-only stream reaches ~7.1 TB/s of DRAM throughput on "
+                        "this part (ncu dram__throughput of span_kernel, profiles/r02a_ncu_full.md), so frac may exceed 1",
                 "algorithmic_bytes_per_launch": round(span_bytes / world / len(SPAN_OPS)),
                 "how": "mean over the 5 whole-array span_kernel launches of a step: algorithmic bytes / CUDA-event time of "
                        "those API calls on the library's stream (includes the scalar D2H); traffic = mean ncu dram read+write "
