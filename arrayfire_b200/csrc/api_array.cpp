@@ -74,9 +74,7 @@ af_err af_create_array(af_array *arr, const void *const data, const unsigned ndi
         const size_t bytes = (size_t)a->elements() * dtype_size(type);
         if (bytes) {
             AFB_ARG(1, data != nullptr);
-            cudaStream_t s = stream_of(a->device());
-            AFB_CUDA(cudaMemcpyAsync(a->data(), data, bytes, cudaMemcpyHostToDevice, s));
-            AFB_CUDA(cudaStreamSynchronize(s));  // the host buffer may be reused as soon as we return
+            upload_sync(a->device(), a->data(), data, bytes);  // the host buffer may be reused as soon as we return
         }
     } catch (...) {
         delete a;
@@ -154,17 +152,18 @@ af_err af_get_data_ptr(void *data, const af_array arr) {
     if (n == 0) return AF_SUCCESS;
     AFB_ARG(0, data != nullptr);
     check_same_device(*a);
-    cudaStream_t s = stream_of(a->device());
     const size_t bytes = (size_t)n * dtype_size(a->info.type);
     if (a->is_linear()) {
-        AFB_CUDA(cudaMemcpyAsync(data, a->data(), bytes, cudaMemcpyDeviceToHost, s));
-        AFB_CUDA(cudaStreamSynchronize(s));
+        download_sync(a->device(), data, a->data(), bytes);
     } else {
         Array *tmp = dense_copy(*a);
-        cudaError_t e = cudaMemcpyAsync(data, tmp->data(), bytes, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        try {
+            download_sync(a->device(), data, tmp->data(), bytes);
+        } catch (...) {
+            delete tmp;
+            throw;
+        }
         delete tmp;
-        AFB_CUDA(e);
     }
     AFB_API_END
 }

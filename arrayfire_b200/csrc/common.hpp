@@ -174,6 +174,9 @@ struct LaunchCtx {
     Scratch *scratch;
 };
 LaunchCtx ctx_for_active_device();
+// blocking copies on dedicated streams (runtime.cpp): overlap with compute and with the opposite direction
+void upload_sync(int device, void *dst, const void *src, size_t bytes);
+void download_sync(int device, void *dst, const void *src, size_t bytes);
 
 // A scalar coming back from a kernel WITHOUT cudaMemcpyAsync + cudaStreamSynchronize: the kernel's last thread writes the
 // payload (<= 40 bytes) into a pinned, device-mapped wire record as five 16-byte lines {data, seq, data, seq} -- flag in

@@ -77,6 +77,11 @@ struct Pool {
 struct Device {
     int id = -1;
     cudaStream_t stream = nullptr;
+    // dedicated copy streams: an upload / a download blocks its caller but not the other direction nor the compute stream
+    // (two host threads can keep both PCIe directions busy); ordered against the compute stream by events
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t up_ev = nullptr, down_ev = nullptr;
+    std::mutex up_mu, down_mu;
     int sms = 0;
     Scratch scratch;
     Pool pool;
@@ -120,6 +125,10 @@ Device &dev(int d) {
         AFB_CUDA(cudaSetDevice(d));
         D.id = d;
         AFB_CUDA(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+        AFB_CUDA(cudaStreamCreateWithFlags(&D.up_stream, cudaStreamNonBlocking));
+        AFB_CUDA(cudaStreamCreateWithFlags(&D.down_stream, cudaStreamNonBlocking));
+        AFB_CUDA(cudaEventCreateWithFlags(&D.up_ev, cudaEventDisableTiming));
+        AFB_CUDA(cudaEventCreateWithFlags(&D.down_ev, cudaEventDisableTiming));
         AFB_CUDA(cudaDeviceGetAttribute(&D.sms, cudaDevAttrMultiProcessorCount, d));
         D.scratch.device = d;
         cudaSetDevice(prev);
@@ -158,6 +167,27 @@ void set_active_device(int d) {
 }
 
 cudaStream_t stream_of(int device) { return dev(device).stream; }
+
+// host -> device, synchronous for the caller (the host buffer may be reused on return).  The copy runs on the upload stream
+// after everything already enqueued on the compute stream (the destination may be a pool buffer an earlier kernel still
+// reads); kernels enqueued after the return see the data because the host has waited for the copy.
+void upload_sync(int device, void *dst, const void *src, size_t bytes) {
+    Device &D = dev(device);
+    std::lock_guard<std::mutex> lk(D.up_mu);
+    AFB_CUDA(cudaEventRecord(D.up_ev, D.stream));
+    AFB_CUDA(cudaStreamWaitEvent(D.up_stream, D.up_ev, 0));
+    AFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, D.up_stream));
+    AFB_CUDA(cudaStreamSynchronize(D.up_stream));
+}
+// device -> host, synchronous for the caller: waits (on the download stream) for the compute work enqueued so far
+void download_sync(int device, void *dst, const void *src, size_t bytes) {
+    Device &D = dev(device);
+    std::lock_guard<std::mutex> lk(D.down_mu);
+    AFB_CUDA(cudaEventRecord(D.down_ev, D.stream));
+    AFB_CUDA(cudaStreamWaitEvent(D.down_stream, D.down_ev, 0));
+    AFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, D.down_stream));
+    AFB_CUDA(cudaStreamSynchronize(D.down_stream));
+}
 int sm_count(int device) { return dev(device).sms; }
 Scratch &scratch_of(int device) { return dev(device).scratch; }
 std::mutex &op_mutex(int device) { return dev(device).op_mu; }

@@ -83,3 +83,21 @@ def test_pending_lifecycle(af):
         h, w.handle = w.handle, None
         af._check(af.lib.afx_pending_scalar(h, ctypes.byref(re), ctypes.byref(im), ctypes.byref(idx)))
     assert af.sum_all(x) == float(np.arange(1 << 16, dtype=np.float64).sum())
+
+
+def test_uploads_and_downloads_from_two_threads(af):
+    """af_create_array / af_get_data_ptr run on dedicated copy streams: a reader thread downloads results while the main
+    thread uploads the next inputs (what bench.py's end-to-end arm does); every byte must still be right"""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(5)
+    n = 1 << 22
+    inputs = [rng.integers(-100, 100, n).astype(np.int32) for _ in range(6)]
+    with ThreadPoolExecutor(max_workers=1) as reader:
+        futs = []
+        for x in inputs * 3:
+            g = af.Array.from_numpy(x)                       # upload (blocking for this thread only)
+            s = af.accum(g, 0)                               # kernel on the compute stream
+            futs.append((x, reader.submit(s.to_numpy)))      # download on the reader thread
+            del g, s                                         # buffers go back to the pool while copies are in flight
+        for x, f in futs:
+            assert np.array_equal(f.result().reshape(-1), np.cumsum(x, dtype=np.int64).astype(np.int32))
