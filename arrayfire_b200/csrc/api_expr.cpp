@@ -94,15 +94,38 @@ int flatten(const ExprNode &n, ExprProg &p, int &nleaf, int &ncst, bool &dbl) {
         p.arg[p.n++] = (unsigned char)idx;
         return 0;
     }
-    int depth = flatten(*n.kid[0], p, nleaf, ncst, dbl);
-    if (n.op < EX_FIRST_UNARY) {
-        const int right = flatten(*n.kid[1], p, nleaf, ncst, dbl) + 1;   // the left value waits in shared memory meanwhile
-        if (right > depth) depth = right;
+    auto const_index = [&](const ExprNode &c) {
+        int idx = -1;
+        for (int i = 0; i < ncst; i++)
+            if (p.cst[i] == c.cst) idx = i;
+        if (idx < 0) {
+            if (ncst >= kExprMaxConsts) fail(AF_ERR_INTERNAL, "expression has too many constants");
+            idx = ncst++;
+            p.cst[idx] = c.cst;
+        }
+        if (c.type == f64) dbl = true;
+        return idx;
+    };
+    int depth, flags = 0, arg = 0;
+    if (n.op < EX_FIRST_UNARY && n.kid[1]->op == EX_CONST && n.kid[0]->op != EX_CONST) {
+        depth = flatten(*n.kid[0], p, nleaf, ncst, dbl);      // x op c: the scalar rides in the instruction
+        flags = EX_RCONST;
+        arg = const_index(*n.kid[1]);
+    } else if (n.op < EX_FIRST_UNARY && n.kid[0]->op == EX_CONST && n.kid[1]->op != EX_CONST) {
+        depth = flatten(*n.kid[1], p, nleaf, ncst, dbl);      // c op x
+        flags = EX_LCONST;
+        arg = const_index(*n.kid[0]);
+    } else {
+        depth = flatten(*n.kid[0], p, nleaf, ncst, dbl);
+        if (n.op < EX_FIRST_UNARY) {
+            const int right = flatten(*n.kid[1], p, nleaf, ncst, dbl) + 1;   // the left value waits in shared memory meanwhile
+            if (right > depth) depth = right;
+        }
     }
     if (n.type == f64) dbl = true;
     if (p.n >= kExprMaxOps) fail(AF_ERR_INTERNAL, "expression program too long");
-    p.op[p.n] = (unsigned char)n.op;
-    p.arg[p.n++] = 0;
+    p.op[p.n] = (unsigned char)(n.op | flags);
+    p.arg[p.n++] = (unsigned char)arg;
     return depth;
 }
 
@@ -113,6 +136,7 @@ ExprProg program_of(const ExprNode &root, bool *dbl) {
     int nleaf = 0, ncst = 0;
     *dbl = false;
     const int depth = flatten(root, p, nleaf, ncst, *dbl);
+    p.nleaf = nleaf;
     if (depth > 8) fail(AF_ERR_INTERNAL, "expression nests too deeply");   // builders evaluate sub-trees before this happens
     return p;
 }
@@ -176,11 +200,19 @@ af_err binary(af_array *out, const af_array lhs_h, const af_array rhs_h, int op,
     }
     Holder kl, kr;
     auto n = std::make_shared<ExprNode>();
-    n->op = op;
     n->type = to;
     n->kid[0] = bounded(node_of(*l, kl), *l);
-    n->kid[1] = bounded(node_of(*r, kr), *r);
-    n->nops = n->kid[0]->nops + n->kid[1]->nops + 1;
+    // x * x of the SAME operand (same handle, or the same buffer region): one load and a square
+    const bool same = (l == r) || (l->expr && l->expr == r->expr) ||
+                      (!l->expr && !r->expr && l->buf == r->buf && l->info.offset == r->info.offset && l->is_linear() && r->is_linear());
+    if (op == EX_MUL && same && l->info.type == r->info.type) {
+        n->op = EX_SQR;
+        n->nops = n->kid[0]->nops + 1;
+    } else {
+        n->op = op;
+        n->kid[1] = bounded(node_of(*r, kr), *r);
+        n->nops = n->kid[0]->nops + n->kid[1]->nops + 1;
+    }
     *out = lazy_array(*l, to, n);
     AFB_API_END
 }

@@ -261,13 +261,16 @@ bool launch_gather(const LaunchCtx &c, af_dtype t, const void *in, const unsigne
 enum ExprOp {
     EX_LEAF = 0, EX_CONST = 1,
     EX_ADD, EX_SUB, EX_MUL, EX_DIV, EX_LT, EX_GT, EX_LE, EX_GE, EX_EQ, EX_NEQ, EX_AND, EX_OR, EX_MIN, EX_MAX, EX_POW,
-    EX_SQRT, EX_ABS, EX_NEG, EX_NOT,
-    EX_FIRST_UNARY = EX_SQRT
+    EX_SQRT, EX_ABS, EX_NEG, EX_NOT, EX_SQR,
+    EX_FIRST_UNARY = EX_SQRT,
+    // flags on a binary op: one operand is the constant cst[arg] instead of a stack entry (no push / pop for scalars)
+    EX_RCONST = 0x40, EX_LCONST = 0x80, EX_OPMASK = 0x3f
 };
 enum ExprReduce { EXR_SUM = 0, EXR_COUNT = 1, EXR_MIN = 2, EXR_MAX = 3, EXR_ANY = 4, EXR_ALL = 5 };
 constexpr int kExprMaxOps = 48, kExprMaxLeaves = 8, kExprMaxConsts = 8;
 struct ExprProg {                 // a postfix program over dense, equally shaped operands
     int n;                        // instructions
+    int nleaf;                    // distinct operands
     unsigned char op[kExprMaxOps], arg[kExprMaxOps];
     const void *leaf[kExprMaxLeaves];
     int leaf_type[kExprMaxLeaves];   // 0 f32, 1 f64, 2 b8

@@ -4,17 +4,19 @@
 //     sum<float>( sqrt(x*x + y*y) < 1 )
 // Here the expression is a short postfix program (api_expr.cpp flattens the tree) that the reduction kernel INTERPRETS in
 // its load path: no run-time compiler, no temporaries -- x and y are streamed once and only the count leaves the chip.
-// Every thread evaluates the program on W consecutive elements at a time: the top of the value stack lives in registers,
+// Every thread evaluates the program on W = 8 (f32) / 4 (f64) consecutive elements at a time, one decode per W elements: the top of the value stack lives in registers,
 // the rest in shared memory ([depth][w][thread]: conflict-free), so one decoded instruction is amortised over W elements.
 // The same interpreter materialises an expression into an array when a non-fused consumer needs it.
+// (Measured and rejected: prefetching the next iteration's operands into registers -- 116 registers, 1.11 -> 1.67 ms on the
+// pi expression over 2 x 2^28 f32: the interpreter is bound by instruction issue, not by load latency.)
 #include "device_ops.cuh"
 
 namespace afb {
 
-constexpr int kExprThreads = 256;
+constexpr int kExprThreads = 128;
 constexpr int kExprDepth = 8;       // value-stack depth (entries below the register-resident top)
 
-template<typename Tc> struct ExprW { static constexpr int value = 16 / (int)sizeof(Tc); };   // 4 floats / 2 doubles
+template<typename Tc> struct ExprW { static constexpr int value = 32 / (int)sizeof(Tc); };   // 8 floats / 4 doubles per decode
 
 template<typename Tc> AFB_DI void expr_load(const ExprProg &p, int leaf, dim_t i, dim_t n, Tc (&v)[ExprW<Tc>::value]) {
     constexpr int W = ExprW<Tc>::value;
@@ -22,10 +24,12 @@ template<typename Tc> AFB_DI void expr_load(const ExprProg &p, int leaf, dim_t i
     const int t = p.leaf_type[leaf];
     if (t == 0) {
         const float *f = (const float *)base;
-        if (W == 4 && p.aligned && i + W <= n) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(f + i));
-            v[0] = (Tc)q.x; v[1] = (Tc)q.y;
-            if (W > 2) { v[2 % W] = (Tc)q.z; v[3 % W] = (Tc)q.w; }
+        if (p.aligned && i + W <= n) {
+#pragma unroll
+            for (int q = 0; q < W / 4; q++) {
+                const float4 v4 = __ldg(reinterpret_cast<const float4 *>(f + i) + q);
+                v[4 * q] = (Tc)v4.x; v[4 * q + 1] = (Tc)v4.y; v[4 * q + 2] = (Tc)v4.z; v[4 * q + 3] = (Tc)v4.w;
+            }
         } else {
 #pragma unroll
             for (int w = 0; w < W; w++) v[w] = i + w < n ? (Tc)__ldg(f + i + w) : (Tc)0;
@@ -49,7 +53,8 @@ AFB_DI void expr_eval(const ExprProg &p, dim_t i, dim_t n, Tc (&top)[ExprW<Tc>::
     int sp = 0;          // entries in shared memory
 #pragma unroll 1
     for (int pc = 0; pc < p.n; pc++) {
-        const int op = p.op[pc], arg = p.arg[pc];
+        const int opf = p.op[pc], arg = p.arg[pc];
+        const int op = opf & EX_OPMASK;
         if (op == EX_LEAF || op == EX_CONST) {
             if (pc > 0) {      // spill the current top
 #pragma unroll
@@ -63,45 +68,63 @@ AFB_DI void expr_eval(const ExprProg &p, dim_t i, dim_t n, Tc (&top)[ExprW<Tc>::
             }
             continue;
         }
+        // the switch sits OUTSIDE the W loops: one decode per W elements
+#define EX_UN(expr)                              \
+    _Pragma("unroll") for (int w = 0; w < W; w++) { \
+        const Tc a = top[w];                     \
+        top[w] = (expr);                         \
+    }                                            \
+    break;
         if (op >= EX_FIRST_UNARY) {
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-                const Tc a = top[w];
-                Tc r;
-                switch (op) {
-                    case EX_SQRT: r = sqrt(a); break;
-                    case EX_ABS: r = a < (Tc)0 ? -a : a; break;
-                    case EX_NEG: r = -a; break;
-                    default: r = (a == (Tc)0) ? (Tc)1 : (Tc)0; break;   // EX_NOT
-                }
-                top[w] = r;
+            switch (op) {
+                case EX_SQRT: EX_UN(sqrt(a))
+                case EX_ABS: EX_UN(a < (Tc)0 ? -a : a)
+                case EX_NEG: EX_UN(-a)
+                case EX_SQR: EX_UN(a * a)
+                default: EX_UN((a == (Tc)0) ? (Tc)1 : (Tc)0)   // EX_NOT
             }
             continue;
         }
-        sp--;               // binary: left operand from shared memory, right operand = top
+#undef EX_UN
+        // binary: left operand from shared memory, right operand = top -- unless one side is a scalar constant
+        Tc l[W], r[W];
+        if (opf & EX_RCONST) {
+            const Tc cv = (Tc)p.cst[arg];
 #pragma unroll
-        for (int w = 0; w < W; w++) {
-            const Tc a = stk[(sp * W + w) * kExprThreads + tid], b = top[w];
-            Tc r;
-            switch (op) {
-                case EX_ADD: r = a + b; break;
-                case EX_SUB: r = a - b; break;
-                case EX_MUL: r = a * b; break;
-                case EX_DIV: r = a / b; break;
-                case EX_LT: r = a < b ? (Tc)1 : (Tc)0; break;
-                case EX_GT: r = a > b ? (Tc)1 : (Tc)0; break;
-                case EX_LE: r = a <= b ? (Tc)1 : (Tc)0; break;
-                case EX_GE: r = a >= b ? (Tc)1 : (Tc)0; break;
-                case EX_EQ: r = a == b ? (Tc)1 : (Tc)0; break;
-                case EX_NEQ: r = a != b ? (Tc)1 : (Tc)0; break;
-                case EX_AND: r = (a != (Tc)0 && b != (Tc)0) ? (Tc)1 : (Tc)0; break;
-                case EX_OR: r = (a != (Tc)0 || b != (Tc)0) ? (Tc)1 : (Tc)0; break;
-                case EX_MIN: r = (b < a) ? b : a; break;
-                case EX_MAX: r = (a < b) ? b : a; break;
-                default: r = pow(a, b); break;                          // EX_POW
-            }
-            top[w] = r;
+            for (int w = 0; w < W; w++) { l[w] = top[w]; r[w] = cv; }
+        } else if (opf & EX_LCONST) {
+            const Tc cv = (Tc)p.cst[arg];
+#pragma unroll
+            for (int w = 0; w < W; w++) { l[w] = cv; r[w] = top[w]; }
+        } else {
+            sp--;
+#pragma unroll
+            for (int w = 0; w < W; w++) { l[w] = stk[(sp * W + w) * kExprThreads + tid]; r[w] = top[w]; }
         }
+#define EX_BIN(expr)                             \
+    _Pragma("unroll") for (int w = 0; w < W; w++) { \
+        const Tc a = l[w], b = r[w];             \
+        top[w] = (expr);                         \
+    }                                            \
+    break;
+        switch (op) {
+            case EX_ADD: EX_BIN(a + b)
+            case EX_SUB: EX_BIN(a - b)
+            case EX_MUL: EX_BIN(a * b)
+            case EX_DIV: EX_BIN(a / b)
+            case EX_LT: EX_BIN(a < b ? (Tc)1 : (Tc)0)
+            case EX_GT: EX_BIN(a > b ? (Tc)1 : (Tc)0)
+            case EX_LE: EX_BIN(a <= b ? (Tc)1 : (Tc)0)
+            case EX_GE: EX_BIN(a >= b ? (Tc)1 : (Tc)0)
+            case EX_EQ: EX_BIN(a == b ? (Tc)1 : (Tc)0)
+            case EX_NEQ: EX_BIN(a != b ? (Tc)1 : (Tc)0)
+            case EX_AND: EX_BIN((a != (Tc)0 && b != (Tc)0) ? (Tc)1 : (Tc)0)
+            case EX_OR: EX_BIN((a != (Tc)0 || b != (Tc)0) ? (Tc)1 : (Tc)0)
+            case EX_MIN: EX_BIN((b < a) ? b : a)
+            case EX_MAX: EX_BIN((a < b) ? b : a)
+            default: EX_BIN(pow(a, b))                          // EX_POW
+        }
+#undef EX_BIN
     }
 }
 
@@ -211,7 +234,7 @@ __global__ void __launch_bounds__(kExprThreads) expr_reduce_kernel(const ExprPro
 
 static unsigned expr_grid(const LaunchCtx &c, dim_t n, int w) {
     dim_t g = (n + (dim_t)kExprThreads * w - 1) / ((dim_t)kExprThreads * w);
-    const dim_t cap = (dim_t)c.sms * 4;
+    const dim_t cap = (dim_t)c.sms * 6;      // 32 KB of value stack per CTA of 128 threads: 6 CTAs per SM
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 

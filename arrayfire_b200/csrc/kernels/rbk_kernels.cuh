@@ -90,10 +90,29 @@ static __global__ void __launch_bounds__(kRbkThreads) rbk_count_kernel(const Rbk
     __syncthreads();
     if (!sm_last) return;
     __threadfence();
-    const dim_t per = (a.ntiles + kRbkThreads - 1) / kRbkThreads;
-    const dim_t lo = (dim_t)tid * per, hi = min(lo + per, a.ntiles);
+    // every thread owns a contiguous share, a multiple of 4 entries, read and rewritten as 16-byte vectors with 8 loads in
+    // flight (first cut: one dependent 4-byte L2 access per entry and thread -- the whole GPU idled ~150 us behind it)
+    dim_t per = (a.ntiles + kRbkThreads - 1) / kRbkThreads;
+    per = (per + 3) / 4 * 4;
+    const dim_t lo = min((dim_t)tid * per, a.ntiles), hi = min(lo + per, a.ntiles);
+    const dim_t nvec = (hi - lo) / 4;
+    const uint4 *vb = reinterpret_cast<const uint4 *>(a.tile_base + lo);   // lo is a multiple of 4, the array is 16-byte aligned
     uint sum = 0;
-    for (dim_t i = lo; i < hi; i++) sum += __ldcg(a.tile_base + i);
+    {
+        dim_t v = 0;
+        for (; v + 8 <= nvec; v += 8) {
+            uint4 q[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) q[u] = __ldcg(vb + v + u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum += q[u].x + q[u].y + q[u].z + q[u].w;
+        }
+        for (; v < nvec; v++) {
+            const uint4 q = __ldcg(vb + v);
+            sum += q.x + q.y + q.z + q.w;
+        }
+        for (dim_t i = lo + nvec * 4; i < hi; i++) sum += __ldcg(a.tile_base + i);
+    }
     uint inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -108,10 +127,37 @@ static __global__ void __launch_bounds__(kRbkThreads) rbk_count_kernel(const Rbk
     for (int w = 0; w < kRbkThreads / 32; w++)
         if (w < warp) before += sm[w];
     uint run = before;
-    for (dim_t i = lo; i < hi; i++) {
-        const uint c = __ldcg(a.tile_base + i);
-        a.tile_base[i] = run;
-        run += c;
+    {
+        uint4 *wb = reinterpret_cast<uint4 *>(a.tile_base + lo);
+        dim_t v = 0;
+        for (; v + 8 <= nvec; v += 8) {
+            uint4 q[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) q[u] = __ldcg(vb + v + u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                uint4 o;
+                o.x = run; run += q[u].x;
+                o.y = run; run += q[u].y;
+                o.z = run; run += q[u].z;
+                o.w = run; run += q[u].w;
+                wb[v + u] = o;
+            }
+        }
+        for (; v < nvec; v++) {
+            const uint4 q = __ldcg(vb + v);
+            uint4 o;
+            o.x = run; run += q.x;
+            o.y = run; run += q.y;
+            o.z = run; run += q.z;
+            o.w = run; run += q.w;
+            wb[v] = o;
+        }
+        for (dim_t i = lo + nvec * 4; i < hi; i++) {
+            const uint c = __ldcg(a.tile_base + i);
+            a.tile_base[i] = run;
+            run += c;
+        }
     }
     if (tid == kRbkThreads - 1) {
         a.tile_base[a.ntiles] = run;   // per >= 1 element for the low threads; the last thread's `run` is the total
