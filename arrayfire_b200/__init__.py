@@ -24,7 +24,7 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libafb200.so")
+LIB_PATH = os.environ.get("AFB200_LIB") or os.path.join(_HERE, "libafb200.so")   # AFB200_LIB: A-B runs of two builds (tools/)
 
 # af_dtype, include/af/defines.h:210-233
 f32, c32, f64, c64, b8, s32, u32, u8, s64, u64, s16, u16, f16, s8 = range(14)

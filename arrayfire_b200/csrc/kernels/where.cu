@@ -440,10 +440,15 @@ __global__ void __launch_bounds__(kChainThreads, 2) chain_where_kernel(const Cha
 // of tile i, so the walker's L2 round trip (2000-4000 cycles under load) is hidden -- compacts 512 bytes of input
 // at a time through a per-warp strip and flushes it with coalesced stores.  Tiles are large (128 KB of input)
 // because one walker step per tile must fit into the tile period even for a sparse mask.
-constexpr int kPW_Warps = 16;
+#ifndef AFB_PW_WARPS
+#define AFB_PW_WARPS 16
+#define AFB_PW_SUB 4
+#define AFB_PW_STAGES 4
+#endif
+constexpr int kPW_Warps = AFB_PW_WARPS;
 constexpr int kPW_U = 4;        // 512-byte slots per warp per sub-tile
-constexpr int kPW_Sub = 4;      // sub-tiles (bulk copies) per tile
-constexpr int kPW_Stages = 4;
+constexpr int kPW_Sub = AFB_PW_SUB;      // sub-tiles (bulk copies) per tile
+constexpr int kPW_Stages = AFB_PW_STAGES;
 constexpr int kPW_Ring = 4;     // per-tile barrier / scratch ring
 constexpr int kPW_Threads = 32 * (kPW_Warps + 3);
 
@@ -468,8 +473,8 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     constexpr int E = Lay::E;
     constexpr int TILE = Lay::TILE, SUBTILE = Lay::SUBTILE;
     constexpr int U = kPW_U, NW = kPW_Warps, ST = kPW_Stages, SUB = kPW_Sub, RING = kPW_Ring;
-    constexpr int NE = SUB * NW;     // (sub-tile, warp) count entries per tile: 64 = two per lane
-    static_assert(NE == 64, "publisher / walker handle two entries per lane");
+    constexpr int NE = 64;           // (sub-tile, warp) count entries per tile, two per publisher / walker lane; unused ones stay 0
+    static_assert(SUB * NW <= NE, "publisher / walker handle two entries per lane");
 
     extern __shared__ __align__(128) unsigned char pipe_smem[];   // see pipe_scan_kernel: keeps the accesses LDS/STS
     unsigned char *stage_base = pipe_smem;
@@ -486,6 +491,8 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
     __shared__ uint sm_wp[RING][NE];            // absolute output offsets
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (SUB * NW < NE)
+        for (int e = tid; e < RING * NE; e += kPW_Threads) (&sm_wtot[0][0])[e] = 0u;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < ST; s++) {
@@ -661,38 +668,54 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
             cw[2] += clock64() - k1;
             k1 = clock64();
             const unsigned short *mkp = masks + (size_t)((i - 1) & 1) * (SUB * Lay::NVEC);
-            // flush `total` indices from the warp's strip (filled from index `shift` = gpos & 3 on, so that its 16-byte
-            // quads line up with `out`): whole quads with 16-byte stores, the ragged ends element by element
-            auto flush = [&](uint gpos, uint shift, uint total) {
+            // flush `total` entries of the warp's strip (filled from index `shift` = gpos & 3 on, so that its 16-byte quads
+            // line up with `out`); the strip holds offsets relative to `add`.  Whole quads: one predicate, one 16-byte
+            // shared-memory load and one 16-byte store each, addressed by immediates off two per-lane bases; the ragged head
+            // (shift != 0) and tail (lim & 3) element-wise outside the unrolled loop.  (r02a tested every quad against both
+            // ends inside the loop: ~75 instructions per flush of 256 indices, as many as the expansion itself.)
+            // REL: strip entries are offsets relative to `add` (E < 16: saves the per-element add of the expansion; with the 16
+            // elements per vector of 1-byte types the registers that takes cost more than the adds -- measured)
+            constexpr bool REL = E < 16;
+            auto flush = [&](uint gpos, uint shift, uint total, uint add) {
+                if (!REL) add = 0u;
                 if (total <= 32u) {                  // one coalesced scalar store
-                    if (lane < total) a.out[gpos + lane] = strip[shift + lane];
+                    if (lane < total) a.out[gpos + lane] = strip[shift + lane] + add;
                     return;
                 }
                 uint *out_al = a.out + (gpos - shift);
                 const uint lim = shift + total;
-                // a strip holds at most 32 * E + 4 indices = kQ quads per lane: all shared-memory loads are issued before
-                // the first store, so their latencies overlap (r01: a load -> store chain per iteration)
                 constexpr int kQ = (32 * E + 4 + 127) / 128;
+                const uint4 *sq = reinterpret_cast<const uint4 *>(strip) + lane;
+                uint4 *oq = reinterpret_cast<uint4 *>(out_al) + lane;
+                const int lim_l = (int)lim - 4 * lane;       // quad lane + 32 j is whole iff 128 j + 4 <= lim_l
                 uint4 v[kQ];
+                bool whole[kQ];
 #pragma unroll
                 for (int j = 0; j < kQ; j++) {
-                    const uint qd = lane + 32u * j;
-                    if (4u * qd < lim) v[j] = *reinterpret_cast<const uint4 *>(strip + 4u * qd);
+                    whole[j] = 128 * j + 4 <= lim_l;
+                    if (j == 0) whole[j] = whole[j] && (lane > 0 || shift == 0u);
+                    if (whole[j]) v[j] = sq[32 * j];
                 }
+                asm volatile("" ::: "memory");       // every shared-memory load is issued before the first store
 #pragma unroll
                 for (int j = 0; j < kQ; j++) {
-                    const uint qd = lane + 32u * j;
-                    if (4u * qd >= lim) continue;
-                    if (4u * qd >= shift && 4u * qd + 4u <= lim) {
-                        *reinterpret_cast<uint4 *>(out_al + 4u * qd) = v[j];
-                    } else {
-                        if (4u * qd + 0u >= shift && 4u * qd + 0u < lim) out_al[4u * qd + 0u] = v[j].x;
-                        if (4u * qd + 1u >= shift && 4u * qd + 1u < lim) out_al[4u * qd + 1u] = v[j].y;
-                        if (4u * qd + 2u >= shift && 4u * qd + 2u < lim) out_al[4u * qd + 2u] = v[j].z;
-                        if (4u * qd + 3u >= shift && 4u * qd + 3u < lim) out_al[4u * qd + 3u] = v[j].w;
+                    if (whole[j]) {
+                        if (REL) v[j].x += add, v[j].y += add, v[j].z += add, v[j].w += add;
+                        oq[32 * j] = v[j];
                     }
                 }
+                if (shift != 0u && lane >= shift && lane < 4u) out_al[lane] = strip[lane] + add;     // total > 32: lim > 4
+                const uint tail = lim & ~3u;
+                if (tail + lane < lim) out_al[tail + lane] = strip[tail + lane] + add;
             };
+            // strip entries are offsets inside the warp's slot / group: lane * E + k sits in registers for the whole
+            // kernel (opaque to the compiler, so that it keeps them instead of re-deriving one per element)
+            uint rk[E];
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                rk[k] = (uint)(lane * E + k);
+                if (REL) asm volatile("" : "+r"(rk[k]));
+            }
 #pragma unroll 1
             for (int sub = 0; sub < SUB; sub++) {
                 uint gpos = sm_wp[bp][sub * NW + warp];
@@ -716,7 +739,8 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
                     }
                     const uint shift = gpos & 3u;
                     uint *p = strip + (shift + inc - c);
-                    const uint first = a.base + (uint)(sub_lo + (dim_t)q0 * E);
+                    const uint gfirst = a.base + (uint)(sub_lo + (dim_t)(warp * U * 32) * E);
+                    const uint first = (uint)(lane * U * E) + (REL ? 0u : gfirst);   // REL: relative to the group's first element
                     uint m = mw.x;
                     while (m) {                      // vectors 0 (bits 0..15) and 1 (bits 16..31)
                         const int b = __ffs(m) - 1;
@@ -730,7 +754,7 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
                         *p++ = first + (uint)(2 * E + (b >> 4) * E + (b & 15));
                     }
                     __syncwarp();
-                    flush(gpos, shift, gtotal);
+                    flush(gpos, shift, gtotal, gfirst);
                     __syncwarp();
                     continue;
                 }
@@ -755,30 +779,30 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
                 for (int u = 0; u < U; u++) {
                     const uint total = __shfl_sync(0xffffffffu, inc[u], 31);
                     if (total == 0u) continue;        // warp-uniform
-                    const int q = (warp * U + u) * 32 + lane;
                     const uint shift = gpos & 3u;
-                    const uint first = a.base + (uint)(sub_lo + (dim_t)q * E);
                     // branch-free expansion through running pointers (one per half vector: two short dependency chains):
                     // per element one predicated store and one predicated pointer bump (r01 recomputed the strip address
                     // from the offset for every element)
                     const uint m = mm[u];
+                    const uint sfirst = a.base + (uint)(sub_lo + (dim_t)((warp * U + u) * 32) * E);
+                    const uint voff = REL ? 0u : sfirst;
                     uint *p0 = strip + (shift + inc[u] - cc[u]);
                     constexpr int H = E >= 2 ? E / 2 : 1;
                     uint *p1 = p0 + __popc(m & ((1u << H) - 1u));
 #pragma unroll
                     for (int k = 0; k < H; k++) {
                         const bool hit = (m >> k) & 1u;
-                        if (hit) *p0 = first + k;
+                        if (hit) *p0 = rk[k] + voff;
                         if (hit) p0++;
                     }
 #pragma unroll
                     for (int k = H; k < E; k++) {
                         const bool hit = (m >> k) & 1u;
-                        if (hit) *p1 = first + k;
+                        if (hit) *p1 = rk[k] + voff;
                         if (hit) p1++;
                     }
                     __syncwarp();
-                    flush(gpos, shift, total);
+                    flush(gpos, shift, total, sfirst);
                     __syncwarp();
                     gpos += total;
                 }
