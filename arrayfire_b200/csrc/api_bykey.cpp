@@ -77,7 +77,7 @@ af_err reduce_by_key(af_array *keys_out, af_array *vals_out, const af_array keys
     const dim_t tile = rbk_tile_elems();
     const dim_t ntiles = (n + tile - 1) / tile;
     Holder bases;
-    const dim_t bd[4] = {ntiles + 1, 1, 1, 1};
+    const dim_t bd[4] = {rbk_scratch_elems(ntiles), 1, 1, 1};
     bases.a = new_array(u32, bd);
     // ---- pass 1: number of runs (the host needs it to size the outputs)
     HostRet ret;

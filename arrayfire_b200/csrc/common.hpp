@@ -284,6 +284,7 @@ void launch_expr_reduce(const LaunchCtx &c, const ExprProg &p, bool dbl, int mod
 // ---- reductions by key (kernels/rbk_*.cu): keys = n dense 32-bit keys, runs of equal consecutive keys are segments
 // pass 1: number of runs -> published through `ret` (u64); tile_base[t] (device, ntiles + 1 words) = runs starting before tile t
 dim_t rbk_tile_elems();
+dim_t rbk_scratch_elems(dim_t ntiles);   // u32 words of the pass-1 scratch: tile bases + one run-head bit per key
 void launch_rbk_count(const LaunchCtx &c, const void *keys, dim_t n, unsigned *tile_base, const HostRet &ret);
 // pass 2: vals reduced per run along `dim` into vals_out (dense, dims[dim] = n_reduced); keys_out (may be null) gets one key per run
 bool launch_rbk_reduce(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const void *keys, dim_t n, const View &vals,

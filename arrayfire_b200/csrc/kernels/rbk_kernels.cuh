@@ -7,17 +7,21 @@
 // What it replaces: the reference CUDA backend loops on the HOST -- per round a block reduce, a cub::DeviceScan, a
 // compaction and a D2H read of a "needs another round" flag (src/backend/cuda/reduce_impl.hpp:88-180,
 // kernel/reduce_by_key.hpp:33-621).  Here:
-//   pass 1  rbk_count_kernel   one streaming pass over the KEYS: runs per 2048-key tile; the last CTA to arrive (ticket)
-//                              turns the counts into exclusive tile bases and publishes the total to a pinned host record
-//                              (the host needs it to size the outputs -- the one unavoidable host round trip).
-//   pass 2  rbk_tile_kernel    dim 0: one CTA per (tile, column): blocked loads, a segmented scan in registers / shuffles,
+//   pass 1  rbk_count_kernel   one streaming pass over the KEYS: runs per 2048-key tile AND the run-head bit of every key
+//                              (one bit per key, n / 8 bytes: pass 2 never reads the keys again); the last CTA to arrive
+//                              (ticket) turns the counts into exclusive tile bases and publishes the total to a pinned host
+//                              record (the host needs it to size the outputs -- the one unavoidable host round trip).
+//   pass 2  rbk_tile_kernel    dim 0: one CTA per (tile, column): head bits (1 byte per thread) + blocked value loads, a
+//                              segmented scan in registers / shuffles,
 //                              every run TAIL writes its reduction straight to out[tile_base + local run index]; heads
 //                              write keys_out.  Only the run that enters a tile from the left is incomplete: its partial is
 //                              written anyway and the tile's (value, has-head) aggregate goes to a side array ...
 //   pass 3  rbk_carry_*        ... which two small launches scan (segmented, one thread per tile) to add the carried-in
 //                              part to the first output of each tile.  Deterministic: no atomics on values, fixed order.
 //           rbk_dim_kernel     dim > 0: lanes along the contiguous dim 0, every thread walks its line serially.
-// Traffic (dim 0): keys twice + values once + outputs; the reference's loop re-reads keys and values every round.
+// Traffic (dim 0): keys once + values once + n / 4 bytes of head bits + outputs (r02a read the keys twice and compared
+// them again in pass 2: 74 instructions per element, 1.13 ms for 2^28 s32 keys + values); the reference's loop re-reads
+// keys and values every round.
 #pragma once
 
 #include "scan_kernels.cuh"
@@ -35,10 +39,15 @@ struct RbkCountArgs {
     const uint *keys;
     dim_t n, ntiles;
     uint *tile_base;                 // [ntiles + 1]
+    unsigned char *bits;             // [ntiles * kRbkTile / 8 + 1]: bit p = key p starts a run; bit n = end-of-line marker
     uint *ticket;                    // self-resetting arrival counter
     void *host_wire;                 // pinned wire record (common.hpp HostRet)
     uint host_seq;
 };
+
+// the head bits live behind the tile bases in the same allocation (16-byte aligned)
+__host__ __device__ inline size_t rbk_bits_word_offset(dim_t ntiles) { return ((size_t)ntiles + 1 + 3) & ~(size_t)3; }
+inline size_t rbk_scratch_words(dim_t ntiles) { return rbk_bits_word_offset(ntiles) + (size_t)ntiles * (kRbkTile / 32) + 4; }
 
 // heads among the EPT keys starting at p0 (bit k: key p0+k starts a run); keys past n never do
 AFB_DI uint rbk_heads(const uint *__restrict__ keys, dim_t n, dim_t p0, uint (&k)[kRbkEPT]) {
@@ -68,15 +77,41 @@ static __global__ void __launch_bounds__(kRbkThreads) rbk_count_kernel(const Rbk
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // a WARP owns a tile: its 8 sub-chunks of 256 keys are independent loads (16 x 16 bytes in flight per lane), one warp
     // reduction per tile, no CTA barrier in the streaming loop (first cut: a CTA per tile with two barriers and a serial
-    // sum by thread 0 per 8 KB -- 2.5 TB/s)
+    // sum by thread 0 per 8 KB -- 2.5 TB/s).  The key in front of a lane's chunk comes from the neighbouring lane by
+    // shuffle (r02a: one more dependent scalar load per chunk).
     const dim_t nwarps = (dim_t)gridDim.x * (kRbkThreads / 32);
+    const bool al = (reinterpret_cast<uintptr_t>(a.keys) & 15) == 0;
     for (dim_t t = (dim_t)blockIdx.x * (kRbkThreads / 32) + warp; t < a.ntiles; t += nwarps) {
         uint c = 0;
+        const dim_t base = t * kRbkTile;
+        unsigned char *bt = a.bits + t * (kRbkTile / 8);
+        if (al && base + kRbkTile <= a.n) {
+            uint last = t > 0 ? __ldg(a.keys + base - 1) : 0u;     // key in front of the sub-chunk's lane 0
 #pragma unroll
-        for (int sub = 0; sub < kRbkThreads / 32; sub++) {
-            uint k[kRbkEPT];
-            c += __popc(rbk_heads(a.keys, a.n, t * kRbkTile + (dim_t)(sub * 32 + lane) * kRbkEPT, k));
+            for (int sub = 0; sub < kRbkThreads / 32; sub++) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(a.keys + base + (dim_t)(sub * 32 + lane) * kRbkEPT);
+                const uint4 q0 = __ldg(p), q1 = __ldg(p + 1);
+                const uint up = __shfl_up_sync(0xffffffffu, q1.w, 1);
+                const uint prevk = lane ? up : last;
+                last = __shfl_sync(0xffffffffu, q1.w, 31);
+                uint hb = (q0.x != prevk ? 1u : 0u) | (q0.y != q0.x ? 2u : 0u) | (q0.z != q0.y ? 4u : 0u) | (q0.w != q0.z ? 8u : 0u) |
+                          (q1.x != q0.w ? 16u : 0u) | (q1.y != q1.x ? 32u : 0u) | (q1.z != q1.y ? 64u : 0u) | (q1.w != q1.z ? 128u : 0u);
+                if (t == 0 && sub == 0 && lane == 0) hb |= 1u;      // position 0 always starts a run
+                c += __popc(hb);
+                bt[sub * 32 + lane] = (unsigned char)hb;
+            }
+        } else {
+#pragma unroll 1
+            for (int sub = 0; sub < kRbkThreads / 32; sub++) {
+                uint k[kRbkEPT];
+                const dim_t p0 = base + (dim_t)(sub * 32 + lane) * kRbkEPT;
+                uint hb = rbk_heads(a.keys, a.n, p0, k);
+                c += __popc(hb);
+                if (p0 <= a.n && a.n < p0 + kRbkEPT) hb |= 1u << (int)(a.n - p0);   // end-of-line marker (not a run)
+                bt[sub * 32 + lane] = (unsigned char)hb;
+            }
         }
+        if (t == a.ntiles - 1 && lane == 0) a.bits[a.ntiles * (kRbkTile / 8)] = (a.n == a.ntiles * kRbkTile) ? 1 : 0;
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0) a.tile_base[t] = c;
     }
@@ -180,6 +215,7 @@ struct RbkArgs {
     const Ti *vals;
     ColGeom g;                      // columns of `vals` (g.len == n)
     const uint *tile_base;
+    const unsigned char *bits;      // run-head bits written by pass 1
     uint *keys_out;                 // may be null
     To *vals_out;                   // column c starts at c * n_reduced
     dim_t n_reduced;
@@ -201,30 +237,40 @@ __global__ void __launch_bounds__(kRbkThreads) rbk_tile_kernel(const RbkArgs<Ti,
     for (dim_t w = blockIdx.x; w < nwork; w += gridDim.x) {
         const dim_t t = w % a.ntiles, c = w / a.ntiles;
         const dim_t p0 = t * kRbkTile + (dim_t)tid * EPT;
-        uint k[EPT];
-        const uint hb = rbk_heads(a.keys, a.n, p0, k);
+        static_assert(EPT == 8, "one byte of head bits per thread");
+        const dim_t bi = t * (kRbkTile / 8) + tid;
+        const uint rawb = (uint)__ldg(a.bits + bi) | ((uint)__ldg(a.bits + bi + 1) << 8);
         const int nv = p0 >= a.n ? 0 : ((a.n - p0) >= EPT ? EPT : (int)(a.n - p0));
-        // is the element after this thread's last one a head (or the end of the line)?
-        bool next_head = true;
-        if (p0 + EPT < a.n) next_head = __ldg(a.keys + p0 + EPT) != k[EPT - 1];
+        const uint vmask = (1u << nv) - 1u;
+        const uint hb = rawb & vmask;            // element j starts a run
+        const uint tb = (rawb >> 1) & vmask;     // element j ends one: its successor starts a run, or the line ends
         const Ti *col = a.vals + col_offset(a.g, c);
-        Acc x[EPT];
-        Acc run = R::init();
-        Ti raw[EPT];
-        constexpr size_t kAlign = sizeof(Ti) * EPT >= 16 ? 16 : sizeof(Ti) * EPT;
-        const bool vec = nv == EPT && (reinterpret_cast<uintptr_t>(col + p0) % kAlign) == 0;
-        if (vec) load_elems<Ti, EPT>(col + p0, raw);
+        Acc v[EPT];
+        {
+            Ti raw[EPT];
+            constexpr size_t kAlign = sizeof(Ti) * EPT >= 16 ? 16 : sizeof(Ti) * EPT;
+            if (nv == EPT && (reinterpret_cast<uintptr_t>(col + p0) % kAlign) == 0) {
+                load_elems<Ti, EPT>(col + p0, raw);
 #pragma unroll
-        for (int j = 0; j < EPT; j++) {
-            Acc v = R::init();
-            if (j < nv) {
-                v = R::pre(vec ? raw[j] : ldg_stream<Ti>(col + p0 + j));
-                if (a.prm.change_nan) v = nan_swap<Acc>(v, a.prm.nanval);
-                // the first run of a line starts from init() (reduce.hpp:137,146-148: b8 min / max normalise through it)
-                if (p0 + j == 0) v = R::join(R::init(), v);
+                for (int j = 0; j < EPT; j++) v[j] = R::pre(raw[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < EPT; j++) v[j] = j < nv ? R::pre(ldg_stream<Ti>(col + p0 + j)) : R::init();
             }
-            // a later run's first element is taken as is (the reference seeds the accumulator with it, reduce.hpp:152-156)
-            run = (j == 0 || ((hb >> j) & 1u)) ? v : R::join(run, v);
+        }
+        if (a.prm.change_nan) {
+#pragma unroll
+            for (int j = 0; j < EPT; j++) v[j] = nan_swap<Acc>(v[j], a.prm.nanval);
+        }
+        // the first run of a line starts from init() (reduce.hpp:137,146-148: b8 min / max normalise through it); a later
+        // run's first element is taken as is (the reference seeds the accumulator with it, reduce.hpp:152-156)
+        if (p0 == 0 && nv > 0) v[0] = R::join(R::init(), v[0]);
+        Acc x[EPT];
+        Acc run = v[0];
+        x[0] = run;
+#pragma unroll
+        for (int j = 1; j < EPT; j++) {
+            run = ((hb >> j) & 1u) ? v[j] : R::join(run, v[j]);
             x[j] = run;
         }
         State inc = State{run, hb != 0u ? 1 : 0};
@@ -257,17 +303,17 @@ __global__ void __launch_bounds__(kRbkThreads) rbk_tile_kernel(const RbkArgs<Ti,
             }
         }
         const State prefix = S::join(before, exc);   // the tile's elements in front of this thread
-        const uint base = __ldg(a.tile_base + t);
-        To *out = a.vals_out + c * a.n_reduced;
+        if (hb | tb) {                               // most threads of long runs hold neither a head nor a tail
+            const uint base = __ldg(a.tile_base + t) + hbefore - 1u;   // (- 1: the run that entered the tile from the left)
+            To *out = a.vals_out + c * a.n_reduced;
 #pragma unroll
-        for (int j = 0; j < EPT; j++) {
-            if (j < nv) {
-                const uint upto = hb & ((2u << j) - 1u);              // heads among this thread's elements 0..j
-                const uint seg = base + hbefore + __popc(upto) - 1u;  // (base - 1: the run that entered the tile from the left)
-                const bool head = (hb >> j) & 1u;
-                const bool tail = (j + 1 < nv) ? ((hb >> (j + 1)) & 1u) : ((p0 + j + 1 >= a.n) || (j + 1 == EPT && next_head));
-                if (head && c == 0 && a.keys_out) a.keys_out[seg] = k[j];
-                if (tail) out[seg] = conv<To, Acc>(upto == 0u ? R::join(prefix.val, x[j]) : x[j]);
+            for (int j = 0; j < EPT; j++) {
+                if (((hb | tb) >> j) & 1u) {
+                    const uint upto = hb & ((2u << j) - 1u);           // heads among this thread's elements 0..j
+                    const uint seg = base + __popc(upto);
+                    if (((hb >> j) & 1u) && c == 0 && a.keys_out) a.keys_out[seg] = __ldg(a.keys + p0 + j);
+                    if ((tb >> j) & 1u) out[seg] = conv<To, Acc>(upto == 0u ? R::join(prefix.val, x[j]) : x[j]);
+                }
             }
         }
         if (tid == kRbkThreads - 1) a.tile_agg[c * a.ntiles + t].v = S::join(prefix, State{run, hb != 0u ? 1 : 0});
@@ -348,8 +394,7 @@ __global__ void __launch_bounds__(kRbkThreads) rbk_carry_apply_kernel(const uint
     __syncthreads();
     const dim_t t = (dim_t)blockIdx.x * kRbkThreads + tid;
     if (t == 0 || t >= ntiles) return;
-    const dim_t p = t * kRbkTile;
-    const bool starts_run = __ldg(keys + p) != __ldg(keys + p - 1);
+    const bool starts_run = (__ldg(reinterpret_cast<const unsigned char *>(tile_base + rbk_bits_word_offset(ntiles)) + t * (kRbkTile / 8)) & 1u) != 0u;
     const uint b = __ldg(tile_base + t), heads = __ldg(tile_base + t + 1) - b;
     // the run entering from the left ends in this tile iff the tile has a head or is the last one
     if (!starts_run && (heads > 0u || t == ntiles - 1)) {
@@ -451,6 +496,7 @@ void run_rbk(const LaunchCtx &c, const void *keys, dim_t n, const View &vals, in
         a.vals = (const Ti *)vals.ptr;
         a.g = col_geom(vals);
         a.tile_base = tile_base;
+        a.bits = reinterpret_cast<const unsigned char *>(tile_base + rbk_bits_word_offset(ntiles));
         a.keys_out = (uint *)keys_out;
         a.vals_out = (To *)vals_out;
         a.n_reduced = n_reduced;

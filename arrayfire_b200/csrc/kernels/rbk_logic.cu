@@ -29,6 +29,7 @@ bool rbk_family_logic(const LaunchCtx &c, Op op, af_dtype ti, af_dtype to, const
 }
 
 dim_t rbk_tile_elems() { return kRbkTile; }
+dim_t rbk_scratch_elems(dim_t ntiles) { return (dim_t)rbk_scratch_words(ntiles); }
 
 void launch_rbk_count(const LaunchCtx &c, const void *keys, dim_t n, unsigned *tile_base, const HostRet &ret) {
     RbkCountArgs a;
@@ -36,11 +37,12 @@ void launch_rbk_count(const LaunchCtx &c, const void *keys, dim_t n, unsigned *t
     a.n = n;
     a.ntiles = (n + kRbkTile - 1) / kRbkTile;
     a.tile_base = tile_base;
+    a.bits = reinterpret_cast<unsigned char *>(tile_base + rbk_bits_word_offset(a.ntiles));
     a.ticket = c.scratch->need_tickets(2) + 1;   // ticket 0 belongs to the whole-array reductions
     a.host_wire = ret.wire;
     a.host_seq = ret.seq;
     dim_t grid = a.ntiles;
-    const dim_t cap = (dim_t)c.sms * 8;
+    const dim_t cap = (dim_t)c.sms * 4;      // 58 registers: 4 resident CTAs per SM, one wave
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     rbk_count_kernel<<<(unsigned)grid, kRbkThreads, 0, c.stream>>>(a);

@@ -65,9 +65,14 @@ void run_scan(const LaunchCtx &c, const View &in, const View *key, int dim, bool
                 constexpr int ES = (int)sizeof(To);
                 constexpr bool NARROW = sizeof(Ti) < sizeof(To);   // promoting scans: smaller tiles, the input has its own ring
                 constexpr int EPT = NARROW ? 12 : (KEYED ? 12 : 20) * 4 / ES;
-                constexpr int NWP = KEYED ? ((sizeof(Tk) > sizeof(To)) ? 12 : 16) : 12;   // 8-byte keys of 4-byte values: smaller tiles
-                constexpr int ST = KEYED ? 6 : 7;
-                constexpr int DL = 3;   // measured: D = 2 (one more tile of prefetch instead) costs the plain scan 25 % (0.140 vs 0.110 ms)
+#ifndef AFB_SBK_NW
+#define AFB_SBK_NW 16
+#define AFB_SBK_ST 6
+#define AFB_SBK_DL 3
+#endif
+                constexpr int NWP = KEYED ? ((sizeof(Tk) > sizeof(To)) ? 12 : AFB_SBK_NW) : 12;   // 8-byte keys of 4-byte values: smaller tiles
+                constexpr int ST = KEYED ? ((sizeof(Tk) > sizeof(To)) ? 6 : AFB_SBK_ST) : 7;
+                constexpr int DL = (KEYED && sizeof(Tk) <= sizeof(To)) ? AFB_SBK_DL : 3;   // measured: D = 2 (one more tile of prefetch instead) costs the plain scan 25 % (0.140 vs 0.110 ms)
                 typedef PipeLayout<KEYED || NARROW, EPT, ST, NWP, DL, (int)sizeof(To), NARROW ? (int)sizeof(Ti) : (int)sizeof(Tk)> PL;
                 static_assert(PL::total <= 225 * 1024, "pipe scan: the stage rings must fit one SM");
                 if (ok && g.len >= 4 * (dim_t)PL::TILE && !env_int("AFB200_NO_PIPE", 0)) {
