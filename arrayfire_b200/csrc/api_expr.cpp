@@ -73,7 +73,7 @@ int flatten(const ExprNode &n, ExprProg &p, int &nleaf, int &ncst, bool &dbl) {
             idx = nleaf++;
             p.leaf[idx] = ptr;
             p.leaf_type[idx] = n.type == f32 ? 0 : (n.type == f64 ? 1 : 2);
-            if (n.type == f32 && (reinterpret_cast<uintptr_t>(ptr) & 15)) p.aligned = 0;
+            if (reinterpret_cast<uintptr_t>(ptr) & 15) p.aligned = 0;
         }
         if (n.type == f64) dbl = true;
         p.op[p.n] = EX_LEAF;
@@ -137,6 +137,7 @@ ExprProg program_of(const ExprNode &root, bool *dbl) {
     *dbl = false;
     const int depth = flatten(root, p, nleaf, ncst, *dbl);
     p.nleaf = nleaf;
+    p.depth = depth;
     if (depth > 8) fail(AF_ERR_INTERNAL, "expression nests too deeply");   // builders evaluate sub-trees before this happens
     return p;
 }

@@ -271,11 +271,12 @@ constexpr int kExprMaxOps = 48, kExprMaxLeaves = 8, kExprMaxConsts = 8;
 struct ExprProg {                 // a postfix program over dense, equally shaped operands
     int n;                        // instructions
     int nleaf;                    // distinct operands
+    int depth;                    // value-stack entries needed besides the register-resident top
     unsigned char op[kExprMaxOps], arg[kExprMaxOps];
     const void *leaf[kExprMaxLeaves];
     int leaf_type[kExprMaxLeaves];   // 0 f32, 1 f64, 2 b8
     double cst[kExprMaxConsts];
-    int aligned;                  // every f32 leaf is 16-byte aligned
+    int aligned;                  // every operand is 16-byte aligned
 };
 // out_type: 0 f32, 1 f64, 2 b8; dbl: interpret in double (any f64 operand) instead of float
 void launch_expr_eval(const LaunchCtx &c, const ExprProg &p, bool dbl, void *out, int out_type, dim_t n);
