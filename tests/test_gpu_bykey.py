@@ -100,6 +100,23 @@ def test_reduce_by_key_large_and_views(af, port_oracle):
     np.testing.assert_allclose(vo.to_numpy().reshape(-1).astype(np.float64), truth, rtol=1e-5)
 
 
+def test_reduce_by_key_tile_multiples(af, port_oracle):
+    """key counts that are exact multiples of the 2048-key tile (the end-of-line marker of the run-head bits then sits in
+    the extra byte behind the last tile), runs ending exactly on tile boundaries, several value columns"""
+    orc = port_oracle
+    rng = np.random.default_rng(11700)
+    for n in (2048, 4096, 6144, 16384):
+        for kind in ("short", "same", "distinct", "tile"):
+            keys = make_keys(rng, n, kind, np.int32) if kind != "tile" else (np.arange(n) // 2048).astype(np.int32)
+            x = np.asfortranarray(rng.integers(-9, 10, (n, 3)).astype(np.int32))
+            gk, gx = af.Array.from_numpy(keys), af.Array.from_numpy(x)
+            for name in ("sum_by_key", "min_by_key", "count_by_key"):
+                tk, wk, tv, wv = getattr(orc, name)(keys, x, 0)
+                ko, vo = getattr(af, name)(gk, gx, 0)
+                same_bits(ko.to_numpy().reshape(-1), wk, "%s keys n=%d %s" % (name, n, kind))
+                same_bits(vo.to_numpy(), d4(wv), "%s vals n=%d %s" % (name, n, kind))
+
+
 def test_by_key_argument_errors(af):
     x = af.Array.from_numpy(np.ones((8, 3), np.float32, order="F"))
     k = af.Array.from_numpy(np.zeros(8, np.int32))

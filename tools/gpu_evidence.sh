@@ -11,7 +11,7 @@ print(d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], "sync", d["sync_ap
 for k,v in d["ops"].items(): print("   %-20s %8.4f ms %8.1f GB/s %.3f" % (k, v["ms"], v["GBps"], v["frac_of_peak_per_gpu"]))
 for k,v in (d.get("extras") or {}).items(): print("   %-50s %s" % (k, v))
 PY
-K='regex:span_kernel|dim_kernel|warp_cols_kernel|lookback_kernel|chain_scan_kernel|chain_where_kernel|pipe_scan_kernel|pipe_where_kernel|warp_scan_cols_kernel|strip_scan_kernel|dim_scan_kernel|where_kernel|fixup_kernel|copy_strided_kernel|fill_kernel|cast_kernel|rbk_|pair_kernel|diff_kernel'
+K='regex:span_kernel|dim_kernel|warp_cols_kernel|lookback_kernel|chain_scan_kernel|chain_where_kernel|pipe_scan_kernel|pipe_where_kernel|warp_scan_cols_kernel|strip_scan_kernel|dim_scan_kernel|where_kernel|fixup_kernel|copy_strided_kernel|fill_kernel|cast_kernel|rbk_|pair_kernel|diff_kernel|expr_'
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-sync-compare --no-check > gpurun_out/b_ncu_$TAG.log 2>&1
 echo "launch list rows: $(wc -l < gpurun_out/launches_$TAG.csv)"

@@ -66,9 +66,17 @@ def main():
             del m, am
     if "sbk" in which or "scan" in which or "rbk" in which:
         n = 1 << 28
+        gap = int(os.environ.get("HOT_GAP", "0"))          # bytes between the big inputs: do 2^30-aligned arrays alias in DRAM?
         v = torch.randint(-15, 15, (n,), generator=g, device=dev, dtype=torch.int32)
+        if gap:
+            pad1 = torch.empty(gap, device=dev, dtype=torch.uint8)
         lens = torch.randint(1, 1025, ((1 << 20) + 2,), generator=g, device=dev)
         k = torch.repeat_interleave(torch.arange((1 << 20) + 2, device=dev, dtype=torch.int32), lens)[:n].contiguous()
+        if gap:
+            kk = torch.empty(n + gap // 4, device=dev, dtype=torch.int32)
+            kk[gap // 4:] = k
+            k = kk[gap // 4:]
+            print("ptrs v %x k %x" % (v.data_ptr(), k.data_ptr()))
         av, ak = af.Array.from_torch(v), af.Array.from_torch(k)
         torch.cuda.synchronize()
         if "sbk" in which:
