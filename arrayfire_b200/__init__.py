@@ -188,6 +188,12 @@ class Array:
         return n.value
 
     @property
+    def device(self):
+        d = ctypes.c_int(0)
+        _check(lib.af_get_device_id(ctypes.byref(d), self.handle))
+        return d.value
+
+    @property
     def numdims(self):
         n = ctypes.c_uint()
         _check(lib.af_get_numdims(ctypes.byref(n), self.handle))

@@ -152,7 +152,7 @@ Array *new_array(af_dtype t, const dim_t dims[4]);  // dense, freshly allocated 
 Array *new_view(const Array &parent, const dim_t dims[4], dim_t offset, const dim_t strides[4]);
 Array *retain(const Array &a);
 void dense_strides(const dim_t dims[4], dim_t strides[4]);
-void check_same_device(const Array &a);      // AF_ERR_DEVICE when the array is not on the active device
+void check_same_device(const Array &a);      // an array living on another device is MOVED to the active one (cuda/Array.cpp:61-74)
 
 // ---------------------------------------------------------------------------------------------
 // type-erased kernel launchers (kernels/*.cu).  Views carry pointers with the offset applied.

@@ -600,10 +600,35 @@ Array *retain(const Array &p) {
     return a;
 }
 
-void check_same_device(const Array &a) {
-    if (a.device() != active_device())
-        fail(AF_ERR_DEVICE, "array lives on device %d but the active device is %d (no implicit migration)",
-             a.device(), active_device());
+// An array used on a device other than the one it lives on is MOVED to the active device, like the reference's
+// checkAndMigrate (/root/reference/src/backend/cuda/Array.cpp:61-74): a fresh buffer from the active device's pool, one
+// peer copy ordered after the work already enqueued on the source device's stream, and the handle now belongs to the
+// active device (other handles / views of the old buffer keep it).  The caller blocks until the copy has landed: the old
+// buffer may return to its pool the moment this handle lets go of it.
+void check_same_device(const Array &ca) {
+    const int act = active_device();
+    if (ca.device() == act) return;
+    Array &a = const_cast<Array &>(ca);
+    if (a.expr)
+        fail(AF_ERR_DEVICE, "an unevaluated expression built on device %d cannot be consumed on device %d", a.device(), act);
+    const int src = a.device();
+    if (a.buf && a.buf->ptr && a.buf->bytes) {
+        Device &S = dev(src), &D = dev(act);
+        std::shared_ptr<Buffer> moved = pool_alloc(a.buf->bytes);   // on the active device
+        cudaEvent_t ev = nullptr;
+        AFB_CUDA(cudaSetDevice(src));
+        AFB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, S.stream);
+        cudaSetDevice(act);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(D.stream, ev, 0);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(moved->ptr, act, a.buf->ptr, src, a.buf->bytes, D.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+        cudaEventDestroy(ev);
+        if (e != cudaSuccess) fail(AF_ERR_DEVICE, "moving an array from device %d to device %d failed: %s", src, act, cudaGetErrorString(e));
+        a.buf = moved;
+        if (g_trace) fprintf(stderr, "[afb200] array moved from device %d to device %d (%zu bytes)\n", src, act, moved->bytes);
+    }
+    a.info.devId = (a.info.devId & ~0xffu) | (unsigned)act;
 }
 
 View view_of(const Array &a) {
