@@ -214,6 +214,7 @@ struct ChainWhereArgs {
     dim_t ntiles;
     uint gen;
     uint base;
+    uint skip;                     // pipe_where_kernel: leading elements of `in` that are not part of the array (unaligned views)
     unsigned long long *ticket;
     unsigned long long ticket_base;
     unsigned long long *debug;     // optional per-CTA cycle counters of pipe_where_kernel (AFB200_PIPE_DEBUG=1)
@@ -644,7 +645,8 @@ __global__ void __launch_bounds__(kPW_Threads, 1) pipe_where_kernel(const ChainW
             for (int u = 0; u < U; u++) {
                 const int q = (warp * U + u) * 32 + lane;
                 const Vec16 v = *reinterpret_cast<const Vec16 *>(stg + (size_t)q * 16);
-                const uint mm = nonzero_mask<T>(v);
+                uint mm = nonzero_mask<T>(v);
+                if (q == 0 && sub == 0 && tile == 0) mm &= ~((1u << a.skip) - 1u);   // unaligned view: the elements in front of it
                 mk[sub * Lay::NVEC + q] = (unsigned short)mm;
                 cnt += __popc(mm);
             }
@@ -823,7 +825,12 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
                       const HostRet *ret, const ShardLink *link) {
     const dim_t n = in.dims[0] * in.dims[1] * in.dims[2] * in.dims[3];
     constexpr dim_t CT = (dim_t)kChainThreads * kCW_U * VecN<T>::value;
-    if (aligned_to(in.ptr, 16) && aligned_to(out, 16) && n >= 2 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
+    // an input that is not 16-byte aligned (a view with an offset) is read from the aligned address below it: the few
+    // elements in front belong to the same allocation (allocations are 256-byte aligned), their mask bits are cleared in
+    // the kernel and the indices are shifted back (r02a sent such views to the 1.2 TB/s first-generation kernel)
+    const uint skip = (uint)((reinterpret_cast<uintptr_t>(in.ptr) & 15) / sizeof(T));
+    const bool elem_aligned = (reinterpret_cast<uintptr_t>(in.ptr) % sizeof(T)) == 0;
+    if (elem_aligned && aligned_to(out, 16) && n >= 2 * (dim_t)PipeWhereLayout<T>::TILE && !env_int("AFB200_NO_PIPE", 0)) {
         typedef PipeWhereLayout<T> PL;
         auto kern = pipe_where_kernel<T>;
         static bool configured[64] = {false};
@@ -834,14 +841,15 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         }
         ChainWhereArgs<T> a;
         a.debug = nullptr;
-        a.in = (const T *)in.ptr;
-        a.n = n;
+        a.in = (const T *)in.ptr - skip;
+        a.n = n + skip;
+        a.skip = skip;
         a.out = out;
         a.total = d_count;
-        a.ntiles = (n + PL::TILE - 1) / PL::TILE;
+        a.ntiles = (a.n + PL::TILE - 1) / PL::TILE;
         a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
         a.gen = c.scratch->next_wepoch(c.stream);
-        a.base = base;
+        a.base = base - skip;
         a.host_wire = ret ? ret->wire : nullptr;
         a.host_seq = ret ? ret->seq : 0u;
         a.comm = peer_comm_of(link);
@@ -892,6 +900,7 @@ static void run_where(const LaunchCtx &c, const View &in, uint *out, unsigned lo
         a.descs = (unsigned long long *)c.scratch->need_wtiles((size_t)a.ntiles * 8, c.stream);
         a.gen = c.scratch->next_wepoch(c.stream);
         a.base = base;
+        a.skip = 0u;
         a.host_wire = ret ? ret->wire : nullptr;
         a.host_seq = ret ? ret->seq : 0u;
         a.comm = peer_comm_of(link);

@@ -502,6 +502,30 @@ def test_pipe_where(af, orc, code):
             same_bits(got.to_numpy().reshape(-1), want, "pipe where n=%d p=%g" % (n, density))
 
 
+@pytest.mark.parametrize("code", [po.U8, po.S16, po.F32, po.F64, po.B8])
+def test_pipe_where_unaligned_views(af, orc, code):
+    """views whose first element is not 16-byte aligned go through the pipelined kernel too: it reads from the aligned
+    address below and drops the elements in front (hits right at the start, in the dropped part and at the very end)"""
+    rng = np.random.default_rng(9250 + code)
+    esz = np.dtype(po.NP_OF[code]).itemsize
+    tile = 4 * 16 * 4 * 32 * (16 // esz)
+    per_vec = 16 // esz
+    n = 2 * tile + 77
+    for off in sorted({1, per_vec - 1, max(1, per_vec // 2)}):
+        for density in (0.5, 0.02, 1.0):
+            base = rand_data(rng, code, (n + off,), small=True)
+            mask = rng.random(n + off) < density
+            mask[:off + 2] = True              # hits in front of the view (must not be reported) and on its first elements
+            mask[-1] = True
+            one = np.ones((), base.dtype)
+            base = np.where(mask, np.where(base == 0, one, base), 0 * one).astype(base.dtype)
+            g = to_gpu(af, base, None, dtype=code).index(af.seq(off, n + off - 1, 1))
+            want = orc.where(base[off:], dtype=code)
+            got = af.where(g)
+            assert got.dims == (want.size, 1, 1, 1), (off, density, got.dims, want.size)
+            same_bits(got.to_numpy().reshape(-1), want, "pipe where view off=%d p=%g" % (off, density))
+
+
 def test_pipe_back_to_back(af, orc):
     """many launches in a row share the descriptor array (generation tags) and the ticket counter"""
     rng = np.random.default_rng(9300)
