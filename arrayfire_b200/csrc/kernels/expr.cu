@@ -319,15 +319,15 @@ template<typename K> static unsigned expr_grid(const LaunchCtx &c, K kern, dim_t
     return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-static int occ[4][kExprDepth + 2];   // resident CTAs per SM by kernel and stack depth (same on every device of a node)
+static int occ[64][4][kExprDepth + 2];   // resident CTAs per SM by device, kernel and stack depth (the shared-memory attribute is per device)
 
 void launch_expr_eval(const LaunchCtx &c, const ExprProg &p, bool dbl, void *out, int out_type, dim_t n) {
     if (n <= 0) return;
     const size_t sm = expr_stack_bytes(p.depth);
     if (dbl) {
-        expr_eval_kernel<double><<<expr_grid(c, expr_eval_kernel<double>, n, ExprW<double>::value, sm, occ[0]), kExprThreads, sm, c.stream>>>(p, out, out_type, n);
+        expr_eval_kernel<double><<<expr_grid(c, expr_eval_kernel<double>, n, ExprW<double>::value, sm, occ[c.device & 63][0]), kExprThreads, sm, c.stream>>>(p, out, out_type, n);
     } else {
-        expr_eval_kernel<float><<<expr_grid(c, expr_eval_kernel<float>, n, ExprW<float>::value, sm, occ[1]), kExprThreads, sm, c.stream>>>(p, out, out_type, n);
+        expr_eval_kernel<float><<<expr_grid(c, expr_eval_kernel<float>, n, ExprW<float>::value, sm, occ[c.device & 63][1]), kExprThreads, sm, c.stream>>>(p, out, out_type, n);
     }
     note_launches(1);
     post_launch_check("expr_eval_kernel");
@@ -342,12 +342,12 @@ void launch_expr_reduce(const LaunchCtx &c, const ExprProg &p, bool dbl, int mod
         fprintf(stderr, "\n");
     }
     if (dbl) {
-        const unsigned grid = expr_grid(c, expr_reduce_kernel<double>, n, ExprW<double>::value, sm, occ[2]);
+        const unsigned grid = expr_grid(c, expr_reduce_kernel<double>, n, ExprW<double>::value, sm, occ[c.device & 63][2]);
         auto *parts = (ExprPart<double> *)c.scratch->need_partials((size_t)grid * sizeof(ExprPart<double>));
         expr_reduce_kernel<double><<<grid, kExprThreads, sm, c.stream>>>(p, mode, n, out, parts, ticket, ret ? ret->wire : nullptr,
                                                                          ret ? ret->seq : 0u);
     } else {
-        const unsigned grid = expr_grid(c, expr_reduce_kernel<float>, n, ExprW<float>::value, sm, occ[3]);
+        const unsigned grid = expr_grid(c, expr_reduce_kernel<float>, n, ExprW<float>::value, sm, occ[c.device & 63][3]);
         auto *parts = (ExprPart<float> *)c.scratch->need_partials((size_t)grid * sizeof(ExprPart<float>));
         expr_reduce_kernel<float><<<grid, kExprThreads, sm, c.stream>>>(p, mode, n, out, parts, ticket, ret ? ret->wire : nullptr,
                                                                         ret ? ret->seq : 0u);
