@@ -183,3 +183,65 @@ def test_b8_rules(af):
     s = af.sum(g, 0)
     assert s.dtype == po.U32
     np.testing.assert_array_equal(s.to_numpy().reshape(-1), A.sum(axis=0).astype(np.uint32))
+
+
+# ---- by-key reductions and ragged max: the known answers of test/reduce.cpp (tests/golden/kat_bykey.py) -------------------
+from tests.golden import kat_bykey as kb  # noqa: E402
+
+BYKEY_TYPES = [po.F32, po.F64, po.S32, po.U32, po.S64, po.U64, po.S16, po.U16, po.U8, po.S8]
+
+
+@pytest.mark.parametrize("code", BYKEY_TYPES)
+def test_by_key_kats(af, code):
+    for name, fn, keys, vals, rkeys, gold, where in kb.TYPED:
+        gk = af.Array.from_numpy(np.asarray(keys, np.int32))
+        gv = af.Array.from_numpy(np.asarray(vals).astype(po.NP_OF[code]), dtype=code)
+        ko, vo = getattr(af, fn)(gk, gv, 0)
+        assert ko.to_numpy().reshape(-1).tolist() == rkeys, (name, where)
+        assert vo.to_numpy().reshape(-1).astype(np.float64).tolist() == [float(g) for g in gold], (name, where, code)
+
+
+@pytest.mark.parametrize("code", [po.F32, po.F64])
+def test_by_key_nans_kat(af, code):
+    name, fn, keys, vals, nanval, rkeys, gold = kb.NAN_CASE
+    ko, vo = getattr(af, fn)(af.Array.from_numpy(np.asarray(keys, np.int32)),
+                             af.Array.from_numpy(np.asarray(vals).astype(po.NP_OF[code])), 0, nanval=nanval)
+    assert ko.to_numpy().reshape(-1).tolist() == rkeys and vo.to_numpy().reshape(-1).tolist() == [float(g) for g in gold]
+
+
+def test_by_key_tiled_dims_kat(af):
+    k = np.asarray(kb.KEYS_A, np.int32)
+    v = np.asarray(kb.VALS_A, np.float32)
+    gold = [0, 8, 6, 10, 4]
+    for dim, shape in ((0, (8, 2, 2, 2)), (1, (2, 8)), (2, (2, 1, 8)), (3, (2, 1, 1, 8))):
+        idx = [None] * len(shape)
+        idx[dim] = slice(None)
+        x = np.asfortranarray(np.broadcast_to(v[tuple(idx)], shape).astype(np.float32))
+        ko, vo = af.sum_by_key(af.Array.from_numpy(k), af.Array.from_numpy(x), dim, nanval=0.0)
+        w = np.moveaxis(vo.to_numpy().reshape(po.dims4(vo.to_numpy().shape), order="F"), dim, 0).reshape(5, -1)
+        assert all(w[:, j].tolist() == gold for j in range(w.shape[1])), (dim, w)
+
+
+def test_ragged_max_kat(af):
+    for name, arr, dims, rl, rdims, dim, gv, gi in kb.RAGGED:
+        x = np.asfortranarray(np.asarray(arr, np.int32).reshape(dims, order="F"))
+        r = np.asfortranarray(np.asarray(rl, np.uint32).reshape(rdims, order="F"))
+        val, idx = af.max_ragged(af.Array.from_numpy(x), af.Array.from_numpy(r), dim)
+        assert val.to_numpy().reshape(-1).tolist() == gv and idx.to_numpy().reshape(-1).tolist() == gi, name
+
+
+def test_by_key_issues_kat(af):
+    key, runs = kb.issue_2955()
+    val = np.random.default_rng(0).random(256).astype(np.float32)
+    ko, vo = af.sum_by_key(af.Array.from_numpy(key), af.Array.from_numpy(val), 0)
+    assert ko.dims[0] == runs and vo.dims[0] == runs
+    val2 = np.asfortranarray(np.random.default_rng(1).random((8, 256)).astype(np.float32))
+    ko, vo = af.sum_by_key(af.Array.from_numpy(key), af.Array.from_numpy(val2), 1)
+    assert ko.dims[0] == runs and vo.dims[1] == runs
+    zeros, ones, n = kb.issue_3062()
+    gz = af.Array.from_numpy(zeros)
+    assert int(af.sum_by_key(gz, af.Array.from_numpy(ones), 0)[1].to_numpy().reshape(-1)[0]) == n
+    assert int(af.count_by_key(gz, af.Array.from_numpy(ones), 0)[1].to_numpy().reshape(-1)[0]) == n
+    ones2 = af.Array.from_numpy(np.asfortranarray(np.ones((2, 129), np.uint32)))
+    assert af.sum_by_key(gz, ones2, 1)[1].to_numpy().reshape(-1).tolist() == [n, n]
+    assert af.count_by_key(gz, ones2, 1)[1].to_numpy().reshape(-1).tolist() == [n, n]
