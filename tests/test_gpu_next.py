@@ -104,3 +104,29 @@ def test_set_unique_sorted(af, port_oracle):
     with pytest.raises(af.AfError) as ei:
         af.set_unique(af.Array.from_numpy(np.array([3, 1, 2], dtype=np.int32)), False)
     assert ei.value.code == 301
+
+
+@pytest.mark.parametrize("code", [po.F32, po.F64, po.S32, po.U32, po.U8, po.S16])
+def test_reference_sat_integral_image(af, code):
+    """SAT.IntegralImage (/root/reference/test/sat.cpp:41-51): sat(a) == accum(accum(a, 0), 1) on a 530 x 671 array, bit for bit"""
+    rng = np.random.default_rng(8800 + code)
+    x = np.asfortranarray(rng.integers(0, 9, (530, 671)).astype(po.NP_OF[code]))
+    g = af.Array.from_numpy(x, dtype=code)
+    s = af.sat(g)
+    c = af.accum(af.accum(g, 0), 1)
+    assert s.dtype == c.dtype and s.dims == c.dims
+    assert s.to_numpy().tobytes() == c.to_numpy().tobytes()
+
+
+def test_reference_diff_large_dim(af):
+    """Diff1.DiffLargeDim / Diff2.DiffLargeDim (/root/reference/test/diff1.cpp:186-211, diff2.cpp:179-206): a constant line of
+    65535 * 32 + 1 elements along each of the four dims differentiates to zeros"""
+    n = 65535 * 32 + 1
+    for dim in range(4):
+        dims = [1, 1, 1, 1]
+        dims[dim] = n
+        one = af.Array.from_numpy(np.ones(dims, dtype=np.float32, order="F"))
+        d1, d2 = af.diff1(one, dim), af.diff2(one, dim)
+        assert d1.dims[dim] == n - 1 and d2.dims[dim] == n - 2
+        assert af.sum_all(d1) == 0.0 and af.sum_all(d2) == 0.0
+        assert af.count_all(d1) == 0.0 and af.count_all(d2) == 0.0
