@@ -245,3 +245,69 @@ def test_by_key_issues_kat(af):
     ones2 = af.Array.from_numpy(np.asfortranarray(np.ones((2, 129), np.uint32)))
     assert af.sum_by_key(gz, ones2, 1)[1].to_numpy().reshape(-1).tolist() == [n, n]
     assert af.count_by_key(gz, ones2, 1)[1].to_numpy().reshape(-1).tolist() == [n, n]
+
+
+# ---- further reduction known answers / properties of test/reduce.cpp (tests/golden/kat_reduce.py) ------------------------------
+from tests.golden import kat_reduce as kr  # noqa: E402
+
+
+def test_reduce_minmax_cplx_nan_kat(af):
+    g = af.Array.from_numpy(np.asfortranarray(kr.CPLX_NAN))
+    np.testing.assert_array_equal(af.min(g, 0).to_numpy().reshape(-1), kr.CPLX_NAN_MIN)
+    np.testing.assert_array_equal(af.max(g, 0).to_numpy().reshape(-1), kr.CPLX_NAN_MAX)
+
+
+def test_reduce_nan_properties_kat(af):
+    a = kr.nan_vector()
+    g = af.Array.from_numpy(a)
+    ok = a[~np.isnan(a)]
+    assert af.min_all(g) == float(ok.min()) and af.max_all(g) == float(ok.max())          # MinMax.MinMaxNaN
+    assert np.isnan(af.sum_all(g))                                                         # Sum.NaN
+    want = float(np.where(np.isnan(a), 0, a).astype(np.float64).sum())
+    assert abs(af.sum_all(g, nanval=0.0) / a.size - want / a.size) < 1e-5
+    p = np.random.default_rng(12).random(5).astype(np.float32)
+    p[2] = np.nan
+    gp = af.Array.from_numpy(p)
+    assert np.isnan(af.product_all(gp))                                                    # Product.NaN
+    assert abs(af.product_all(gp, nanval=1.0) - float(np.prod(np.where(np.isnan(p), 1, p).astype(np.float64)))) < 1e-5
+    a, b = kr.count_nan_pair()
+    assert af.count_all(af.Array.from_numpy(a)) == af.count_all(af.Array.from_numpy(b)) == float(np.count_nonzero(b))   # Count.NaN
+    a, b = kr.anyall_nan_pair()
+    ga, gb = af.Array.from_numpy(a), af.Array.from_numpy(b)
+    assert af.any_true_all(gb) and af.all_true_all(gb) and af.any_true_all(ga) and not af.all_true_all(ga)            # AnyAll.NaN
+
+
+def test_reduce_product_of_bools_issue_2543_kat(af):
+    ones = af.Array.from_numpy(np.ones((5, 5), np.int8, order="F"), dtype=po.B8)
+    assert af.product_all(ones) > 0
+    x = np.asfortranarray((np.random.default_rng(13).random((5, 5)) < 0.8).astype(np.int8))
+    g = af.Array.from_numpy(x, dtype=po.B8)
+    assert af.product_all(g) == float(np.prod(x.astype(np.uint32)))
+    assert af.all_true(g, 0).to_numpy().reshape(-1).astype(np.int64).tolist() == \
+        af.product(g, 0).to_numpy().reshape(-1).astype(np.int64).tolist()
+
+
+def test_reduce_nanval_issue_3255_kat(af):
+    gk = af.Array.from_numpy(kr.ISSUE_3255_KEYS)
+    for i in range(8):
+        v = kr.ISSUE_3255_VALS.copy()
+        v[i] = np.nan
+        gv = af.Array.from_numpy(v)
+        for fn in (af.product_by_key, af.sum_by_key):
+            ko, vo = fn(gk, gv, 0, nanval=1.0)
+            assert not np.isnan(vo.to_numpy()).any(), (fn.__name__, i)
+            assert ko.to_numpy().reshape(-1).tolist() == [0, 1, 2, 0]
+
+
+def test_reduce_max_all_indexed_kat(af):
+    """MaxAll.IndexedSmall / IndexedBig / Reduce.AllSmallIndexed (test/reduce.cpp:1301-1355): whole-array max of a sub-array view"""
+    rng = np.random.default_rng(14)
+    for num, st, en in ((1000, 10, 900), (100000, 1000, 99000)):
+        a = rng.random(num).astype(np.float32)
+        g = af.Array.from_numpy(a).index(af.seq(st, en, 1))
+        assert af.max_all(g) == float(a[st:en + 1].max())
+    ln = 512
+    r = np.asfortranarray(np.stack([np.arange(ln, dtype=np.float32)] * 2, axis=1))
+    gb = af.Array.from_numpy(r).index(af.seq(0, ln // 2 - 1, 1), af.seq(0, 1, 1))
+    for _ in range(50):
+        assert af.max_all(gb) == ln // 2 - 1
