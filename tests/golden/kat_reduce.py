@@ -40,3 +40,20 @@ def anyall_nan_pair(seed=9, num=10000):
 # Reduce.nanval_issue_3255 (test/reduce.cpp:2382-2412): one NaN at every position in turn; *_by_key_nan(nanval = 1) never yields NaN
 ISSUE_3255_KEYS = np.asarray([0, 0, 1, 1, 1, 2, 2, 0], np.uint32)
 ISSUE_3255_VALS = np.asarray([1, 2, 3, 4, 5, 6, 7, 8], np.float64)
+
+
+def reduce_half_cases():
+    """ReduceHalf.Sum / Product (test/reduce.cpp:1375-1488): constant f16 arrays reduced along `dim` (-1: the first non-singleton
+    dim) give value * n (sum) / value ** n (product, skipped when it overflows) as f32.  Yields (value, dims, dim)."""
+    for n in (10, 2048, 2049, 8192):
+        for tail in ((), (10,), (10, 10), (10, 10, 10)):
+            yield 1.0, (n,) + tail, -1
+    for n in (10, 2048, 2049, 8192):
+        for tail in ((), (10,), (10, 10)):
+            yield 1.25, (10, n) + tail, 1
+    for n in (10, 2048, 2049, 8192):
+        for tail in ((), (10,)):
+            yield 1.25, (10, 10, n) + tail, 2
+
+
+HALF_RAMP = np.asarray([1, 2, 3, 4, 5, 6, 7], np.float16)   # ReduceHalf.Min / Max / Count / AnyTrue / AllTrue (test/reduce.cpp:1490-1548)

@@ -62,3 +62,21 @@ def test_nanval_issue_3255(orc):
             tk, wk, tv, wv = getattr(orc, fn)(kr.ISSUE_3255_KEYS, v, 0, nanval=1.0)
             assert not np.isnan(wv).any(), (fn, i)
             assert wk.reshape(-1).tolist() == [0, 1, 2, 0]
+
+
+def test_reduce_half(orc):
+    for value, dims, dim in kr.reduce_half_cases():
+        x = np.full(dims, value, np.float16, order="F")
+        d = dim if dim >= 0 else 0
+        n = dims[d]
+        t, w = orc.sum(x, d, dtype=po.F16)
+        assert t == po.F32 and np.all(w == np.float32(value * n)), (dims, dim)
+        with np.errstate(over="ignore"):
+            p = np.float32(value) ** n
+        if np.isfinite(p):
+            t, w = orc.product(x, d, dtype=po.F16)
+            assert t == po.F32 and np.all(w == p), (dims, dim)
+    r = kr.HALF_RAMP
+    assert orc.min(r, 0, dtype=po.F16)[1].reshape(-1)[0] == np.float16(1) and orc.max(r, 0, dtype=po.F16)[1].reshape(-1)[0] == np.float16(7)
+    assert int(orc.count(r, 0, dtype=po.F16)[1].reshape(-1)[0]) == 7
+    assert bool(orc.any_true(r, 0, dtype=po.F16)[1].reshape(-1)[0]) and bool(orc.all_true(r, 0, dtype=po.F16)[1].reshape(-1)[0])
