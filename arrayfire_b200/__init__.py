@@ -545,10 +545,19 @@ def stdev_all(a, bias=AF_VARIANCE_POPULATION):
     return _all(lib.af_stdev_all_v2, a, ctypes.c_int(bias))
 
 
-def meanvar(a, dim=-1, bias=AF_VARIANCE_POPULATION):
+def meanvar(a, dim=-1, bias=AF_VARIANCE_POPULATION, weights=None):
+    """af::meanvar (api/cpp/var.cpp; api/c/var.cpp:418-470): weights=None is the reference's empty weights array"""
     m, v = _vp(), _vp()
-    _check(lib.af_meanvar(ctypes.byref(m), ctypes.byref(v), a.handle, None, ctypes.c_int(bias), ctypes.c_longlong(_fnsd(a, dim))))
+    _check(lib.af_meanvar(ctypes.byref(m), ctypes.byref(v), a.handle, weights.handle if weights is not None else None, ctypes.c_int(bias),
+                          ctypes.c_longlong(_fnsd(a, dim))))
     return Array(m), Array(v)
+
+
+def var_weighted(a, weights, dim=-1):
+    """af::var(in, weights, dim) (api/c/var.cpp:263-325)"""
+    h = _vp()
+    _check(lib.af_var_weighted(ctypes.byref(h), a.handle, weights.handle, ctypes.c_longlong(_fnsd(a, dim))))
+    return Array(h)
 
 
 def norm(a, kind=AF_NORM_VECTOR_2, p=1.0, q=1.0):

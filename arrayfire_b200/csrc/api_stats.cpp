@@ -219,15 +219,31 @@ af_err af_var_v2(af_array *out, const af_array in, const af_var_bias bias, const
 af_err af_var(af_array *out, const af_array in, const bool isbiased, const dim_t dim) {
     return af_var_v2(out, in, isbiased ? AF_VARIANCE_SAMPLE : AF_VARIANCE_POPULATION, dim);   // var.cpp:187-192
 }
+static af_err meanvar_weighted(af_array *mean, af_array *var, const af_array in, const af_array weights, int bias, dim_t dim);
+
 af_err af_meanvar(af_array *mean, af_array *var, const af_array in, const af_array weights, const af_var_bias bias,
                   const dim_t dim) {
     if (weights != nullptr) {   // an EMPTY weights array means "unweighted" (var.cpp:113: weights.isEmpty()); af::array() is one
-        AFB_API_BEGIN
-        Array *w = from_handle(weights);
-        AFB_ARG(3, w->info.type == f32 || w->info.type == f64);                                  // var.cpp:424-426
-        if (w->elements() > 0) fail(AF_ERR_NOT_SUPPORTED, "af_meanvar: weighted form is not supported by libafb200 yet");
+        bool weighted = false;
+        {
+            AFB_API_BEGIN
+            Array *w = from_handle(weights);
+            AFB_ARG(3, w->info.type == f32 || w->info.type == f64);                              // var.cpp:424-426
+            weighted = w->elements() > 0;
+            }
+            catch (...) { return ::afb::current_exception_to_err(); }
         }
-        catch (...) { return ::afb::current_exception_to_err(); }
+        if (weighted) {
+            {
+                AFB_API_BEGIN
+                AFB_ARG(5, dim >= 0 && dim <= 3);
+                AFB_ARG(0, mean != nullptr);
+                AFB_ARG(1, var != nullptr);
+                }
+                catch (...) { return ::afb::current_exception_to_err(); }
+            }
+            return meanvar_weighted(mean, var, in, weights, (int)bias, dim);
+        }
     }
     return moments_dim(var, mean, true, in, (int)bias, dim, false, false, 5);
 }
@@ -485,10 +501,55 @@ af_err af_var_all_weighted(double *real, double *imag, const af_array in, const 
     return AF_SUCCESS;
 }
 
-af_err af_var_weighted(af_array *, const af_array, const af_array, const dim_t) {
-    AFB_API_BEGIN
-    fail(AF_ERR_NOT_SUPPORTED, "af_var_weighted: the dim-wise weighted variance needs a broadcast of the means; not supported by libafb200 yet");
-    AFB_API_END
+af_err af_var_weighted(af_array *out, const af_array in, const af_array weights, const dim_t dim) {
+    {
+        AFB_API_BEGIN
+        AFB_ARG(3, dim >= 0 && dim <= 3);                                        // var.cpp:267
+        AFB_ARG(0, out != nullptr);
+        }
+        catch (...) { return ::afb::current_exception_to_err(); }
+    }
+    H m;
+    return meanvar_weighted(&m.h, out, in, weights, (int)AF_VARIANCE_POPULATION, dim);      // var.cpp:283-325
 }
 
 }  // extern "C"
+
+
+// The dim-wise weighted mean / variance pair of the reference (var.cpp:104-142): mean = sum(w x) / sum(w) and
+//     var = sum_dim((x - mean)^2) / (sum(w) - (bias == SAMPLE))
+// -- the weights enter the mean and the normaliser only, the squared deviations are NOT weighted (var.cpp:134-139).  No
+// broadcast of the means is needed: with m the plain mean and M2 = sum((x - m)^2) of ONE Welford pass over x (launch_var),
+//     sum((x - mean)^2) = M2 + n (m - mean)^2,
+// so x is read twice (the moments, the weighted sum) and w twice (its sum, the weighted sum); everything after that runs on
+// the reduced arrays.
+static af_err meanvar_weighted(af_array *mean, af_array *var, const af_array in, const af_array weights, int bias, dim_t dim) {
+    H x, w, wm, m, v, wsum, d, d2, t, nn, t2, den, q, one;
+    AFB_TRY(weighted_operands(x, w, in, weights, 2));
+    AFB_TRY(af_mean_weighted(&wm.h, in, weights, dim));
+    AFB_TRY(moments_dim(&v.h, &m.h, true, in, BIAS_POPULATION, dim, false, false, 5));
+    AFB_TRY(weighted_cast(x, w, in, weights));
+    AFB_TRY(af_sum(&wsum.h, w.h, (int)dim));
+    af_dtype tc;
+    AFB_TRY(af_get_type(&tc, wm.h));
+    dim_t id[4], od[4];
+    AFB_TRY(af_get_dims(&id[0], &id[1], &id[2], &id[3], in));
+    AFB_TRY(af_get_dims(&od[0], &od[1], &od[2], &od[3], wm.h));
+    AFB_TRY(af_sub(&d.h, m.h, wm.h, false));
+    AFB_TRY(af_mul(&d2.h, d.h, d.h, false));
+    AFB_TRY(af_add(&t.h, v.h, d2.h, false));
+    AFB_TRY(af_constant(&nn.h, (double)id[dim], 4, od, tc));
+    AFB_TRY(af_mul(&t2.h, t.h, nn.h, false));
+    if (bias == BIAS_SAMPLE) {                                                   // var.cpp:127-129
+        AFB_TRY(af_constant(&one.h, 1.0, 4, od, tc));
+        AFB_TRY(af_sub(&den.h, wsum.h, one.h, false));
+    } else {
+        AFB_TRY(af_retain_array(&den.h, wsum.h));
+    }
+    AFB_TRY(af_div(&q.h, t2.h, den.h, false));
+    AFB_TRY(af_eval(q.h));
+    *mean = wm.h;
+    *var = q.h;
+    wm.h = q.h = nullptr;
+    return AF_SUCCESS;
+}

@@ -260,7 +260,7 @@ AFAPI af_err af_mean_weighted(af_array *out, const af_array in, const af_array w
 AFAPI af_err af_mean_all_weighted(double *real, double *imag, const af_array in, const af_array weights);
 AFAPI af_err af_var(af_array *out, const af_array in, const bool isbiased, const dim_t dim);              /* var.cpp:187 */
 AFAPI af_err af_var_v2(af_array *out, const af_array in, const af_var_bias bias, const dim_t dim);        /* var.cpp:194 */
-AFAPI af_err af_var_weighted(af_array *out, const af_array in, const af_array weights, const dim_t dim);
+AFAPI af_err af_var_weighted(af_array *out, const af_array in, const af_array weights, const dim_t dim); /* var.cpp:263 */
 AFAPI af_err af_var_all(double *realVal, double *imagVal, const af_array in, const bool isbiased);        /* var.cpp:336 */
 AFAPI af_err af_var_all_v2(double *realVal, double *imagVal, const af_array in, const af_var_bias bias);  /* var.cpp:343 */
 AFAPI af_err af_var_all_weighted(double *realVal, double *imagVal, const af_array in, const af_array weights);

@@ -602,6 +602,26 @@ class AfOracle:
         denom = n if bias == AF_VARIANCE_POPULATION else n - 1
         return STAT_TO[ti], self.o.var(x, dim, denom, False, want_mean, ti)
 
+    @staticmethod
+    def meanvar_weighted(x, w, dim, bias=AF_VARIANCE_POPULATION):
+        """af_meanvar with weights / af_var_weighted (api/c/var.cpp:104-142, 263-325), restated step by step in the result type
+        (f32; f64 for f64 / s64 / u64 inputs): mean = sum(x w) / sum(w) (mean.cpp, weighted); the squared deviations from that
+        mean are summed UNWEIGHTED (var.cpp:134-136) and scaled by 1 / (sum(w) - (bias == SAMPLE)) (var.cpp:122-130)."""
+        if not (0 <= dim <= 3):
+            raise AfArgError("dim")
+        x, w = np.asarray(x), np.asarray(w)
+        if w.dtype not in (np.float32, np.float64):
+            raise AfArgError("weights")
+        tc = np.float64 if x.dtype in (np.float64, np.int64, np.uint64) else np.float32
+        d = dims4(x.shape)
+        xc, wc = x.astype(tc).reshape(d, order="F"), w.astype(tc).reshape(d, order="F")
+        wsum = wc.sum(axis=dim, keepdims=True, dtype=tc)
+        mean = ((xc * wc).sum(axis=dim, keepdims=True, dtype=tc) / wsum).astype(tc)
+        diff = xc - mean
+        red = (diff * diff).sum(axis=dim, keepdims=True, dtype=tc)
+        norm = tc(1) / (wsum - tc(1) if bias == AF_VARIANCE_SAMPLE else wsum)
+        return mean, (norm * red).astype(tc)
+
     def var_all(self, x, bias=AF_VARIANCE_POPULATION, dtype=None):
         """af_var_all_v2: N - (bias == SAMPLE) (api/c/var.cpp:71-73)"""
         return self.o.var_all(x, np.asarray(x).size - (1 if bias == AF_VARIANCE_SAMPLE else 0), False, code_of(np.asarray(x), dtype))

@@ -311,3 +311,25 @@ def test_reduce_max_all_indexed_kat(af):
     gb = af.Array.from_numpy(r).index(af.seq(0, ln // 2 - 1, 1), af.seq(0, 1, 1))
     for _ in range(50):
         assert af.max_all(gb) == ln // 2 - 1
+
+
+def test_reduce_half_kat(af):
+    """ReduceHalf.* (test/reduce.cpp:1375-1548): sums / products of constant f16 arrays come back as f32 (value * n, value ** n);
+    min / max stay f16; count / any / all of the 1..7 ramp"""
+    for value, dims, dim in kr.reduce_half_cases():
+        x = np.full(dims, value, np.float16, order="F")
+        g = af.Array.from_numpy(x)
+        n = dims[dim if dim >= 0 else 0]
+        s = af.sum(g, dim)
+        assert s.dtype == po.F32 and np.all(s.to_numpy() == np.float32(value * n)), (dims, dim)
+        with np.errstate(over="ignore"):
+            p = np.float32(value) ** n
+        if np.isfinite(p):
+            q = af.product(g, dim)
+            assert q.dtype == po.F32 and np.all(q.to_numpy() == p), (dims, dim)
+    g = af.Array.from_numpy(kr.HALF_RAMP)
+    mn, mx = af.min(g, 0), af.max(g, 0)
+    assert mn.dtype == po.F16 and mx.dtype == po.F16
+    assert mn.to_numpy().reshape(-1)[0] == np.float16(1) and mx.to_numpy().reshape(-1)[0] == np.float16(7)
+    assert int(af.count(g, 0).to_numpy().reshape(-1)[0]) == 7
+    assert bool(af.any_true(g, 0).to_numpy().reshape(-1)[0]) and bool(af.all_true(g, 0).to_numpy().reshape(-1)[0])

@@ -162,9 +162,9 @@ def test_reference_known_answers_on_gpu(af):
         af.stdev(A(np.full(10, 1 - 1j, dtype=np.complex128)), 0)
     with pytest.raises(af.AfError):
         af._check(af.lib.af_stdev(__import__("ctypes").byref(af._vp()), ones.handle, __import__("ctypes").c_longlong(5)))
-    # the one weighted form without a kernel fails loudly
+    # weighted statistics take real inputs only; the failure is loud
     with pytest.raises(af.AfError) as ei:
-        af._check(af.lib.af_var_weighted(__import__("ctypes").byref(af._vp()), ones.handle, ones.handle, __import__("ctypes").c_longlong(0)))
+        af.var_weighted(A(np.full(10, 1 - 1j, dtype=np.complex64)), ones, 0)
     assert ei.value.code == 301
 
 
@@ -265,3 +265,66 @@ def test_weighted_mean_and_variance(af):
     gd, g1 = af.Array.from_numpy(np.asfortranarray(data)), af.Array.from_numpy(np.ones((1, 512), np.float32, order="F"))
     af._check(af.lib.af_mean_weighted(ctypes.byref(h), gd.handle, g1.handle, ctypes.c_longlong(1)))
     assert abs(float(af.Array(h).to_numpy().reshape(-1)[0]) - float(data.astype(np.float64).mean())) <= 1e-3
+
+
+def test_meanvar_large_known_answers(af):
+    """MeanVar*.Large (test/meanvar.cpp:239-266, 299-311) on the CUDA path: 0..1999 along its long dim -> mean 999.5, sample
+    variance 333500; as 500x4 along dim 0 -> means 249.5 + 500 k, sample variance 20875"""
+    ramp = np.arange(2000)
+    for dt in (np.float32, np.float64, np.int32, np.uint32, np.int64, np.uint64, np.int16, np.uint16):
+        x = ramp.astype(dt)
+        for dim, shape in enumerate([(2000,), (1, 2000), (1, 1, 2000)]):
+            m, v = af.meanvar(af.Array.from_numpy(np.asfortranarray(x.reshape(shape))), dim, po.AF_VARIANCE_SAMPLE)
+            assert abs(float(m.to_numpy().reshape(-1)[0]) - 999.5) <= 1e-3, (dt, dim)
+            assert abs(float(v.to_numpy().reshape(-1)[0]) - 333500) <= 333500 * 1e-5, (dt, dim)
+        m, v = af.meanvar(af.Array.from_numpy(np.asfortranarray(x.reshape((500, 4), order="F"))), 0, po.AF_VARIANCE_SAMPLE)
+        assert np.abs(m.to_numpy().reshape(-1) - np.asarray([249.5, 749.5, 1249.5, 1749.5])).max() <= 1e-3
+        assert np.abs(v.to_numpy().reshape(-1) - 20875).max() <= 20875 * 1e-5
+
+
+def test_weighted_variance_along_dim(af, port_oracle):
+    """af_var_weighted / af_meanvar with weights (api/c/var.cpp:104-142, 263-325, 418-470) against the oracle's restatement:
+    weighted mean, UNWEIGHTED squared deviations, 1 / (sum(w) - (bias == SAMPLE)); also on offset views of x and w"""
+    import ctypes
+    orc = port_oracle
+    rng = np.random.default_rng(15)
+    for dt in (np.float32, np.float64, np.int32, np.int64, np.uint8, np.int16):
+        for shape in [(2000,), (500, 4), (4, 500), (20, 7, 3), (4, 5, 3, 2), (70000, 3)]:
+            x = (rng.standard_normal(shape) * 3 + 1).astype(dt) if np.issubdtype(dt, np.floating) else rng.integers(0, 50, shape).astype(dt)
+            f64 = dt in (np.float64, np.int64)
+            wdt = np.float64 if f64 else np.float32
+            w = (rng.random(shape) + 0.5).astype(wdt)
+            x, w = np.asfortranarray(x), np.asfortranarray(w)
+            gx, gw = af.Array.from_numpy(x), af.Array.from_numpy(w)
+            tol = 1e-11 if f64 else 2e-5
+            scale = float(np.abs(x.astype(np.float64)).max()) + 1.0
+            for dim in range(len(shape)):
+                for bias in (po.AF_VARIANCE_POPULATION, po.AF_VARIANCE_SAMPLE):
+                    om, ov = orc.meanvar_weighted(x, w, dim, bias)
+                    m, v = af.meanvar(gx, dim, bias, weights=gw)
+                    gm, gv = m.to_numpy(), v.to_numpy()
+                    assert gm.dtype == wdt and gv.dtype == wdt
+                    vs = max(scale * scale, float(np.abs(ov).max()))
+                    assert np.abs(gm.reshape(-1, order="F") - om.reshape(-1, order="F")).max() <= tol * scale * 4, (dt, shape, dim, bias)
+                    assert np.abs(gv.reshape(-1, order="F") - ov.reshape(-1, order="F")).max() <= tol * vs * 16, (dt, shape, dim, bias)
+                _, ov = orc.meanvar_weighted(x, w, dim, po.AF_VARIANCE_POPULATION)
+                gv = af.var_weighted(gx, gw, dim).to_numpy()
+                assert np.abs(gv.reshape(-1, order="F") - ov.reshape(-1, order="F")).max() <= tol * max(scale * scale, float(np.abs(ov).max())) * 16
+    # offset views of both operands
+    x = np.asfortranarray(rng.standard_normal((300, 40)).astype(np.float32))
+    w = np.asfortranarray((rng.random((300, 40)) + 0.5).astype(np.float32))
+    sx = af.Array.from_numpy(x).index(af.seq(17, 280, 1), af.seq(3, 33, 1))
+    sw = af.Array.from_numpy(w).index(af.seq(17, 280, 1), af.seq(3, 33, 1))
+    for dim in (0, 1):
+        om, ov = orc.meanvar_weighted(x[17:281, 3:34], w[17:281, 3:34], dim)
+        m, v = af.meanvar(sx, dim, po.AF_VARIANCE_POPULATION, weights=sw)
+        assert np.abs(m.to_numpy().reshape(-1, order="F") - om.reshape(-1, order="F")).max() <= 1e-4
+        assert np.abs(v.to_numpy().reshape(-1, order="F") - ov.reshape(-1, order="F")).max() <= 1e-3
+    # an EMPTY weights array is the unweighted form (var.cpp:113); integer weights are an argument error (var.cpp:424-426)
+    g = af.Array.from_numpy(np.arange(10, dtype=np.float32))
+    with pytest.raises(af.AfError) as ei:
+        af.meanvar(g, 0, po.AF_VARIANCE_POPULATION, weights=af.Array.from_numpy(np.ones(10, np.int32)))
+    assert ei.value.code == 202
+    with pytest.raises(af.AfError) as ei:
+        af._check(af.lib.af_var_weighted(ctypes.byref(af._vp()), g.handle, g.handle, ctypes.c_longlong(4)))
+    assert ei.value.code == 202

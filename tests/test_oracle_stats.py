@@ -126,3 +126,54 @@ def test_norm_corrcoef_cov_vs_numpy(port_oracle):
     x64, y64 = x.astype(np.float64), y.astype(np.float64)
     want = ((x64 - x64.mean()) * (y64 - y64.mean())).sum(0) / (500 - 1)
     assert np.abs(c.reshape(-1) - want).max() <= 1e-4
+
+
+def test_meanvar_large_known_answers(port_oracle):
+    """MeanVar*.Large (test/meanvar.cpp:239-266, 299-311): 0..1999 as 2000x1x1 / 1x2000 / 1x1x2000 along its long dim ->
+    mean 999.5, sample variance 333500; as 500x4 along dim 0 -> means 249.5 + 500 k, sample variance 20875 each."""
+    orc = port_oracle
+    ramp = np.arange(2000)
+    for code in (po.F32, po.F64, po.S32, po.U32, po.S64, po.U64, po.S16, po.U16):
+        x = ramp.astype(po.NP_OF[code])
+        for dim, shape in enumerate([(2000,), (1, 2000), (1, 1, 2000)]):
+            _, (m, v) = orc.var(np.asfortranarray(x.reshape(shape)), dim, po.AF_VARIANCE_SAMPLE, want_mean=True)
+            assert abs(float(m.reshape(-1)[0]) - 999.5) <= 1e-3 and abs(float(v.reshape(-1)[0]) - 333500) <= 333500 * 1e-5, (code, dim)
+        _, (m, v) = orc.var(np.asfortranarray(x.reshape((500, 4), order="F")), 0, po.AF_VARIANCE_SAMPLE, want_mean=True)
+        assert np.abs(m.reshape(-1) - np.asarray([249.5, 749.5, 1249.5, 1749.5])).max() <= 1e-3
+        assert np.abs(v.reshape(-1) - 20875).max() <= 20875 * 1e-5
+
+
+def test_meanvar_weighted_restatement(port_oracle):
+    """the weighted af_meanvar / af_var_weighted restatement (api/c/var.cpp:104-142): unit weights reproduce the unweighted pair
+    (population: 1 / N; sample: 1 / (N - 1)); in general the mean is weighted, the squared deviations are not"""
+    orc = port_oracle
+    rng = np.random.default_rng(77)
+    for dt in (np.float32, np.float64, np.int32, np.int64, np.uint8):
+        for shape in [(2000,), (500, 4), (20, 7, 3), (4, 5, 3, 2)]:
+            x = (rng.standard_normal(shape) * 3 + 1).astype(dt) if np.issubdtype(dt, np.floating) else rng.integers(0, 50, shape).astype(dt)
+            x = np.asfortranarray(x)
+            f64 = dt in (np.float64, np.int64)
+            wdt = np.float64 if f64 else np.float32
+            tol = 1e-12 if f64 else 2e-5
+            x64 = x.astype(np.float64)
+            scale = float(np.abs(x64).max()) + 1.0
+            for dim in range(len(shape)):
+                for bias in (po.AF_VARIANCE_POPULATION, po.AF_VARIANCE_SAMPLE):
+                    if bias == po.AF_VARIANCE_SAMPLE and shape[dim] == 1:
+                        continue
+                    m1, v1 = orc.meanvar_weighted(x, np.ones(shape, wdt), dim, bias)
+                    _, (m0, v0) = orc.var(x, dim, bias, want_mean=True)
+                    assert m1.dtype == wdt and v1.dtype == wdt
+                    assert np.abs(m1.reshape(-1) - m0.reshape(-1)).max() <= tol * scale * 4
+                    assert np.abs(v1.reshape(-1) - v0.reshape(-1)).max() <= tol * scale * scale * 16
+                    w = np.asfortranarray((rng.random(shape) + 0.5).astype(wdt))
+                    w64 = w.astype(np.float64)
+                    m, v = orc.meanvar_weighted(x, w, dim, bias)
+                    wm = (x64 * w64).sum(axis=dim, keepdims=True) / w64.sum(axis=dim, keepdims=True)
+                    want = ((x64 - wm) ** 2).sum(axis=dim) / (w64.sum(axis=dim) - (1 if bias == po.AF_VARIANCE_SAMPLE else 0))
+                    assert np.abs(m.reshape(-1) - wm.reshape(-1)).max() <= tol * scale * 4
+                    assert np.abs(v.reshape(-1) - want.reshape(-1)).max() <= tol * scale * scale * 16 * max(1.0, float(np.abs(want).max()) / (scale * scale))
+    with pytest.raises(po.AfArgError):
+        orc.meanvar_weighted(np.ones(4, np.float32), np.ones(4, np.float32), 4)
+    with pytest.raises(po.AfArgError):
+        orc.meanvar_weighted(np.ones(4, np.float32), np.ones(4, np.int32), 0)
