@@ -130,3 +130,11 @@ def test_reference_diff_large_dim(af):
         assert d1.dims[dim] == n - 1 and d2.dims[dim] == n - 2
         assert af.sum_all(d1) == 0.0 and af.sum_all(d2) == 0.0
         assert af.count_all(d1) == 0.0 and af.count_all(d2) == 0.0
+
+
+def test_reference_set_unique_snippets(af):
+    """Set.SNIPPET_setUniqueSorted / setUniqueSortedDesc (test/set.cpp:161-199)"""
+    from tests.golden import kat_stats as ks
+    for x, want in ks.SET_UNIQUE_SORTED:
+        got = af.set_unique(af.Array.from_numpy(x), True)
+        assert got.elements == want.size and got.to_numpy().reshape(-1).tolist() == want.tolist()

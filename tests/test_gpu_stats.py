@@ -328,3 +328,17 @@ def test_weighted_variance_along_dim(af, port_oracle):
     with pytest.raises(af.AfError) as ei:
         af._check(af.lib.af_var_weighted(ctypes.byref(af._vp()), g.handle, g.handle, ctypes.c_longlong(4)))
     assert ei.value.code == 202
+
+
+def test_var_known_answers(af):
+    """Var.AllCPPSmall / Medium / Large (test/var.cpp:52-116) on the CUDA path"""
+    from tests.golden import kat_stats as ks
+    for dt in (np.float32, np.float64, np.int32, np.uint32, np.int64, np.uint64, np.int16, np.uint16, np.int8, np.uint8, np.complex64,
+               np.complex128):
+        for dims in ks.VAR_CONST_DIMS:
+            g = af.Array.from_numpy(np.full(dims, ks.VAR_CONST_VALUE, dtype=dt, order="F"))
+            for bias in (po.AF_VARIANCE_POPULATION, po.AF_VARIANCE_SAMPLE):
+                assert abs(af.var_all(g, bias)) <= ks.VAR_TOL, (dt, dims, bias)
+        g = af.Array.from_numpy(ks.VAR_RAMP.astype(dt))
+        assert abs(af.var_all(g, po.AF_VARIANCE_POPULATION) - ks.VAR_RAMP_POPULATION) <= ks.VAR_TOL
+        assert abs(af.var_all(g, po.AF_VARIANCE_SAMPLE) - ks.VAR_RAMP_SAMPLE) <= ks.VAR_TOL

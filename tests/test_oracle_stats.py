@@ -177,3 +177,19 @@ def test_meanvar_weighted_restatement(port_oracle):
         orc.meanvar_weighted(np.ones(4, np.float32), np.ones(4, np.float32), 4)
     with pytest.raises(po.AfArgError):
         orc.meanvar_weighted(np.ones(4, np.float32), np.ones(4, np.int32), 0)
+
+
+def test_var_and_set_known_answers(port_oracle):
+    from tests.golden import kat_stats as ks
+    orc = port_oracle
+    for code in (po.F32, po.F64, po.S32, po.U32, po.S64, po.U64, po.S16, po.U16, po.S8, po.U8, po.C32, po.C64):
+        dt = po.NP_OF[code]
+        for dims in ks.VAR_CONST_DIMS[:2]:
+            x = np.full(dims, ks.VAR_CONST_VALUE, dtype=dt, order="F")
+            for bias in (po.AF_VARIANCE_POPULATION, po.AF_VARIANCE_SAMPLE):
+                assert abs(orc.var_all(x, bias)) <= ks.VAR_TOL
+        r = ks.VAR_RAMP.astype(dt)
+        assert abs(orc.var_all(r, po.AF_VARIANCE_POPULATION) - ks.VAR_RAMP_POPULATION) <= ks.VAR_TOL
+        assert abs(orc.var_all(r, po.AF_VARIANCE_SAMPLE) - ks.VAR_RAMP_SAMPLE) <= ks.VAR_TOL
+    for x, want in ks.SET_UNIQUE_SORTED:
+        assert orc.set_unique_sorted(x).tolist() == want.tolist()
