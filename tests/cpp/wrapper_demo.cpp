@@ -116,6 +116,13 @@ int main(int argc, char **argv) {
         dump<float>("meanvar_m.out", mv_m);
         dump<float>("meanvar_v.out", mv_v);
         dump<float>("cov.out", af::cov(z, z, AF_VARIANCE_SAMPLE));
+        // weighted forms (af_var_weighted, af_meanvar with weights, af_mean_weighted): weights = z * z + 1/2, built lazily
+        af::array wz = z * z + 0.5;
+        dump<float>("wvar_d0.out", af::var(z, wz, 0));
+        dump<float>("wmean_d1.out", af::mean(z, wz, 1));
+        af::meanvar(mv_m, mv_v, z, wz, AF_VARIANCE_SAMPLE, 1);
+        dump<float>("wmeanvar_m.out", mv_m);
+        dump<float>("wmeanvar_v.out", mv_v);
         double stats[4];
         stats[0] = af::mean<float>(z);
         stats[1] = af::var<float>(z, AF_VARIANCE_SAMPLE);

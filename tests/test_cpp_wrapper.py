@@ -147,6 +147,15 @@ def test_cpp_program_through_the_reference_wrapper(port_oracle):
         near("meanvar_m.out", z64.mean(0), 1e-4)
         near("meanvar_v.out", z64.var(0), 1e-3)
         near("cov.out", ((z64 - z64.mean()) ** 2).sum(0) / (rows - 1), 1e-3)
+        w32 = z * z + np.float32(0.5)
+        for dim, bias in ((0, po.AF_VARIANCE_POPULATION), (1, po.AF_VARIANCE_SAMPLE)):
+            om, ov = orc.meanvar_weighted(z, w32, dim, bias)
+            if dim == 0:
+                near("wvar_d0.out", ov, 1e-3)
+            else:
+                near("wmean_d1.out", om, 1e-4)
+                near("wmeanvar_m.out", om, 1e-4)
+                near("wmeanvar_v.out", ov, 1e-3 * max(1.0, float(np.abs(ov).max())))
         st = np.fromfile(os.path.join(d, "stats.out"), dtype=np.float64)
         assert abs(st[0] - z64.mean()) <= 1e-4 and abs(st[1] - z64.var(ddof=1)) <= 1e-3
         assert abs(st[2] - z64.std()) <= 1e-3 and abs(st[3] - 1.0) <= 1e-4
