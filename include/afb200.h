@@ -253,7 +253,8 @@ AFAPI af_err afcu_set_native_id(int nativeid);                                  
 /* ===================== statistics on the reduction path =====================
  * include/af/statistics.h:348-659, include/af/lapack.h:568.  One fused streaming pass per input (kernels/stats_*.cu);
  * floating-point results agree with the reference within 1e-5 (f32) / 1e-12 (f64) relative, not bit for bit.
- * The weighted forms return AF_ERR_NOT_SUPPORTED. */
+ * The weighted forms (real inputs; weights of the input's dims) are compositions of those passes; weighted statistics of
+ * complex / f16 inputs return AF_ERR_NOT_SUPPORTED. */
 AFAPI af_err af_mean(af_array *out, const af_array in, const dim_t dim);                                  /* mean.cpp:65 */
 AFAPI af_err af_mean_all(double *real, double *imag, const af_array in);                                  /* mean.cpp:151 */
 AFAPI af_err af_mean_weighted(af_array *out, const af_array in, const af_array weights, const dim_t dim);
