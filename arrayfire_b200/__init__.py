@@ -483,6 +483,13 @@ def flat(a):
     return Array(h, a._keepalive)
 
 
+def tile(a, x, y=1, z=1, w=1):
+    """af::tile (src/api/cpp/data.cpp; api/c/tile.cpp:82-90)"""
+    h = _vp()
+    _check(lib.af_tile(ctypes.byref(h), a.handle, ctypes.c_uint(x), ctypes.c_uint(y), ctypes.c_uint(z), ctypes.c_uint(w)))
+    return Array(h)
+
+
 # ---- scans (af::accum / scan / scanByKey default dim = 0, src/api/cpp/scan.cpp:15-33) --------------
 def accum(a, dim=0):
     h = _vp()
@@ -523,6 +530,13 @@ def _stat_dim(fn, a, dim, *extra):
 
 def mean(a, dim=-1):
     return _stat_dim(lib.af_mean, a, dim)
+
+
+def mean_weighted(a, weights, dim=-1):
+    """af::mean(in, weights, dim) (api/c/mean.cpp:95-149): a weights dim of 1 is repeated up to the input's"""
+    h = _vp()
+    _check(lib.af_mean_weighted(ctypes.byref(h), a.handle, weights.handle, ctypes.c_longlong(_fnsd(a, dim))))
+    return Array(h)
 
 
 def mean_all(a):

@@ -87,6 +87,32 @@ af_err af_moddims(af_array *out, const af_array in_h, const unsigned ndims, cons
     AFB_API_END
 }
 
+// af_tile (/root/reference/src/api/c/tile.cpp:41-90): the array repeated x / y / z / w times along dims 0..3 -- here because the
+// weighted mean broadcasts its weights with it (api/c/mean.cpp:112-124)
+af_err af_tile(af_array *out, const af_array in_h, const unsigned x, const unsigned y, const unsigned z, const unsigned w) {
+    AFB_API_BEGIN
+    AFB_ARG(0, out != nullptr);
+    Array *in = from_handle(in_h);
+    if (in->ndims() == 0) {                                  // tile.cpp:46
+        *out = retain(*in);
+        return AF_SUCCESS;
+    }
+    if (in->elements() <= 0) fail(AF_ERR_SIZE, "af_tile: the input holds no element");          // DIM_ASSERT(1, ...)
+    if ((dim_t)x * y * z * w <= 0) fail(AF_ERR_SIZE, "af_tile: every repeat count must be at least 1");   // DIM_ASSERT(2, ...)
+    check_same_device(*in);
+    const dim_t od[4] = {in->info.dims[0] * x, in->info.dims[1] * y, in->info.dims[2] * z, in->info.dims[3] * w};
+    Array *res = new_array(in->info.type, od);
+    try {
+        LaunchCtx c = ctx_for_active_device();
+        launch_tile(c, in->info.type, view_of(*in), od, res->data());
+    } catch (...) {
+        delete res;
+        throw;
+    }
+    *out = res;
+    AFB_API_END
+}
+
 af_err af_flat(af_array *out, const af_array in_h) {
     AFB_API_BEGIN
     AFB_ARG(0, out != nullptr);

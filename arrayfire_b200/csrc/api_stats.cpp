@@ -419,16 +419,30 @@ struct H {           // releases af_array temporaries
         if (e_ != AF_SUCCESS) return e_;     \
     } while (0)
 
-// x as the compute type (f32, or f64 for f64 / s64 / u64) and w as the same type; complex / f16 are not handled
-af_err weighted_operands(H &x, H &w, const af_array in, const af_array weights, int arg_w) {
-    AFB_API_BEGIN
-    Array *a = from_handle(in), *ww = from_handle(weights);
-    AFB_ARG(arg_w, ww->info.type == f32 || ww->info.type == f64);            // mean.cpp:105-110
-    const af_dtype t = a->info.type;
-    if (t == c32 || t == c64 || t == f16) fail(AF_ERR_NOT_SUPPORTED, "weighted statistics: complex and f16 inputs are not supported by libafb200");
-    for (int i = 0; i < 4; i++)
-        if (a->info.dims[i] != ww->info.dims[i]) fail(AF_ERR_NOT_SUPPORTED, "weighted statistics: the weights must have the dims of the input (no broadcast)");
-    AFB_API_END
+// x as the compute type (f32, or f64 for f64 / s64 / u64) and w as the same type; complex / f16 are not handled.
+// `wt` receives the weights tiled up to the dims of the input when `may_tile` (af_mean_weighted, mean.cpp:112-124: a
+// weights dim of 1 is repeated); the other weighted forms of the reference do not tile, nor do they here.
+af_err weighted_operands(H &wt, const af_array in, const af_array weights, int arg_w, bool may_tile = false) {
+    unsigned rep[4] = {1, 1, 1, 1};
+    bool tile = false;
+    {
+        AFB_API_BEGIN
+        Array *a = from_handle(in), *ww = from_handle(weights);
+        AFB_ARG(arg_w, ww->info.type == f32 || ww->info.type == f64);            // mean.cpp:105-110
+        const af_dtype t = a->info.type;
+        if (t == c32 || t == c64 || t == f16) fail(AF_ERR_NOT_SUPPORTED, "weighted statistics: complex and f16 inputs are not supported by libafb200");
+        for (int i = 0; i < 4; i++) {
+            if (a->info.dims[i] == ww->info.dims[i]) continue;
+            if (!may_tile) fail(AF_ERR_NOT_SUPPORTED, "weighted statistics: the weights must have the dims of the input (no broadcast)");
+            AFB_ARG(arg_w, ww->info.dims[i] == 1);                               // mean.cpp:118
+            rep[i] = (unsigned)a->info.dims[i];
+            tile = true;
+        }
+        }
+        catch (...) { return ::afb::current_exception_to_err(); }
+    }
+    if (tile) return af_tile(&wt.h, weights, rep[0], rep[1], rep[2], rep[3]);
+    return af_retain_array(&wt.h, weights);
 }
 af_err weighted_cast(H &x, H &w, const af_array in, const af_array weights) {
     af_dtype t;
@@ -448,9 +462,9 @@ af_err af_mean_weighted(af_array *out, const af_array in, const af_array weights
         }
         catch (...) { return ::afb::current_exception_to_err(); }
     }
-    H x, w, xw, num, den, q;
-    AFB_TRY(weighted_operands(x, w, in, weights, 2));
-    AFB_TRY(weighted_cast(x, w, in, weights));
+    H x, w, wt, xw, num, den, q;
+    AFB_TRY(weighted_operands(wt, in, weights, 2, true));
+    AFB_TRY(weighted_cast(x, w, in, wt.h));
     AFB_TRY(af_mul(&xw.h, x.h, w.h, false));
     AFB_TRY(af_sum(&num.h, xw.h, (int)dim));
     AFB_TRY(af_sum(&den.h, w.h, (int)dim));
@@ -468,8 +482,8 @@ af_err af_mean_all_weighted(double *real, double *imag, const af_array in, const
         }
         catch (...) { return ::afb::current_exception_to_err(); }
     }
-    H x, w, xw;
-    AFB_TRY(weighted_operands(x, w, in, weights, 3));
+    H x, w, wt, xw;
+    AFB_TRY(weighted_operands(wt, in, weights, 3));
     AFB_TRY(weighted_cast(x, w, in, weights));
     AFB_TRY(af_mul(&xw.h, x.h, w.h, false));
     double num = 0, den = 0, im = 0;
@@ -524,8 +538,8 @@ af_err af_var_weighted(af_array *out, const af_array in, const af_array weights,
 // so x is read twice (the moments, the weighted sum) and w twice (its sum, the weighted sum); everything after that runs on
 // the reduced arrays.
 static af_err meanvar_weighted(af_array *mean, af_array *var, const af_array in, const af_array weights, int bias, dim_t dim) {
-    H x, w, wm, m, v, wsum, d, d2, t, nn, t2, den, q, one;
-    AFB_TRY(weighted_operands(x, w, in, weights, 2));
+    H x, w, wt, wm, m, v, wsum, d, d2, t, nn, t2, den, q, one;
+    AFB_TRY(weighted_operands(wt, in, weights, 2));
     AFB_TRY(af_mean_weighted(&wm.h, in, weights, dim));
     AFB_TRY(moments_dim(&v.h, &m.h, true, in, BIAS_POPULATION, dim, false, false, 5));
     AFB_TRY(weighted_cast(x, w, in, weights));

@@ -24,7 +24,7 @@ AFB_STUB(af_bitnot)
 AFB_STUB(af_bitand) AFB_STUB(af_bitor) AFB_STUB(af_bitxor) AFB_STUB(af_bitshiftl) AFB_STUB(af_bitshiftr)
 AFB_STUB(af_real) AFB_STUB(af_imag) AFB_STUB(af_cplx) AFB_STUB(af_cplx2) AFB_STUB(af_conjg) 
 // data movement / generation (include/af/data.h, index.h)
-AFB_STUB(af_tile) AFB_STUB(af_reorder) AFB_STUB(af_join) AFB_STUB(af_join_many) AFB_STUB(af_shift) AFB_STUB(af_flip)
+AFB_STUB(af_reorder) AFB_STUB(af_join) AFB_STUB(af_join_many) AFB_STUB(af_shift) AFB_STUB(af_flip)
 AFB_STUB(af_lower) AFB_STUB(af_upper) AFB_STUB(af_pad) AFB_STUB(af_range) AFB_STUB(af_iota) AFB_STUB(af_identity)
 AFB_STUB(af_diag_create) AFB_STUB(af_diag_extract) AFB_STUB(af_lookup) AFB_STUB(af_assign_gen) AFB_STUB(af_assign_seq)
 AFB_STUB(af_select) AFB_STUB(af_select_scalar_l) AFB_STUB(af_select_scalar_r)

@@ -297,6 +297,7 @@ void launch_peer_exchange(const LaunchCtx &c, const void *payload, const unsigne
                           unsigned epoch, void *host_out, unsigned *host_flag);
 // dense copy of a strided view (same dtype), value fill, dtype cast (dense -> dense)
 void launch_copy_strided(const LaunchCtx &c, af_dtype t, const View &in, void *out);
+void launch_tile(const LaunchCtx &c, af_dtype t, const View &in, const dim_t odims[4], void *out);   // af_tile
 void launch_fill(const LaunchCtx &c, af_dtype t, void *out, dim_t n, double re, double im);
 bool launch_cast(const LaunchCtx &c, af_dtype ti, af_dtype to, const View &in, void *out);
 

@@ -36,6 +36,41 @@ void launch_copy_strided(const LaunchCtx &c, af_dtype t, const View &in, void *o
     post_launch_check("copy_strided_kernel");
 }
 
+// af_tile (/root/reference/src/api/c/tile.cpp:41-84, backend/common/tile.hpp): out(x, y, z, w) = in(x % d0, y % d1, z % d2, w % d3);
+// one thread per output element, consecutive threads along dim 0 (coalesced stores, loads coalesced within each repeat)
+template<typename W>
+__global__ void tile_kernel(const W *in, W *out, dim_t o0, dim_t o1, dim_t o2, dim_t n, dim_t d0, dim_t d1, dim_t d2, dim_t d3,
+                            dim_t s0, dim_t s1, dim_t s2, dim_t s3) {
+    for (dim_t i = (dim_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (dim_t)gridDim.x * blockDim.x) {
+        const dim_t x = i % o0, r = i / o0;
+        const dim_t y = r % o1, r2 = r / o1;
+        const dim_t z = r2 % o2, w = r2 / o2;
+        out[i] = in[(x % d0) * s0 + (y % d1) * s1 + (z % d2) * s2 + (w % d3) * s3];
+    }
+}
+
+void launch_tile(const LaunchCtx &c, af_dtype t, const View &in, const dim_t odims[4], void *out) {
+    const dim_t n = odims[0] * odims[1] * odims[2] * odims[3];
+    if (n == 0) return;
+    dim_t blocks = (n + 255) / 256;
+    const dim_t cap = (dim_t)c.sms * 16;
+    if (blocks > cap) blocks = cap;
+#define AFB_TILE(W)                                                                                                        \
+    tile_kernel<W><<<(unsigned)blocks, 256, 0, c.stream>>>((const W *)in.ptr, (W *)out, odims[0], odims[1], odims[2], n,    \
+                                                           in.dims[0], in.dims[1], in.dims[2], in.dims[3], in.strides[0],  \
+                                                           in.strides[1], in.strides[2], in.strides[3])
+    switch (dtype_size(t)) {
+        case 1: AFB_TILE(uchar); break;
+        case 2: AFB_TILE(ushort); break;
+        case 4: AFB_TILE(uint); break;
+        case 8: AFB_TILE(uintl); break;
+        default: AFB_TILE(double2); break;
+    }
+#undef AFB_TILE
+    note_launches(1);
+    post_launch_check("tile_kernel");
+}
+
 template<typename T> __global__ void fill_kernel(T *out, dim_t n, T v) {
     for (dim_t i = (dim_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (dim_t)gridDim.x * blockDim.x) out[i] = v;
 }

@@ -179,6 +179,8 @@ AFAPI af_err af_get_size_of(size_t *size, af_dtype type);
  * (src/api/cpp/array.cpp, data.cpp, index.cpp call these; api_extra.cpp) */
 AFAPI af_err af_moddims(af_array *out, const af_array in, const unsigned ndims, const dim_t *const dims); /* moddims.cpp:42 */
 AFAPI af_err af_flat(af_array *out, const af_array in);                                        /* moddims.cpp:84 */
+AFAPI af_err af_tile(af_array *out, const af_array in, const unsigned x, const unsigned y, const unsigned z,
+                     const unsigned w);                                                    /* tile.cpp:82 */
 AFAPI af_err af_cast(af_array *out, const af_array in, const af_dtype type);                   /* cast.cpp:34 */
 /* af_seq / span indexers only (views); array indexers return AF_ERR_NOT_SUPPORTED.  index.cpp:217 */
 AFAPI af_err af_index_gen(af_array *out, const af_array in, const dim_t ndims, const af_index_t *indices);

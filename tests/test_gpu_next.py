@@ -138,3 +138,43 @@ def test_reference_set_unique_snippets(af):
     for x, want in ks.SET_UNIQUE_SORTED:
         got = af.set_unique(af.Array.from_numpy(x), True)
         assert got.elements == want.size and got.to_numpy().reshape(-1).tolist() == want.tolist()
+
+
+def test_tile(af):
+    """af_tile (api/c/tile.cpp:41-90; test/tile.cpp): every dtype size, repeats along each dim, views; numpy's tile on the
+    Fortran-ordered array is the truth (pure data movement: bit-exact)"""
+    rng = np.random.default_rng(8600)
+    for dt in (np.uint8, np.int16, np.float32, np.float64, np.complex128, np.float16):
+        for shape, reps in [((5,), (3, 1, 1, 1)), ((5,), (1, 4, 1, 1)), ((7, 3), (2, 3, 1, 1)), ((4, 1, 3), (1, 5, 2, 2)),
+                            ((2, 3, 2, 2), (3, 1, 2, 1)), ((1000, 33), (1, 7, 1, 1)), ((1, 1), (100000, 3, 1, 1))]:
+            x = np.asfortranarray((rng.random(shape) * 100).astype(dt))
+            got = af.tile(af.Array.from_numpy(x), *reps)
+            x4 = x.reshape(po.dims4(shape), order="F")
+            want = np.tile(x4, reps)
+            assert got.dims == tuple(want.shape), (shape, reps)
+            assert got.to_numpy().reshape(want.shape, order="F").tobytes() == np.asfortranarray(want).tobytes(), (dt, shape, reps)
+    x = np.asfortranarray(rng.random((40, 30)).astype(np.float32))
+    sub = af.Array.from_numpy(x).index(af.seq(3, 20, 1), af.seq(5, 25, 2))
+    got = af.tile(sub, 2, 3)
+    want = np.tile(x[3:21, 5:26:2], (2, 3))
+    assert got.to_numpy().reshape(want.shape, order="F").tobytes() == np.asfortranarray(want).tobytes()
+    with pytest.raises(af.AfError) as ei:
+        af.tile(af.Array.from_numpy(x), 0, 1)
+    assert ei.value.code == 203   # AF_ERR_SIZE
+
+
+def test_weighted_mean_broadcasts_its_weights(af):
+    """af_mean_weighted repeats a weights dim of 1 up to the input's (api/c/mean.cpp:112-124); a mismatch that is not 1 is an
+    argument error (mean.cpp:118)"""
+    rng = np.random.default_rng(8601)
+    x = np.asfortranarray(rng.standard_normal((300, 17, 3)).astype(np.float32))
+    x64 = x.astype(np.float64)
+    for wshape, dim in (((300, 1, 1), 0), ((300, 1, 3), 0), ((1, 17, 1), 1), ((1, 1, 3), 2), ((300, 17, 1), 1)):
+        w = np.asfortranarray((rng.random(wshape) + 0.5).astype(np.float32))
+        wb = np.broadcast_to(w.astype(np.float64), x.shape)
+        got = af.mean_weighted(af.Array.from_numpy(x), af.Array.from_numpy(w), dim).to_numpy()
+        want = (x64 * wb).sum(axis=dim) / wb.sum(axis=dim)
+        assert np.abs(got.reshape(-1, order="F") - want.reshape(-1, order="F")).max() <= 1e-4, (wshape, dim)
+    with pytest.raises(af.AfError) as ei:
+        af.mean_weighted(af.Array.from_numpy(x), af.Array.from_numpy(np.ones((150, 17, 3), np.float32, order="F")), 0)
+    assert ei.value.code == 202
