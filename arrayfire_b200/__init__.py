@@ -634,7 +634,10 @@ def _operand(a, like):
     """a scalar becomes a (lazy) constant of `like`'s dims, typed as the C++ operators do (array op double)"""
     if isinstance(a, Array):
         return a
-    t = like.dtype if like.dtype in (f32, f64) else f32
+    if isinstance(a, int) and not isinstance(a, bool) and like.dtype in (s32, u32, s16, u16, s8, u8):
+        t = like.dtype if like.dtype == u32 else s32      # array op int: an s32 scalar (u32 against a u32 array), array.cpp implicit_dtype
+    else:
+        t = like.dtype if like.dtype in (f32, f64) else f32
     return constant(float(a), [int(d) for d in like.dims], t)
 
 

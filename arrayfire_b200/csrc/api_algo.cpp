@@ -151,6 +151,7 @@ af_err reduce_all_scalar(double *real, double *imag, const af_array in_h, Family
     {
         Array *lazy = peek_handle(in_h);
         if (lazy->expr && real != nullptr && lazy->elements() > 0 && !change_nan &&
+            (lazy->info.type == f32 || lazy->info.type == f64 || lazy->info.type == b8) &&   // a lazy INTEGER constant takes the evaluated path
             (op == OP_ADD || op == OP_NOTZERO || op == OP_MIN || op == OP_MAX || op == OP_OR || op == OP_AND)) {
             check_same_device(*lazy);
             *real = 0;

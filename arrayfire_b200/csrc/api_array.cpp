@@ -296,7 +296,8 @@ af_err af_constant(af_array *arr, const double val, const unsigned ndims, const 
     dim_t d[4];
     dims_from(ndims, dims, d);
     for (int i = 0; i < 4; i++) AFB_ARG(3, d[i] >= 0);
-    if ((type == f32 || type == f64 || type == b8) && d[0] * d[1] * d[2] * d[3] > 0) {
+    if ((type == f32 || type == f64 || type == b8 || type == s32 || type == u32 || type == s16 || type == u16 || type == s8 || type == u8) &&
+        d[0] * d[1] * d[2] * d[3] > 0) {
         // a ScalarNode, as in the reference (data.cpp:45-90): no memory until a consumer needs the values
         *arr = lazy_constant(type, d, val);
         return AF_SUCCESS;

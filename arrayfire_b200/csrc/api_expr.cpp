@@ -6,7 +6,7 @@
 // consumer evaluates the tree in one kernel; af_constant is a ScalarNode (no memory, src/api/c/data.cpp:45-90).  The
 // pi benchmark (examples/benchmarks/pi.cpp:28-31) is the shape this serves:  sum<float>(sqrt(x*x + y*y) < 1).
 // Scope: f32 / f64 / b8 operands of identical dims; arithmetic (+ - * /), comparisons, logical and / or / not, sqrt, abs,
-// min / max / pow.  Anything else returns AF_ERR_NOT_SUPPORTED (never a wrong result, never a CPU fallback).
+// min / max / pow; s32 / u32 / s16 / u16 / s8 / u8 operands in comparisons and logic (exact in the double interpreter).  Anything else returns AF_ERR_NOT_SUPPORTED (never a wrong result, never a CPU fallback).
 // Fused consumers: af_sum_all, af_count_all, af_min_all, af_max_all, af_any_true_all, af_all_true_all (api_algo.cpp);
 // every other entry point sees a normal array because from_handle() materialises the expression first.
 #include <cmath>
@@ -26,6 +26,7 @@ struct ExprNode {
     std::shared_ptr<Buffer> buf;             // leaf
     size_t offset_bytes = 0;
     double cst = 0.0;                        // constant
+    bool via_f32 = false;                    // integer leaf whose consumer works in f32: value rounded through float
     int nops = 1;                            // instructions of the flattened subtree
 };
 }  // namespace afb
@@ -43,6 +44,31 @@ struct Holder {
 };
 
 bool expr_type_ok(af_dtype t) { return t == f32 || t == f64 || t == b8; }
+// integer operands: comparisons / logic only (the value is exact in the double interpreter); no integer-valued node exists
+bool expr_int_ok(af_dtype t) { return t == s32 || t == u32 || t == s16 || t == u16 || t == s8 || t == u8; }
+bool is_signed_int(af_dtype t) { return t == s32 || t == s16 || t == s8; }
+int leaf_code(af_dtype t) {
+    switch (t) {
+        case f32: return 0;
+        case f64: return 1;
+        case s32: return 3;
+        case u32: return 4;
+        case s16: return 5;
+        case u16: return 6;
+        case u8: return 7;
+        default: return 2;   // b8, s8: one signed byte
+    }
+}
+// the reference's implicit() (src/api/c/implicit.cpp:20-45) restricted to the operand types of this interpreter
+af_dtype implicit_of(af_dtype l, af_dtype r) {
+    if (l == r) return l;
+    if (l == f64 || r == f64) return f64;
+    if (l == f32 || r == f32) return f32;
+    const af_dtype order[] = {u32, s32, u16, s16, u8, s8};
+    for (af_dtype t : order)
+        if (l == t || r == t) return t;
+    return b8;
+}
 
 // the node an operand contributes: its own expression, or a leaf over its (dense) buffer
 std::shared_ptr<ExprNode> node_of(Array &a, Holder &keep) {
@@ -66,16 +92,17 @@ int flatten(const ExprNode &n, ExprProg &p, int &nleaf, int &ncst, bool &dbl) {
     if (n.op == EX_LEAF) {
         const void *ptr = (const char *)n.buf->ptr + n.offset_bytes;
         int idx = -1;
+        const int lt = leaf_code(n.type) | (n.via_f32 ? 16 : 0);
         for (int i = 0; i < nleaf; i++)
-            if (p.leaf[i] == ptr) idx = i;
+            if (p.leaf[i] == ptr && p.leaf_type[i] == lt) idx = i;
         if (idx < 0) {
             if (nleaf >= kExprMaxLeaves) fail(AF_ERR_INTERNAL, "expression has too many operands");
             idx = nleaf++;
             p.leaf[idx] = ptr;
-            p.leaf_type[idx] = n.type == f32 ? 0 : (n.type == f64 ? 1 : 2);
+            p.leaf_type[idx] = lt;
             if (reinterpret_cast<uintptr_t>(ptr) & 15) p.aligned = 0;
         }
-        if (n.type == f64) dbl = true;
+        if (n.type == f64 || lt >= 3) dbl = true;
         p.op[p.n] = EX_LEAF;
         p.arg[p.n++] = (unsigned char)idx;
         return 0;
@@ -89,7 +116,7 @@ int flatten(const ExprNode &n, ExprProg &p, int &nleaf, int &ncst, bool &dbl) {
             idx = ncst++;
             p.cst[idx] = n.cst;
         }
-        if (n.type == f64) dbl = true;
+        if (n.type == f64 || expr_int_ok(n.type)) dbl = true;
         p.op[p.n] = EX_CONST;
         p.arg[p.n++] = (unsigned char)idx;
         return 0;
@@ -103,7 +130,7 @@ int flatten(const ExprNode &n, ExprProg &p, int &nleaf, int &ncst, bool &dbl) {
             idx = ncst++;
             p.cst[idx] = c.cst;
         }
-        if (c.type == f64) dbl = true;
+        if (c.type == f64 || expr_int_ok(c.type)) dbl = true;
         return idx;
     };
     int depth, flags = 0, arg = 0;
@@ -188,8 +215,18 @@ af_err binary(af_array *out, const af_array lhs_h, const af_array rhs_h, int op,
     for (int i = 0; i < 4; i++)
         if (l->info.dims[i] != r->info.dims[i])
             fail(AF_ERR_NOT_SUPPORTED, "%s: operands must have identical dims (batch / broadcast is not supported by libafb200)", name);
-    if (!expr_type_ok(l->info.type) || !expr_type_ok(r->info.type))
-        fail(AF_ERR_NOT_SUPPORTED, "%s: libafb200 evaluates element-wise expressions over f32 / f64 / b8 operands only", name);
+    const af_dtype tl = l->info.type, tr = r->info.type;
+    const bool ints = expr_int_ok(tl) || expr_int_ok(tr);
+    if (!(expr_type_ok(tl) || expr_int_ok(tl)) || !(expr_type_ok(tr) || expr_int_ok(tr)))
+        fail(AF_ERR_NOT_SUPPORTED, "%s: libafb200 evaluates element-wise expressions over f32 / f64 / b8 operands (and 8- to 32-bit integers in comparisons) only", name);
+    const af_dtype imp = implicit_of(tl, tr);
+    if (ints) {
+        if (kind == K_ARITH)
+            fail(AF_ERR_NOT_SUPPORTED, "%s: integer operands are supported in comparisons and logical operations only (af_cast them for arithmetic)", name);
+        // the reference compares in implicit(l, r): an unsigned result type would wrap a signed operand's negatives
+        if ((imp == u32 || imp == u16 || imp == u8) && (is_signed_int(tl) || is_signed_int(tr)))
+            fail(AF_ERR_NOT_SUPPORTED, "%s: mixed signed / unsigned integer operands are not supported", name);
+    }
     check_same_device(*l);
     check_same_device(*r);
     af_dtype to;
@@ -202,7 +239,15 @@ af_err binary(af_array *out, const af_array lhs_h, const af_array rhs_h, int op,
     Holder kl, kr;
     auto n = std::make_shared<ExprNode>();
     n->type = to;
-    n->kid[0] = bounded(node_of(*l, kl), *l);
+    // an s32 / u32 operand meeting an f32 one is cast to float by the reference before the comparison
+    auto adapt = [&](std::shared_ptr<ExprNode> k, af_dtype own) {
+        if (!(imp == f32 && (own == s32 || own == u32))) return k;
+        auto c = std::make_shared<ExprNode>(*k);
+        if (c->op == EX_LEAF) c->via_f32 = true;
+        else if (c->op == EX_CONST) c->cst = (double)(float)c->cst;
+        return c;
+    };
+    n->kid[0] = adapt(bounded(node_of(*l, kl), *l), tl);
     // x * x of the SAME operand (same handle, or the same buffer region): one load and a square
     const bool same = (l == r) || (l->expr && l->expr == r->expr) ||
                       (!l->expr && !r->expr && l->buf == r->buf && l->info.offset == r->info.offset && l->is_linear() && r->is_linear());
@@ -211,7 +256,7 @@ af_err binary(af_array *out, const af_array lhs_h, const af_array rhs_h, int op,
         n->nops = n->kid[0]->nops + 1;
     } else {
         n->op = op;
-        n->kid[1] = bounded(node_of(*r, kr), *r);
+        n->kid[1] = adapt(bounded(node_of(*r, kr), *r), tr);
         n->nops = n->kid[0]->nops + n->kid[1]->nops + 1;
     }
     *out = lazy_array(*l, to, n);
@@ -222,7 +267,7 @@ af_err unary(af_array *out, const af_array in_h, int op, bool to_bool, const cha
     AFB_API_BEGIN
     AFB_ARG(0, out != nullptr);
     Array *in = peek_handle(in_h);
-    if (!expr_type_ok(in->info.type) || (!to_bool && in->info.type == b8))
+    if (!(expr_type_ok(in->info.type) || (to_bool && expr_int_ok(in->info.type))) || (!to_bool && in->info.type == b8))
         fail(AF_ERR_NOT_SUPPORTED, "%s: libafb200 evaluates this function over f32 / f64 operands only", name);
     check_same_device(*in);
     Holder k;
@@ -250,7 +295,8 @@ void materialize(Array &a) {
     if (n > 0) {
         OpLock lk(a.device());
         LaunchCtx c = ctx_for_active_device();
-        launch_expr_eval(c, p, dbl, buf->ptr, t == f32 ? 0 : (t == f64 ? 1 : 2), n);
+        if (expr_int_ok(t)) launch_fill(c, t, buf->ptr, n, root->cst, 0.0);   // the only integer-valued node is a constant
+        else launch_expr_eval(c, p, dbl, buf->ptr, t == f32 ? 0 : (t == f64 ? 1 : 2), n);
     }
     a.buf = buf;
     a.info.offset = 0;
@@ -258,7 +304,7 @@ void materialize(Array &a) {
     a.expr.reset();
 }
 
-// a lazy constant (af_constant of f32 / f64 / b8): no memory until somebody needs the values
+// a lazy constant (af_constant of f32 / f64 / b8 and the 8- to 32-bit integers): no memory until somebody needs the values
 Array *lazy_constant(af_dtype type, const dim_t dims[4], double val) {
     Array *a = new_array(type, (const dim_t[4]){0, 1, 1, 1});   // a handle with this device's identity, no payload
     for (int i = 0; i < 4; i++) a->info.dims[i] = dims[i];
@@ -267,7 +313,17 @@ Array *lazy_constant(af_dtype type, const dim_t dims[4], double val) {
     auto n = std::make_shared<ExprNode>();
     n->op = EX_CONST;
     n->type = type;
-    n->cst = type == b8 ? (val != 0.0 ? 1.0 : 0.0) : (type == f32 ? (double)(float)val : val);
+    switch (type) {      // the value the stored type holds (launch_fill's conversions)
+        case b8: n->cst = val != 0.0 ? 1.0 : 0.0; break;
+        case f32: n->cst = (double)(float)val; break;
+        case s32: n->cst = (double)(int)val; break;
+        case u32: n->cst = (double)(unsigned int)val; break;
+        case s16: n->cst = (double)(short)val; break;
+        case u16: n->cst = (double)(unsigned short)val; break;
+        case s8: n->cst = (double)(signed char)val; break;
+        case u8: n->cst = (double)(unsigned char)val; break;
+        default: n->cst = val; break;
+    }
     a->expr = n;
     return a;
 }

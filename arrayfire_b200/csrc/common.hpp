@@ -274,7 +274,7 @@ struct ExprProg {                 // a postfix program over dense, equally shape
     int depth;                    // value-stack entries needed besides the register-resident top
     unsigned char op[kExprMaxOps], arg[kExprMaxOps];
     const void *leaf[kExprMaxLeaves];
-    int leaf_type[kExprMaxLeaves];   // 0 f32, 1 f64, 2 b8
+    int leaf_type[kExprMaxLeaves];   // 0 f32, 1 f64, 2 b8 / s8, 3 s32, 4 u32, 5 s16, 6 u16, 7 u8 (3.. : double interpreter only); +16: through float
     double cst[kExprMaxConsts];
     int aligned;                  // every operand is 16-byte aligned
 };

@@ -29,11 +29,44 @@ template<typename Tc> struct ExprW {
 struct alignas(16) ExprVec { unsigned int w[4]; };
 inline size_t expr_stack_bytes(int depth) { return (size_t)(depth < 1 ? 1 : depth) * kExprChunks * kExprThreads * sizeof(ExprVec); }
 
+// integer operands (leaf types 3.. of ExprProg::leaf_type): only the double interpreter carries them -- every 8- / 16- / 32-bit
+// integer is exact in f64, so comparisons and logic on them give the reference's answers bit for bit; flag 16 rounds the
+// value through float first (an s32 / u32 operand compared with an f32 one: the reference casts it to float, implicit.cpp:20-45)
+AFB_DI void expr_load_int(const void *base, int t, dim_t blk, dim_t n, bool whole, double (&v)[ExprW<double>::value]) {
+    constexpr int C = ExprW<double>::C;
+    const int bt = t & 15, tid = threadIdx.x;
+    const bool via_float = (t & 16) != 0;
+#pragma unroll
+    for (int q = 0; q < kExprChunks; q++) {
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            const dim_t i = blk + ((dim_t)q * kExprThreads + tid) * C + k;
+            double x = 0.0;
+            if (whole || i < n) {
+                switch (bt) {
+                    case 3: x = (double)__ldg((const int *)base + i); break;
+                    case 4: x = (double)__ldg((const unsigned int *)base + i); break;
+                    case 5: x = (double)__ldg((const short *)base + i); break;
+                    case 6: x = (double)__ldg((const unsigned short *)base + i); break;
+                    default: x = (double)__ldg((const unsigned char *)base + i); break;   // 7: u8 (s8 shares the b8 path)
+                }
+            }
+            v[q * C + k] = via_float ? (double)(float)x : x;
+        }
+    }
+}
+
 template<typename Tc> AFB_DI void expr_load(const ExprProg &p, int leaf, dim_t blk, dim_t n, bool whole, Tc (&v)[ExprW<Tc>::value]) {
     constexpr int C = ExprW<Tc>::C;
     const void *base = p.leaf[leaf];
     const int t = p.leaf_type[leaf];
     const int tid = threadIdx.x;
+    if constexpr (sizeof(Tc) == 8) {
+        if (t >= 3) {
+            expr_load_int(base, t, blk, n, whole, v);
+            return;
+        }
+    }
     if (whole && p.aligned) {
         if (t == 0) {
             const float *f = (const float *)base + blk + (dim_t)tid * C;

@@ -291,8 +291,9 @@ AFAPI af_err af_set_unique(af_array *out, const af_array in, const bool is_sorte
  * whole-array reduction (af_sum_all, af_count_all, af_min_all, af_max_all, af_any_true_all, af_all_true_all) that consumes
  * one interprets the expression in its load path -- sum<float>(sqrt(x*x + y*y) < 1) of examples/benchmarks/pi.cpp streams x
  * and y once and writes nothing.  Any other consumer evaluates the expression into an array first.  f32 / f64 / b8 operands
- * of identical dims (`batch` is ignored); everything else returns AF_ERR_NOT_SUPPORTED.  af_constant of these types is
- * lazy as well (no memory until needed). */
+ * of identical dims (`batch` is ignored); s32 / u32 / s16 / u16 / s8 / u8 operands in comparisons and logical operations
+ * (compared in the reference's implicit() type, exactly); everything else returns AF_ERR_NOT_SUPPORTED.  af_constant of
+ * these types is lazy as well (no memory until needed). */
 AFAPI af_err af_add(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
 AFAPI af_err af_sub(af_array *out, const af_array lhs, const af_array rhs, const bool batch);
 AFAPI af_err af_mul(af_array *out, const af_array lhs, const af_array rhs, const bool batch);

@@ -85,3 +85,57 @@ def test_lazy_constant_and_limits(af):
     with pytest.raises(af.AfError) as ei:      # no broadcasting
         af.add(af.Array.from_numpy(np.ones(4, np.float32)), af.Array.from_numpy(np.ones(5, np.float32)))
     assert ei.value.code == 301
+
+
+def test_integer_operands_in_comparisons(af):
+    """8- to 32-bit integer operands in comparisons / logic (the reference compares in implicit(l, r), api/c/implicit.cpp:20-45,
+    binary.cpp): exact in the double interpreter, fused into count / sum / any / all, and feeding af_where"""
+    rng = np.random.default_rng(99)
+    n = 3 * (1 << 18) + 11
+    for dt in (np.int32, np.uint32, np.int16, np.uint16, np.int8, np.uint8):
+        info = np.iinfo(dt)
+        x = rng.integers(max(info.min, -40), min(info.max, 40), n, endpoint=True).astype(dt)
+        y = rng.integers(max(info.min, -40), min(info.max, 40), n, endpoint=True).astype(dt)
+        x[:8] = [info.min, info.max, 0, 1, info.min, info.max, 3, 3]
+        y[:8] = [info.max, info.min, 0, 1, info.min, info.max, 3, 4]
+        gx, gy = af.Array.from_numpy(x), af.Array.from_numpy(y)
+        af.launch_count(reset=True)
+        e = af.eq(gx, 3)
+        assert af.launch_count() == 0
+        assert af.count_all(e) == int(np.count_nonzero(x == 3)) and af.launch_count() == 1
+        for fn, ref in ((af.lt, np.less), (af.gt, np.greater), (af.le, np.less_equal), (af.ge, np.greater_equal), (af.eq, np.equal),
+                        (af.neq, np.not_equal)):
+            got = fn(gx, gy)
+            assert got.dtype == af.b8
+            assert af.sum_all(got) == int(np.count_nonzero(ref(x, y))), (dt, fn)
+            assert got.to_numpy().reshape(-1).astype(bool).tobytes() == ref(x, y).tobytes(), (dt, fn)
+        assert af.count_all(af.logical_and(gx, gy)) == int(np.count_nonzero((x != 0) & (y != 0)))
+        assert af.count_all(af.logical_or(gx, gy)) == int(np.count_nonzero((x != 0) | (y != 0)))
+        assert af.count_all(af.logical_not(gx)) == int(np.count_nonzero(x == 0))
+        assert af.any_true_all(af.gt(gx, 39)) == bool((x > 39).any()) and bool(af.all_true_all(af.ge(gx, int(info.min))))
+        hits = af.where(af.logical_and(af.ge(gx, 2), af.lt(gx, 5)))
+        assert hits.to_numpy().reshape(-1).tobytes() == np.flatnonzero((x >= 2) & (x < 5)).astype(np.uint32).tobytes()
+    # s32 / u32 against f32: the integer is rounded to float first (16777217 == 16777216.0f); against f64 it is exact
+    xi = np.asarray([16777217, 16777216, -16777217, 5, 2147483647, -7], np.int32)
+    yf = np.asarray([16777216, 16777216, -16777216, 5.5, 2147483648.0, -7], np.float32)
+    gi, gf, gd = af.Array.from_numpy(xi), af.Array.from_numpy(yf), af.Array.from_numpy(yf.astype(np.float64))
+    assert af.eq(gi, gf).to_numpy().reshape(-1).astype(bool).tolist() == (xi.astype(np.float32) == yf).tolist()
+    assert af.lt(gf, gi).to_numpy().reshape(-1).astype(bool).tolist() == (yf < xi.astype(np.float32)).tolist()
+    assert af.eq(gi, gd).to_numpy().reshape(-1).astype(bool).tolist() == (xi.astype(np.float64) == yf.astype(np.float64)).tolist()
+    assert af.gt(gi, 5.5).to_numpy().reshape(-1).astype(bool).tolist() == (xi.astype(np.float32) > np.float32(5.5)).tolist()
+    # narrower signed against wider signed; b8 against an integer
+    s16 = np.asarray([-3, 7, 100, -32768], np.int16)
+    s32 = np.asarray([-3, 8, 99, -32769], np.int32)
+    assert af.le(af.Array.from_numpy(s16), af.Array.from_numpy(s32)).to_numpy().reshape(-1).astype(bool).tolist() == (s16 <= s32).tolist()
+    flags = af.gt(af.Array.from_numpy(s16), 0)
+    assert af.eq(flags, af.Array.from_numpy(np.asarray([0, 1, 1, 0], np.int32))).to_numpy().reshape(-1).astype(bool).all()
+    # lazy integer constants evaluate to what the stored type holds
+    c = af.constant(5, (1000, 3), af.s32)
+    assert c.dtype == af.s32 and af.sum_all(c) == 15000.0 and int(c.to_numpy().reshape(-1)[77]) == 5
+    assert int(af.constant(200, (10,), af.u8).to_numpy().reshape(-1)[0]) == 200
+    # outside the supported set: integer arithmetic, mixed signedness (the reference would wrap the negatives), 64-bit integers
+    for a, b, fn in ((xi, xi, af.mul), (np.asarray([1], np.int32), np.asarray([1], np.uint32), af.lt),
+                     (np.asarray([1], np.int64), np.asarray([1], np.int64), af.eq)):
+        with pytest.raises(af.AfError) as ei:
+            fn(af.Array.from_numpy(a), af.Array.from_numpy(b))
+        assert ei.value.code == 301
