@@ -97,6 +97,12 @@ int main(int argc, char **argv) {
         // where / count on a byte mask, and on a sub-array view (indices relative to the view)
         dump<unsigned>("where_m.out", af::where(m));
         dump<unsigned>("where_view.out", af::where(x(af::seq(1, (double)rows - 2), af::seq(1, (double)cols - 1))));
+        // integer keys through af::array's comparison operators (array == int -> an s32 constant, array.cpp): lazy, exact
+        dump<unsigned>("where_k3.out", af::where(k == 3));
+        double kc[2];
+        kc[0] = af::count<unsigned>(k >= 2 && k < 5);
+        kc[1] = af::sum<float>(k > x);            // s32 against f32: compared in float, NaN compares false
+        dump_bytes("kcounts.out", kc, sizeof(kc));
         // sub-array + flat + moddims feeding the path
         af::array sub = x(af::seq(2, (double)rows - 1), af::span);
         dump<float>("sub_sum_d0.out", af::sum(sub, 0));

@@ -128,6 +128,11 @@ def test_cpp_program_through_the_reference_wrapper(port_oracle):
         same("sbk_min_incl.out", np.float32, orc.scan_by_key(k, x, 0, po.AF_BINARY_MIN, True)[1], po.F32)
         same("where_m.out", np.uint32, orc.where(m), po.U32)
         same("where_view.out", np.uint32, orc.where(x[1:rows - 1, 1:cols]), po.U32)
+        same("where_k3.out", np.uint32, orc.where((k == 3).astype(np.int8)), po.U32)
+        kc = np.fromfile(os.path.join(d, "kcounts.out"), dtype=np.float64)
+        assert kc[0] == float(np.count_nonzero((k >= 2) & (k < 5)))
+        with np.errstate(invalid="ignore"):
+            assert kc[1] == float(np.count_nonzero(k.astype(np.float32) > x))
         sub = x[2:rows, :]
         same("sub_sum_d0.out", np.float32, orc.sum(sub, 0)[1], po.F32)
         same("flat_accum.out", np.float32, orc.accum(np.asfortranarray(sub).reshape(-1, order="F"), 0)[1], po.F32)
