@@ -127,3 +127,40 @@ def test_prototypes_match_the_reference_headers():
             assert sig == ref[name], (name, sig, ref[name])
         checked += 1
     assert checked >= 140
+
+
+def _enum_values(text):
+    """{enumerator: value} of every `typedef enum { ... }` of a header (C rules: previous + 1 unless assigned)"""
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    out = {}
+    for body in re.findall(r"typedef\s+enum\s*\w*\s*\{(.*?)\}", text, flags=re.S):
+        val = -1
+        for item in body.split(","):
+            item = re.sub(r"#(if|endif|else)[^\n]*\n?", "", item.strip() + "\n").strip()
+            if not item:
+                continue
+            m = re.match(r"^(\w+)\s*(?:=\s*(.+))?$", item, flags=re.S)
+            assert m, item
+            if m.group(2) is not None:
+                try:
+                    val = int(m.group(2).strip(), 0)
+                except ValueError:
+                    val = eval(m.group(2).strip(), {}, dict(out))   # e.g. AF_BACKEND_CUDA = 2 written via another enumerator
+            else:
+                val += 1
+            out[m.group(1)] = val
+    return out
+
+
+def test_enum_values_match_the_reference_header():
+    """af_err codes, af_dtype, af_binary_op, af_var_bias, af_norm_type, af_backend ...: same names, same values as
+    /root/reference/include/af/defines.h (a caller compiled against the reference's headers passes these integers)"""
+    ref_hdr = "/root/reference/include/af/defines.h"
+    if not os.path.isfile(ref_hdr):
+        pytest.skip("/root/reference is not present")
+    ours, ref = _enum_values(open(HDR).read()), _enum_values(open(ref_hdr).read())
+    assert len(ours) >= 50
+    for name, value in ours.items():
+        assert name in ref, name
+        assert ref[name] == value, (name, value, ref[name])
