@@ -164,3 +164,17 @@ def test_enum_values_match_the_reference_header():
     for name, value in ours.items():
         assert name in ref, name
         assert ref[name] == value, (name, value, ref[name])
+
+
+def test_python_mirror_and_oracle_use_the_header_values(lib):
+    """the ctypes mirror (arrayfire_b200) and the oracle's Python front (oracle/pyoracle.py) spell af_dtype / af_binary_op /
+    af_var_bias / af_norm_type with the integers of include/afb200.h"""
+    import arrayfire_b200 as af
+    from oracle import pyoracle as po
+    e = _enum_values(open(HDR).read())
+    for n in ("f32", "c32", "f64", "c64", "b8", "s32", "u32", "u8", "s64", "u64", "s16", "u16", "f16", "s8"):
+        assert getattr(af, n) == e[n] and getattr(po, n.upper()) == e[n], n
+    for n in ("AF_BINARY_ADD", "AF_BINARY_MUL", "AF_BINARY_MIN", "AF_BINARY_MAX", "AF_VARIANCE_DEFAULT", "AF_VARIANCE_SAMPLE",
+              "AF_VARIANCE_POPULATION", "AF_NORM_VECTOR_1", "AF_NORM_VECTOR_INF", "AF_NORM_VECTOR_2", "AF_NORM_VECTOR_P",
+              "AF_NORM_MATRIX_1", "AF_NORM_MATRIX_INF", "AF_NORM_MATRIX_2", "AF_NORM_MATRIX_L_PQ"):
+        assert getattr(af, n) == e[n] and getattr(po, n) == e[n], n
