@@ -66,6 +66,14 @@ def test_error_codes_without_a_device(lib):
     lib.af_get_last_error(ctypes.byref(msg), ctypes.byref(n))     # fetched + cleared
     assert n.value == 0
     assert lib.af_err_to_string(204) == b"Function does not support this data type"
+    # the entry points beyond the north-star path validate their arguments the same way (AF_ERR_ARG before any device work)
+    m = ctypes.c_void_p()
+    assert lib.af_tile(ctypes.byref(out), None, 1, 1, 1, 1) == 202 and lib.af_tile(None, None, 1, 1, 1, 1) == 202
+    assert lib.af_var_weighted(ctypes.byref(out), None, None, ctypes.c_longlong(4)) == 202      # var.cpp:267 dim in 0..3
+    assert lib.af_var_weighted(None, None, None, ctypes.c_longlong(0)) == 202
+    assert lib.af_mean_weighted(ctypes.byref(out), None, None, ctypes.c_longlong(-1)) == 202    # mean.cpp:98
+    assert lib.af_meanvar(ctypes.byref(m), ctypes.byref(out), None, None, 2, ctypes.c_longlong(0)) == 202
+    assert lib.af_eq(ctypes.byref(out), None, None, False) == 202
     maj, mi, pa = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     assert lib.af_get_version(ctypes.byref(maj), ctypes.byref(mi), ctypes.byref(pa)) == 0 and (maj.value, mi.value) == (3, 10)
 
